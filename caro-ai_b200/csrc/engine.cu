@@ -1,0 +1,375 @@
+// Host side of the engine: workspace carving, kernel dispatch per game family, C ABI.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/caro_b200.h"
+#include "common_host.h"
+#include "engine_kernels.cuh"
+#include "net.h"
+
+namespace caro {
+
+struct Region {
+  std::string name;
+  size_t offset, bytes;
+  int elem;
+  int64_t dims[4];
+};
+
+struct Carver {
+  size_t cur = 0;
+  std::vector<Region> regions;
+  size_t add(const char* name, size_t elem, int64_t d0, int64_t d1 = 0, int64_t d2 = 0, int64_t d3 = 0) {
+    size_t count = (size_t)d0 * (size_t)(d1 ? d1 : 1) * (size_t)(d2 ? d2 : 1) * (size_t)(d3 ? d3 : 1);
+    cur = (cur + 255) & ~(size_t)255;
+    Region r{name, cur, count * elem, (int)elem, {d0, d1, d2, d3}};
+    regions.push_back(r);
+    cur += count * elem;
+    return r.offset;
+  }
+};
+
+static int round_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace caro
+
+using namespace caro;
+
+struct caro_engine {
+  caro_engine_config cfg;
+  Dims dm;
+  SearchParams sp;
+  int max_plies;
+  size_t board_bytes;
+  char* ws;
+  size_t ws_bytes;
+  Carver carve;
+  View<C4Board> v_c4;
+  View<MnkBoard> v_mnk;
+  MnkRules mnk;
+};
+
+namespace {
+
+template <class Board>
+void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
+  const int64_t trees = (int64_t)dm.G * dm.tpg;
+  const int64_t nodes = trees * dm.node_cap;
+  const int64_t GB = (int64_t)dm.G * dm.B;
+  auto P = [&](size_t off) { return base ? base + off : (char*)nullptr; };
+#define CARVE(field, name, type, ...) v->field = reinterpret_cast<type*>(P(c.add(name, sizeof(type), __VA_ARGS__)))
+  CARVE(N, "N", int32_t, nodes, dm.Apad);
+  CARVE(W, "W", float, nodes, dm.Apad);
+  CARVE(Q, "Q", float, nodes, dm.Apad);
+  CARVE(P, "P", float, nodes, dm.Apad);
+  CARVE(flags, "flags", uint32_t, nodes, dm.FW);
+  CARVE(key_hi, "key_hi", uint64_t, nodes);
+  CARVE(node_board, "node_board", Board, nodes);
+  CARVE(node_player, "node_player", uint8_t, nodes);
+  CARVE(ht, "hash", HashSlot, trees, dm.hash_cap);
+  CARVE(node_count, "node_count", int32_t, trees);
+  CARVE(tree_gen, "tree_gen", uint32_t, trees);
+  CARVE(root_board, "root_board", Board, dm.G);
+  CARVE(root_player, "root_player", uint8_t, dm.G);
+  CARVE(status, "status", uint8_t, dm.G);
+  CARVE(ply, "ply", int32_t, dm.G);
+  CARVE(result, "result", int32_t, dm.G);
+  CARVE(uid, "uid", uint64_t, dm.G);
+  CARVE(played, "played", uint32_t, dm.G);
+  CARVE(hist_board, "hist_board", Board, dm.G, dm.max_plies);
+  CARVE(hist_player, "hist_player", uint8_t, dm.G, dm.max_plies);
+  CARVE(hist_pi, "hist_pi", float, dm.G, dm.max_plies, dm.A);
+  CARVE(d_kind, "desc_kind", uint8_t, dm.G, dm.B);
+  CARVE(d_value, "desc_value", float, dm.G, dm.B);
+  CARVE(d_board, "desc_board", Board, dm.G, dm.B);
+  CARVE(d_player, "desc_player", uint8_t, dm.G, dm.B);
+  CARVE(d_key_lo, "desc_key_lo", uint64_t, dm.G, dm.B);
+  CARVE(d_key_hi, "desc_key_hi", uint64_t, dm.G, dm.B);
+  CARVE(d_path_len, "desc_path_len", int32_t, dm.G, dm.B);
+  CARVE(d_path_node, "desc_path_node", int32_t, dm.G, dm.B, dm.max_depth);
+  CARVE(d_path_action, "desc_path_action", uint8_t, dm.G, dm.B, dm.max_depth);
+  CARVE(d_slot, "desc_slot", int32_t, dm.G, dm.B);
+  CARVE(q_len, "queue_len", int32_t, dm.G);
+  CARVE(q_order, "queue_order", uint8_t, dm.G, dm.B);
+  CARVE(leaf_board, "leaf_board", Board, GB);
+  CARVE(leaf_player, "leaf_player", uint8_t, GB);
+  CARVE(leaf_count, "leaf_count", int32_t, 1);
+  CARVE(probs, "probs", float, GB, dm.A);
+  CARVE(values, "values", float, GB);
+  const int64_t rc = dm.replay_cap > 0 ? dm.replay_cap : 1;
+  CARVE(rp_board, "replay_board", Board, rc);
+  CARVE(rp_player, "replay_player", uint8_t, rc);
+  CARVE(rp_pi, "replay_pi", float, rc, dm.A);
+  CARVE(rp_z, "replay_z", float, rc);
+  CARVE(rp_cursor, "replay_cursor", unsigned long long, 1);
+  CARVE(ctr, "counters", unsigned long long, CTR_COUNT);
+#undef CARVE
+}
+
+int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
+  if (!cfg) return caro_fail(CARO_E_ARG, "null config");
+  if (cfg->games <= 0 || cfg->node_capacity <= 0) return caro_fail(CARO_E_ARG, "games and node_capacity must be positive");
+  if (cfg->trees_per_game != 1 && cfg->trees_per_game != 2) return caro_fail(CARO_E_ARG, "trees_per_game must be 1 or 2");
+  if (cfg->max_batch <= 0 || cfg->max_batch > 64) return caro_fail(CARO_E_ARG, "max_batch must be in 1..64");
+  int A, plies;
+  if (cfg->game == CARO_GAME_CONNECT4) {
+    A = 7;
+    plies = 42;
+  } else if (cfg->game == CARO_GAME_MNK) {
+    if (cfg->n < 2 || cfg->n > 15 || cfg->k < 2 || cfg->k > cfg->n) return caro_fail(CARO_E_ARG, "m,n,k needs 2 <= k <= n <= 15");
+    A = cfg->n * cfg->n;
+    plies = A;
+  } else {
+    return caro_fail(CARO_E_ARG, "unknown game");
+  }
+  dm->G = cfg->games;
+  dm->tpg = cfg->trees_per_game;
+  dm->B = cfg->max_batch;
+  dm->A = A;
+  dm->Apad = (A + 7) & ~7;
+  dm->FW = (A + 31) / 32;
+  dm->node_cap = cfg->node_capacity;
+  dm->hash_cap = round_pow2(2 * cfg->node_capacity);
+  dm->max_depth = plies;
+  dm->max_plies = plies;
+  dm->replay_cap = cfg->replay_capacity;
+  *max_plies = plies;
+  return CARO_OK;
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// group width / actions per lane for the select kernel
+template <class R, class Board>
+int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const SearchParams& sp, int batch, int mb,
+                  const double* noise, double* noise_out, cudaStream_t st) {
+  const long long groups = (long long)dm.G * batch;
+  auto grid = [&](int gw) { return (unsigned)((groups * gw + 255) / 256); };
+  const int A = dm.A;
+  if (A <= 8) select_kernel<R, 8, 1><<<grid(8), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  else if (A <= 16) select_kernel<R, 16, 1><<<grid(16), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  else if (A <= 32) select_kernel<R, 32, 1><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  else if (A <= 64) select_kernel<R, 32, 2><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  else if (A <= 128) select_kernel<R, 32, 4><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  else select_kernel<R, 32, 8><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  return caro_check_launch("select_kernel");
+}
+
+}  // namespace
+
+static int do_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player, int bump, void* stream);
+
+extern "C" {
+
+size_t caro_engine_workspace_bytes(const caro_engine_config* cfg) {
+  Dims dm;
+  int plies;
+  if (fill_dims(cfg, &dm, &plies) != CARO_OK) return 0;
+  Carver c;
+  if (cfg->game == CARO_GAME_CONNECT4) {
+    View<C4Board> v;
+    build_view<C4Board>(c, dm, nullptr, &v);
+  } else {
+    View<MnkBoard> v;
+    build_view<MnkBoard>(c, dm, nullptr, &v);
+  }
+  return (c.cur + 255) & ~(size_t)255;
+}
+
+int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t bytes, caro_engine** out, void* stream) {
+  if (!out || !d_workspace) return caro_fail(CARO_E_ARG, "null argument");
+  if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the engine has no CPU fallback");
+  Dims dm;
+  int plies;
+  int rc = fill_dims(cfg, &dm, &plies);
+  if (rc != CARO_OK) return rc;
+  const size_t need = caro_engine_workspace_bytes(cfg);
+  if (bytes < need) return caro_fail(CARO_E_ARG, "workspace too small");
+  caro_engine* e = new caro_engine();
+  e->cfg = *cfg;
+  e->dm = dm;
+  e->max_plies = plies;
+  e->sp.c_puct = cfg->c_puct;
+  e->sp.alpha = cfg->alpha;
+  e->sp.explore = cfg->explore;
+  e->sp.seed_lo = (uint32_t)cfg->seed;
+  e->sp.seed_hi = (uint32_t)(cfg->seed >> 32);
+  e->ws = (char*)d_workspace;
+  e->ws_bytes = need;
+  e->mnk.n = cfg->n;
+  e->mnk.k = cfg->k;
+  if (cfg->game == CARO_GAME_CONNECT4) {
+    build_view<C4Board>(e->carve, dm, e->ws, &e->v_c4);
+    e->board_bytes = sizeof(C4Board);
+  } else {
+    build_view<MnkBoard>(e->carve, dm, e->ws, &e->v_mnk);
+    e->board_bytes = sizeof(MnkBoard);
+  }
+  cudaError_t ce = cudaMemsetAsync(e->ws, 0, need, S(stream));
+  if (ce != cudaSuccess) {
+    delete e;
+    return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  }
+  *out = e;
+  return do_reset(e, nullptr, -1, 0, stream);
+}
+
+void caro_engine_destroy(caro_engine* e) { delete e; }
+
+int caro_engine_region(const caro_engine* e, const char* name, size_t* offset, size_t* bytes, int32_t* elem_bytes,
+                       int64_t dims[4]) {
+  if (!e || !name) return caro_fail(CARO_E_ARG, "null argument");
+  for (const Region& r : e->carve.regions) {
+    if (r.name == name) {
+      if (offset) *offset = r.offset;
+      if (bytes) *bytes = r.bytes;
+      if (elem_bytes) *elem_bytes = r.elem;
+      if (dims) memcpy(dims, r.dims, sizeof(r.dims));
+      return CARO_OK;
+    }
+  }
+  return caro_fail(CARO_E_ARG, "unknown region");
+}
+
+int caro_engine_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player, void* stream) {
+  return do_reset(e, h_game_mask, first_player, 1, stream);
+}
+
+}  // extern "C"
+
+static int do_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player, int bump, void* stream) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  uint8_t* d_mask = nullptr;
+  if (h_game_mask) {
+    // staged through the (currently unused) leaf_player region: G <= G*B bytes
+    d_mask = e->cfg.game == CARO_GAME_CONNECT4 ? e->v_c4.leaf_player : e->v_mnk.leaf_player;
+    cudaError_t ce = cudaMemcpyAsync(d_mask, h_game_mask, (size_t)e->dm.G, cudaMemcpyHostToDevice, S(stream));
+    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  }
+  const unsigned grid = (unsigned)((e->dm.G + 127) / 128);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    reset_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, e->sp, d_mask, first_player, bump);
+  else
+    reset_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, e->sp, d_mask, first_player, bump);
+  return caro_check_launch("reset_kernel");
+}
+
+extern "C" {
+
+int caro_engine_set_roots(caro_engine* e, const void* h_boards, const uint8_t* h_players, void* stream) {
+  if (!e || !h_boards || !h_players) return caro_fail(CARO_E_ARG, "null argument");
+  void* d_b = e->cfg.game == CARO_GAME_CONNECT4 ? (void*)e->v_c4.root_board : (void*)e->v_mnk.root_board;
+  uint8_t* d_p = e->cfg.game == CARO_GAME_CONNECT4 ? e->v_c4.root_player : e->v_mnk.root_player;
+  uint8_t* d_s = e->cfg.game == CARO_GAME_CONNECT4 ? e->v_c4.status : e->v_mnk.status;
+  cudaError_t ce = cudaMemcpyAsync(d_b, h_boards, e->board_bytes * (size_t)e->dm.G, cudaMemcpyHostToDevice, S(stream));
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_p, h_players, (size_t)e->dm.G, cudaMemcpyHostToDevice, S(stream));
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(d_s, ST_ACTIVE, (size_t)e->dm.G, S(stream));
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  return CARO_OK;
+}
+
+int caro_engine_select(caro_engine* e, int batch, int minibatch_index, const double* d_noise, double* d_noise_out,
+                       void* stream) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  if (batch <= 0 || batch > e->dm.B) return caro_fail(CARO_E_ARG, "batch exceeds max_batch");
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    return launch_select<C4Rules>(e->v_c4, C4Rules(), e->dm, e->sp, batch, minibatch_index, d_noise, d_noise_out, S(stream));
+  return launch_select<MnkRules>(e->v_mnk, e->mnk, e->dm, e->sp, batch, minibatch_index, d_noise, d_noise_out, S(stream));
+}
+
+int caro_engine_plan(caro_engine* e, int batch, void* stream) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  if (batch <= 0 || batch > e->dm.B) return caro_fail(CARO_E_ARG, "batch exceeds max_batch");
+  const unsigned grid = (unsigned)((e->dm.G + 127) / 128);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    plan_kernel<C4Board><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch);
+  else
+    plan_kernel<MnkBoard><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch);
+  return caro_check_launch("plan_kernel");
+}
+
+int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, const float* d_values, void* stream) {
+  if (!e || !d_probs || !d_values) return caro_fail(CARO_E_ARG, "null argument");
+  const unsigned grid = (unsigned)(((long long)e->dm.G * 32 + 127) / 128);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    expand_backup_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
+  else
+    expand_backup_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch, d_probs, d_values);
+  return caro_check_launch("expand_backup_kernel");
+}
+
+int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl, void* stream) {
+  if (!e || !net) return caro_fail(CARO_E_ARG, "null argument");
+  const bool c4 = e->cfg.game == CARO_GAME_CONNECT4;
+  const void* lb = c4 ? (const void*)e->v_c4.leaf_board : (const void*)e->v_mnk.leaf_board;
+  const uint8_t* lp = c4 ? e->v_c4.leaf_player : e->v_mnk.leaf_player;
+  const int32_t* lc = c4 ? e->v_c4.leaf_count : e->v_mnk.leaf_count;
+  float* pr = c4 ? e->v_c4.probs : e->v_mnk.probs;
+  float* va = c4 ? e->v_c4.values : e->v_mnk.values;
+  for (int i = 0; i < count; ++i) {
+    int rc = caro_engine_select(e, batch, i, nullptr, nullptr, stream);
+    if (rc == CARO_OK) rc = caro_engine_plan(e, batch, stream);
+    if (rc == CARO_OK)
+      rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, lb, lp, lc, (int64_t)e->dm.G * batch, pr, va, net_impl, stream);
+    if (rc == CARO_OK) rc = caro_engine_expand_backup(e, batch, pr, va, stream);
+    if (rc != CARO_OK) return rc;
+  }
+  return CARO_OK;
+}
+
+int caro_engine_root_policy(caro_engine* e, int tau_mode, int tau_plies, double* d_pi, float* d_q, int32_t* d_n, void* stream) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  const unsigned grid = (unsigned)((e->dm.G + 127) / 128);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    root_policy_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, C4Rules(), e->dm, tau_mode, tau_plies, d_pi, d_q, d_n);
+  else
+    root_policy_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, tau_mode, tau_plies, d_pi, d_q, d_n);
+  return caro_check_launch("root_policy_kernel");
+}
+
+int caro_engine_advance(caro_engine* e, int tau_plies, const double* d_uniform, int auto_restart, int first_player,
+                        int32_t* d_action_out, void* stream) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  const unsigned grid = (unsigned)((e->dm.G + 127) / 128);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    advance_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, C4Rules(), e->dm, e->sp, tau_plies, d_uniform, auto_restart,
+                                                            first_player, d_action_out);
+  else
+    advance_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, e->sp, tau_plies, d_uniform, auto_restart,
+                                                             first_player, d_action_out);
+  return caro_check_launch("advance_kernel");
+}
+
+int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int moves, int count, int batch, int tau_plies,
+                     int auto_restart, int first_player, int net_impl, void* stream) {
+  if (!e || !net_p0 || !net_p1) return caro_fail(CARO_E_ARG, "null argument");
+  if (net_p0 != net_p1 && (first_player < 0 || auto_restart))
+    return caro_fail(CARO_E_ARG, "two different nets need a fixed first player and no auto-restart (lock-step plies)");
+  for (int m = 0; m < moves; ++m) {
+    caro_net* net = net_p0;
+    if (net_p0 != net_p1) net = ((first_player ^ (m & 1)) == 0) ? net_p0 : net_p1;
+    int rc = caro_engine_search(e, net, count, batch, net_impl, stream);
+    if (rc == CARO_OK) rc = caro_engine_advance(e, tau_plies, nullptr, auto_restart, first_player, nullptr, stream);
+    if (rc != CARO_OK) return rc;
+  }
+  return CARO_OK;
+}
+
+int caro_engine_counters(caro_engine* e, uint64_t h_out[8], void* stream) {
+  if (!e || !h_out) return caro_fail(CARO_E_ARG, "null argument");
+  const unsigned long long* src = e->cfg.game == CARO_GAME_CONNECT4 ? e->v_c4.ctr : e->v_mnk.ctr;
+  cudaError_t ce = cudaMemcpyAsync(h_out, src, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream));
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(stream));
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  return CARO_OK;
+}
+
+}  // extern "C"

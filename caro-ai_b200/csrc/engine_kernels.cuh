@@ -1,0 +1,613 @@
+// Search kernels: PUCT select (one lane-group per descent), minibatch plan (dedup + leaf gather),
+// expand + ordered back-up (one warp per game), root policy and the per-ply game step.
+//
+// Arithmetic contract (SURVEY.md A.4 = the reference under numpy >= 2): interior scores float32
+// with no FMA contraction, root (noisy) scores float64, W/Q float32, ties -> lowest action.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "engine.cuh"
+#include "rng.cuh"
+
+namespace caro {
+
+// ------------------------------------------------------------------------------ small helpers
+template <int GW>
+__device__ __forceinline__ unsigned group_mask() {
+  if (GW == 32) return 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  return ((1u << GW) - 1u) << (lane & ~(unsigned)(GW - 1));
+}
+
+__device__ __forceinline__ HashSlot load_slot(const HashSlot* p) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  HashSlot s;
+  s.key = ((uint64_t)v.y << 32) | v.x;
+  s.node = (int32_t)v.z;
+  s.gen = v.w;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t slot_home(uint64_t key_lo, int cap) {
+  return (uint32_t)mix64(key_lo) & (uint32_t)(cap - 1);
+}
+
+// Transposition lookup, GW slots probed per round by the GW lanes of a descent group
+// (is_leaf, lib/mcts.py:150-160).  Returns the arena-local node index or -1.
+template <int GW>
+__device__ __forceinline__ int ht_lookup(const HashSlot* __restrict__ ht, int cap, uint32_t gen, Key128 key,
+                                         const uint64_t* __restrict__ key_hi /* arena base or nullptr */,
+                                         int gl, unsigned gmask) {
+  const uint32_t home = slot_home(key.lo, cap);
+  const int gbase = (threadIdx.x & 31) & ~(GW - 1);
+  for (int it = 0; it < cap; it += GW) {
+    const uint32_t idx = (home + (uint32_t)(it + gl)) & (uint32_t)(cap - 1);
+    const HashSlot sl = load_slot(ht + idx);
+    const bool empty = sl.gen != gen;
+    bool match = !empty && sl.key == key.lo;
+    if (match && key_hi != nullptr) match = key_hi[sl.node] == key.hi;
+    const unsigned bm = __ballot_sync(gmask, match) >> gbase;
+    const unsigned be = __ballot_sync(gmask, empty) >> gbase;
+    const int fm = bm ? (__ffs(bm) - 1) : 64;
+    const int fe = be ? (__ffs(be) - 1) : 64;
+    if (fm < fe) return __shfl_sync(gmask, sl.node, gbase + fm);
+    if (fe < 64) return -1;
+  }
+  return -1;
+}
+
+// single-thread variant (expand / policy kernels)
+__device__ __forceinline__ int ht_lookup1(const HashSlot* __restrict__ ht, int cap, uint32_t gen, Key128 key,
+                                          const uint64_t* __restrict__ key_hi) {
+  uint32_t idx = slot_home(key.lo, cap);
+  for (int it = 0; it < cap; ++it) {
+    const HashSlot sl = load_slot(ht + idx);
+    if (sl.gen != gen) return -1;
+    if (sl.key == key.lo && (key_hi == nullptr || key_hi[sl.node] == key.hi)) return sl.node;
+    idx = (idx + 1u) & (uint32_t)(cap - 1);
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void ht_insert1(HashSlot* __restrict__ ht, int cap, uint32_t gen, uint64_t key_lo, int node) {
+  uint32_t idx = slot_home(key_lo, cap);
+  for (int it = 0; it < cap; ++it) {
+    if (ht[idx].gen != gen) {
+      uint4 v;
+      v.x = (uint32_t)key_lo;
+      v.y = (uint32_t)(key_lo >> 32);
+      v.z = (uint32_t)node;
+      v.w = gen;
+      *reinterpret_cast<uint4*>(ht + idx) = v;
+      return;
+    }
+    idx = (idx + 1u) & (uint32_t)(cap - 1);
+  }
+}
+
+template <class R>
+struct RulesTraits {
+  static constexpr bool kHasKeyHi = true;
+};
+template <>
+struct RulesTraits<C4Rules> {
+  static constexpr bool kHasKeyHi = false;
+};
+
+// ---------------------------------------------------------------------------------- select
+// One group of GW lanes per descent, APL actions per lane (action = lane + i*GW).
+template <class R, int GW, int APL>
+__global__ void __launch_bounds__(256)
+select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch, int mb_index,
+              const double* __restrict__ noise_in, double* __restrict__ noise_out) {
+  using Board = typename R::Board;
+  const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gthread == 0) {
+    *e.leaf_count = 0;  // plan_kernel (next launch on the stream) accumulates into it
+  }
+  const long long grp = gthread / GW;
+  if (grp >= (long long)dm.G * batch) return;
+  const int gl = threadIdx.x & (GW - 1);
+  const unsigned gmask = group_mask<GW>();
+  const int g = (int)(grp / batch), j = (int)(grp % batch);
+  const size_t di = (size_t)g * dm.B + j;
+  if (e.status[g] != ST_ACTIVE) {
+    if (gl == 0) {
+      e.d_kind[di] = KIND_SKIP;
+      e.d_slot[di] = -1;
+    }
+    return;
+  }
+  const int A = dm.A;
+  Board s = e.root_board[g];
+  int who = e.root_player[g];
+  const int root_who = who;
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? who : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  const HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const uint64_t* khi = RulesTraits<R>::kHasKeyHi ? (e.key_hi + nb) : nullptr;
+
+  const float c_f = (float)sp.c_puct;                 // python float * np.float32 -> float32 (NEP 50)
+  const float keep_f = (float)(1.0 - sp.explore);     // (1 - EXPLORE) * prob, lib/mcts.py:59
+  Key128 key = rules.key(s);
+  int node = ht_lookup<GW>(ht, dm.hash_cap, gen, key, khi, gl, gmask);
+  int depth = 0;
+  int kind = KIND_EXPAND;
+  float term_value = 0.0f;
+  int32_t* path_node = e.d_path_node + di * dm.max_depth;
+  uint8_t* path_action = e.d_path_action + di * dm.max_depth;
+
+  while (node >= 0) {
+    const size_t row = (nb + (size_t)node) * dm.Apad;
+    int n_loc[APL];
+    float q_loc[APL], p_loc[APL];
+    int sum_n = 0;
+#pragma unroll
+    for (int i = 0; i < APL; ++i) {
+      const int a = gl + i * GW;
+      if (a < A) {
+        n_loc[i] = e.N[row + a];
+        q_loc[i] = e.Q[row + a];
+        p_loc[i] = e.P[row + a];
+      } else {
+        n_loc[i] = 0;
+        q_loc[i] = 0.0f;
+        p_loc[i] = 0.0f;
+      }
+      sum_n += n_loc[i];
+    }
+#pragma unroll
+    for (int off = GW / 2; off > 0; off >>= 1) sum_n += __shfl_xor_sync(gmask, sum_n, off);
+
+    double best = -INFINITY;
+    int best_a = 0x7fffffff;
+    if (depth == 0) {
+      // ---- root: Dirichlet noise + float64 scores (lib/mcts.py:48-62,131-132) -------------
+      double z[APL];
+      if (noise_in != nullptr) {
+#pragma unroll
+        for (int i = 0; i < APL; ++i) {
+          const int a = gl + i * GW;
+          z[i] = (a < A) ? noise_in[((size_t)g * batch + j) * A + a] : 0.0;
+        }
+      } else {
+        double zs = 0.0;
+        const uint64_t uid = e.uid[g];
+        const uint32_t ply = (uint32_t)e.ply[g];
+#pragma unroll
+        for (int i = 0; i < APL; ++i) {
+          const int a = gl + i * GW;
+          z[i] = 0.0;
+          if (a < A) {
+            z[i] = (double)gamma_small((float)sp.alpha, sp.seed_lo ^ kStreamDirichlet, sp.seed_hi,
+                                       (uint32_t)uid, (uint32_t)(uid >> 32) ^ (ply << 16) ^ (uint32_t)root_who,
+                                       ((uint32_t)(mb_index * batch + j) << 8) | (uint32_t)a);
+          }
+          zs += z[i];
+        }
+#pragma unroll
+        for (int off = GW / 2; off > 0; off >>= 1) zs += __shfl_xor_sync(gmask, zs, off);
+#pragma unroll
+        for (int i = 0; i < APL; ++i) z[i] = __ddiv_rn(z[i], zs);
+      }
+      if (noise_out != nullptr) {
+#pragma unroll
+        for (int i = 0; i < APL; ++i) {
+          const int a = gl + i * GW;
+          if (a < A) noise_out[((size_t)g * batch + j) * A + a] = z[i];
+        }
+      }
+      const double sq = sqrt((double)sum_n);
+#pragma unroll
+      for (int i = 0; i < APL; ++i) {
+        const int a = gl + i * GW;
+        if (a < A && rules.legal(s, a)) {
+          const double pn = __dadd_rn((double)__fmul_rn(keep_f, p_loc[i]), __dmul_rn(sp.explore, z[i]));
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq), (double)(1 + n_loc[i]));
+          // Q keeps python-float (float64) precision until a float32 value touched W(s,a)
+          double q64 = (double)q_loc[i];
+          const bool f32 = (e.flags[(nb + (size_t)node) * dm.FW + (a >> 5)] >> (a & 31)) & 1u;
+          if (!f32 && n_loc[i] > 0) q64 = __ddiv_rn((double)e.W[row + a], (double)n_loc[i]);
+          const double sc = __dadd_rn(q64, u);
+          if (sc > best) {
+            best = sc;
+            best_a = a;
+          }
+        }
+      }
+    } else {
+      // ---- interior: float32 scores (lib/mcts.py:64-84 under NEP 50) ----------------------
+      const float sq = (float)sqrt((double)sum_n);
+#pragma unroll
+      for (int i = 0; i < APL; ++i) {
+        const int a = gl + i * GW;
+        if (a < A && rules.legal(s, a)) {
+          const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p_loc[i]), sq), (float)(1 + n_loc[i]));
+          const double sc = (double)__fadd_rn(q_loc[i], t);
+          if (sc > best) {
+            best = sc;
+            best_a = a;
+          }
+        }
+      }
+    }
+    // first maximum over the group (np.argmax, lib/mcts.py:136)
+#pragma unroll
+    for (int off = GW / 2; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(gmask, best, off);
+      const int oa = __shfl_xor_sync(gmask, best_a, off);
+      if (ob > best || (ob == best && oa < best_a)) {
+        best = ob;
+        best_a = oa;
+      }
+    }
+    const int a = best_a;
+    if (gl == 0) {
+      path_node[depth] = node;
+      path_action[depth] = (uint8_t)a;
+    }
+    ++depth;
+    const bool won = rules.apply(s, a, who);  // lib/mcts.py:138-139
+    who ^= 1;
+    if (won) {
+      kind = KIND_TERMINAL;
+      term_value = -1.0f;  // lib/mcts.py:140-142
+      break;
+    }
+    if (!rules.any_legal(s)) {
+      kind = KIND_TERMINAL;
+      term_value = 0.0f;   // lib/mcts.py:145-146
+      break;
+    }
+    key = rules.key(s);
+    node = ht_lookup<GW>(ht, dm.hash_cap, gen, key, khi, gl, gmask);
+  }
+  if (gl == 0) {
+    e.d_kind[di] = (uint8_t)kind;
+    e.d_value[di] = term_value;
+    e.d_board[di] = s;
+    e.d_player[di] = (uint8_t)who;
+    e.d_key_lo[di] = key.lo;
+    e.d_key_hi[di] = key.hi;
+    e.d_path_len[di] = depth;
+    e.d_slot[di] = -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------ plan
+// One thread per game: back-up queue = terminal descents in descent order, then the first
+// occurrence of every distinct new leaf (lib/mcts.py:265-278); unique leaves are appended to the
+// compact batch (order across games is arbitrary; results do not depend on it).
+template <class Board>
+__global__ void __launch_bounds__(128)
+plan_kernel(View<Board> e, Dims dm, int batch) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int n_term = 0, n_new = 0;
+  uint8_t order[64];
+  const bool live = g < dm.G && e.status[g] == ST_ACTIVE;
+  const size_t d0 = (size_t)(g < dm.G ? g : 0) * dm.B;
+  if (live) {
+    for (int j = 0; j < batch; ++j)
+      if (e.d_kind[d0 + j] == KIND_TERMINAL) order[n_term++] = (uint8_t)j;
+    for (int j = 0; j < batch; ++j) {
+      if (e.d_kind[d0 + j] != KIND_EXPAND) continue;
+      const uint64_t lo = e.d_key_lo[d0 + j], hi = e.d_key_hi[d0 + j];
+      bool dup = false;
+      for (int q = n_term; q < n_term + n_new; ++q) {
+        const int jj = order[q];
+        dup = dup || (e.d_key_lo[d0 + jj] == lo && e.d_key_hi[d0 + jj] == hi);
+      }
+      if (!dup) order[n_term + n_new++] = (uint8_t)j;
+    }
+  }
+  // warp-aggregated reservation in the compact leaf batch
+  int incl = n_new;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && warp_total > 0) base = atomicAdd(e.leaf_count, warp_total);
+  base = __shfl_sync(0xffffffffu, base, 31) + incl - n_new;
+  if (!live) {
+    if (g < dm.G) e.q_len[g] = 0;
+    return;
+  }
+  e.q_len[g] = n_term + n_new;
+  for (int q = 0; q < n_term + n_new; ++q) {
+    const int j = order[q];
+    e.q_order[d0 + q] = (uint8_t)j;
+    if (q >= n_term) {
+      const int slot = base + (q - n_term);
+      e.d_slot[d0 + j] = slot;
+      e.leaf_board[slot] = e.d_board[d0 + j];
+      e.leaf_player[slot] = e.d_player[d0 + j];
+    }
+  }
+  if (n_new) atomicAdd(e.ctr + CTR_LEAVES, (unsigned long long)n_new);
+  atomicAdd(e.ctr + CTR_DESCENTS, (unsigned long long)batch);
+}
+
+// --------------------------------------------------------------------------- expand + backup
+// One warp per game.  Queue entries are applied strictly in order (float32 W sums are order
+// dependent); inside an entry the lanes take one edge of the path each (edges of one path are
+// distinct nodes, and an edge always sits at the same depth, hence on the same lane).
+template <class R>
+__global__ void __launch_bounds__(128)
+expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
+                     const float* __restrict__ values) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= dm.G || e.status[g] != ST_ACTIVE) return;
+  const int who0 = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? who0 : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const size_t d0 = (size_t)g * dm.B;
+  const int qn = e.q_len[g];
+  int count = e.node_count[tree];
+  for (int q = 0; q < qn; ++q) {
+    const size_t di = d0 + e.q_order[d0 + q];
+    const int kind = e.d_kind[di];
+    float v;
+    bool from_net = false;
+    if (kind == KIND_EXPAND) {
+      const int slot = e.d_slot[di];
+      v = values[slot];
+      from_net = true;
+      if (count < dm.node_cap) {  // _create_node, lib/mcts.py:178-190
+        const int node = count++;
+        const size_t row = (nb + (size_t)node) * dm.Apad;
+        for (int a = lane; a < dm.Apad; a += 32) {
+          e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
+          e.N[row + a] = 0;
+          e.W[row + a] = 0.0f;
+          e.Q[row + a] = 0.0f;
+        }
+        for (int w = lane; w < dm.FW; w += 32) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
+        if (lane == 0) {
+          e.node_board[nb + node] = e.d_board[di];
+          e.node_player[nb + node] = e.d_player[di];
+          if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + node] = e.d_key_hi[di];
+          ht_insert1(ht, dm.hash_cap, gen, e.d_key_lo[di], node);
+        }
+      } else if (lane == 0) {
+        atomicOr(e.ctr + CTR_ERRORS, ERR_ARENA_FULL);
+      }
+    } else {
+      v = e.d_value[di];
+    }
+    // _backup, lib/mcts.py:225-246
+    const int d = e.d_path_len[di];
+    const int32_t* pn = e.d_path_node + di * dm.max_depth;
+    const uint8_t* pa = e.d_path_action + di * dm.max_depth;
+    for (int i = lane; i < d; i += 32) {
+      const int a = pa[i];
+      const size_t idx = (nb + (size_t)pn[i]) * dm.Apad + a;
+      const float cur = ((d - 1 - i) & 1) ? v : -v;
+      const int n = e.N[idx] + 1;
+      const float w = __fadd_rn(e.W[idx], cur);
+      e.N[idx] = n;
+      e.W[idx] = w;
+      e.Q[idx] = __fdiv_rn(w, (float)n);
+      if (from_net) e.flags[(nb + (size_t)pn[i]) * dm.FW + (a >> 5)] |= 1u << (a & 31);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) e.node_count[tree] = count;
+}
+
+// ------------------------------------------------------------------------------ root policy
+// MCTS.get_policy_value (lib/mcts.py:289-313).  One thread per game.
+template <class R>
+__device__ __forceinline__ int root_node_of(const View<typename R::Board>& e, const R& rules, const Dims& dm, int g,
+                                            size_t* nb_out) {
+  const int who = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? who : 0);
+  const size_t nb = (size_t)tree * dm.node_cap;
+  *nb_out = nb;
+  const Key128 key = rules.key(e.root_board[g]);
+  return ht_lookup1(e.ht + (size_t)tree * dm.hash_cap, dm.hash_cap, e.tree_gen[tree], key,
+                    RulesTraits<R>::kHasKeyHi ? (e.key_hi + nb) : nullptr);
+}
+
+template <class R>
+__global__ void root_policy_kernel(View<typename R::Board> e, R rules, Dims dm, int tau_mode, int tau_plies,
+                                   double* __restrict__ pi, float* __restrict__ qout, int32_t* __restrict__ nout) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= dm.G) return;
+  const int A = dm.A;
+  size_t nb;
+  const int node = root_node_of<R>(e, rules, dm, g, &nb);
+  if (node < 0) {
+    for (int a = 0; a < A; ++a) {
+      if (pi) pi[(size_t)g * A + a] = 0.0;
+      if (qout) qout[(size_t)g * A + a] = 0.0f;
+      if (nout) nout[(size_t)g * A + a] = 0;
+    }
+    return;
+  }
+  const size_t row = (nb + (size_t)node) * dm.Apad;
+  const int tau = tau_mode == 2 ? (e.ply[g] < tau_plies ? 1 : 0) : tau_mode;
+  long long total = 0;
+  int best_n = -1, best_a = 0;
+  for (int a = 0; a < A; ++a) {
+    const int n = e.N[row + a];
+    total += n;
+    if (n > best_n) {
+      best_n = n;
+      best_a = a;
+    }
+  }
+  for (int a = 0; a < A; ++a) {
+    const int n = e.N[row + a];
+    if (pi) pi[(size_t)g * A + a] = tau == 0 ? (a == best_a ? 1.0 : 0.0) : __ddiv_rn((double)n, (double)total);
+    if (qout) qout[(size_t)g * A + a] = e.Q[row + a];
+    if (nout) nout[(size_t)g * A + a] = n;
+  }
+}
+
+// ----------------------------------------------------------------------------------- advance
+// One ply of lib/utils.py:76-106 for every active game.  One thread per game.
+template <class R>
+__global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int tau_plies,
+                               const double* __restrict__ uniform_in, int auto_restart, int first_player,
+                               int32_t* __restrict__ action_out) {
+  using Board = typename R::Board;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= dm.G) return;
+  if (action_out) action_out[g] = -1;
+  if (e.status[g] != ST_ACTIVE) return;
+  const int A = dm.A;
+  size_t nb;
+  const int node = root_node_of<R>(e, rules, dm, g, &nb);
+  Board s = e.root_board[g];
+  const int who = e.root_player[g];
+  const int ply = e.ply[g];
+  const int tau = ply < tau_plies ? 1 : 0;  // lib/utils.py:68,97-99
+  // visit counts -> pi
+  long long total = 0;
+  int best_n = -1, best_a = 0;
+  const size_t row = (nb + (size_t)(node < 0 ? 0 : node)) * dm.Apad;
+  if (node >= 0) {
+    for (int a = 0; a < A; ++a) {
+      const int n = e.N[row + a];
+      total += n;
+      if (n > best_n) {
+        best_n = n;
+        best_a = a;
+      }
+    }
+  }
+  // np.random.choice(A, p=pi): cdf = cumsum(p) / cumsum(p)[-1]; first index with cdf > u
+  double u;
+  if (uniform_in != nullptr) {
+    u = uniform_in[g];
+  } else {
+    const uint64_t uid = e.uid[g];
+    const Philox4 r = philox4x32_10((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)ply, 0u,
+                                    sp.seed_lo ^ kStreamChoice, sp.seed_hi);
+    u = u01d(r.v[0], r.v[1]);
+  }
+  int action = best_a;
+  if (tau != 0 && total > 0) {
+    double last = 0.0;
+    for (int a = 0; a < A; ++a) last = __dadd_rn(last, __ddiv_rn((double)e.N[row + a], (double)total));
+    double c = 0.0;
+    action = A - 1;
+    for (int a = 0; a < A; ++a) {
+      c = __dadd_rn(c, __ddiv_rn((double)e.N[row + a], (double)total));
+      if (__ddiv_rn(c, last) > u) {
+        action = a;
+        break;
+      }
+    }
+  }
+  if (action_out) action_out[g] = action;
+  // history (lib/utils.py:81)
+  const int hidx = ply < dm.max_plies ? ply : dm.max_plies - 1;
+  const size_t h = (size_t)g * dm.max_plies + hidx;
+  e.hist_board[h] = s;
+  e.hist_player[h] = (uint8_t)who;
+  for (int a = 0; a < A; ++a) {
+    float p;
+    if (tau == 0 || total <= 0) p = (a == best_a) ? 1.0f : 0.0f;
+    else p = (float)__ddiv_rn((double)e.N[row + a], (double)total);
+    e.hist_pi[h * A + a] = p;
+  }
+  if (!rules.legal(s, action)) atomicOr(e.ctr + CTR_ERRORS, ERR_ILLEGAL_ACTION);  // "Impossible action selected"
+  const bool won = rules.apply(s, action, who);
+  atomicAdd(e.ctr + CTR_PLIES, 1ull);
+  int finished = 0, res = 0;  // res from the last mover's point of view (lib/utils.py:88,94)
+  if (won) {
+    finished = 1;
+    res = 1;
+  } else if (!rules.any_legal(s)) {
+    finished = 1;
+    res = 0;
+  }
+  if (!finished) {
+    e.root_board[g] = s;
+    e.root_player[g] = (uint8_t)(who ^ 1);
+    e.ply[g] = ply + 1;
+    return;
+  }
+  // ---- game over -------------------------------------------------------------------------
+  const int n_hist = hidx + 1;
+  e.result[g] = won ? (who == 0 ? 1 : -1) : 0;  // net1 == player 0 (lib/utils.py:89)
+  atomicAdd(e.ctr + CTR_GAMES, 1ull);
+  atomicAdd(e.ctr + (won ? (who == 0 ? CTR_WIN0 : CTR_WIN1) : CTR_DRAW), 1ull);
+  if (dm.replay_cap > 0) {
+    // lib/utils.py:101-106: z = result for the last entry, sign flips walking back
+    const unsigned long long base = atomicAdd(e.rp_cursor, (unsigned long long)n_hist);
+    if (n_hist > dm.replay_cap) atomicOr(e.ctr + CTR_ERRORS, ERR_REPLAY_OVERRUN);
+    for (int t = 0; t < n_hist; ++t) {
+      const size_t src = (size_t)g * dm.max_plies + t;
+      const size_t dst = (size_t)((base + (unsigned long long)t) % (unsigned long long)dm.replay_cap);
+      e.rp_board[dst] = e.hist_board[src];
+      e.rp_player[dst] = e.hist_player[src];
+      for (int a = 0; a < A; ++a) e.rp_pi[dst * A + a] = e.hist_pi[src * A + a];
+      const int back = n_hist - 1 - t;
+      e.rp_z[dst] = (float)((back & 1) ? -res : res);
+    }
+  }
+  e.root_board[g] = s;  // terminal position stays visible until the slot is re-seated
+  e.root_player[g] = (uint8_t)(who ^ 1);
+  e.status[g] = ST_FINISHED;
+  if (auto_restart) {
+    const uint32_t played = e.played[g] + 1u;
+    e.played[g] = played;
+    const uint64_t uid = (uint64_t)g + (uint64_t)dm.G * (uint64_t)played;
+    e.uid[g] = uid;
+    int fp = first_player;
+    if (fp < 0) {
+      const Philox4 r = philox4x32_10((uint32_t)uid, (uint32_t)(uid >> 32), 0u, 0u, sp.seed_lo ^ kStreamFirst, sp.seed_hi);
+      fp = (int)(r.v[0] & 1u);
+    }
+    e.root_board[g] = R::empty();
+    e.root_player[g] = (uint8_t)fp;
+    e.ply[g] = 0;
+    e.status[g] = ST_ACTIVE;
+    for (int t = 0; t < dm.tpg; ++t) {  // MCTS.clear(): bump the generation, no memset
+      e.node_count[g * dm.tpg + t] = 0;
+      e.tree_gen[g * dm.tpg + t] += 1u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- reset
+template <class R>
+__global__ void reset_kernel(View<typename R::Board> e, Dims dm, SearchParams sp, const uint8_t* __restrict__ mask,
+                             int first_player, int bump_uid) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= dm.G) return;
+  if (mask != nullptr && mask[g] == 0) return;
+  uint32_t played = e.played[g];
+  if (bump_uid) {
+    played += 1u;
+    e.played[g] = played;
+  }
+  const uint64_t uid = (uint64_t)g + (uint64_t)dm.G * (uint64_t)played;
+  e.uid[g] = uid;
+  int fp = first_player;
+  if (fp < 0) {
+    const Philox4 r = philox4x32_10((uint32_t)uid, (uint32_t)(uid >> 32), 0u, 0u, sp.seed_lo ^ kStreamFirst, sp.seed_hi);
+    fp = (int)(r.v[0] & 1u);
+  }
+  e.root_board[g] = R::empty();
+  e.root_player[g] = (uint8_t)fp;
+  e.ply[g] = 0;
+  e.status[g] = ST_ACTIVE;
+  e.result[g] = 0;
+  for (int t = 0; t < dm.tpg; ++t) {
+    e.node_count[g * dm.tpg + t] = 0;
+    e.tree_gen[g * dm.tpg + t] += 1u;
+  }
+}
+
+}  // namespace caro

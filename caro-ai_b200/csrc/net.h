@@ -1,0 +1,63 @@
+// Internal definition of the network handle shared by net.cu (handle, SIMT tower) and
+// net_tc.cu (tcgen05 tower).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace caro {
+
+constexpr int kFilters = 64;      // lib/model.py:7
+constexpr int kBlocks = 5;        // conv_1 .. conv_5
+constexpr float kLeaky = 0.01f;   // nn.LeakyReLU default slope
+
+// Offsets (in floats) of the folded-weight blob described in include/caro_b200.h
+struct BlobLayout {
+  size_t conv_in_w, conv_in_b;
+  size_t conv_w[kBlocks], conv_b[kBlocks];
+  size_t val_conv_w, val_conv_b, val_fc1_w, val_fc1_b, val_fc2_w, val_fc2_b;
+  size_t pol_conv_w, pol_conv_b, pol_fc_w, pol_fc_b;
+  size_t total;
+};
+
+inline BlobLayout blob_layout(int H, int W, int A) {
+  BlobLayout L;
+  size_t o = 0;
+  const size_t hw = (size_t)H * W;
+  auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+  L.conv_in_w = take(kFilters * 2 * 9);
+  L.conv_in_b = take(kFilters);
+  for (int i = 0; i < kBlocks; ++i) {
+    L.conv_w[i] = take((size_t)kFilters * kFilters * 9);
+    L.conv_b[i] = take(kFilters);
+  }
+  L.val_conv_w = take(kFilters);
+  L.val_conv_b = take(1);
+  L.val_fc1_w = take(20 * hw);
+  L.val_fc1_b = take(20);
+  L.val_fc2_w = take(20);
+  L.val_fc2_b = take(1);
+  L.pol_conv_w = take(2 * kFilters);
+  L.pol_conv_b = take(2);
+  L.pol_fc_w = take((size_t)A * 2 * hw);
+  L.pol_fc_b = take(A);
+  L.total = o;
+  return L;
+}
+
+}  // namespace caro
+
+struct caro_net {
+  int H, W, A;
+  caro::BlobLayout layout;
+  float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
+  void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
+  float* d_tc_bias;     // [6][64] folded conv biases
+  float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] for coalesced reads in the TC epilogue
+};
+
+// net_tc.cu
+int caro_net_tc_pack(caro_net* net, const float* h_blob);
+void caro_net_tc_free(caro_net* net);
+int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);

@@ -1,0 +1,220 @@
+"""Lock-step batched MCTS self-play engine (host wrapper over the ``caro_engine_*`` C ABI).
+
+G independent games, each with its own tree arena(s), are advanced together: every
+``search`` step is the reference's ``MCTS.search_minibatch`` (lib/mcts.py:248-287) for all games
+at once, every ``advance`` one ply of ``play_game`` (lib/utils.py:76-99).  torch is used for device
+memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .model import DeviceNet, IMPL_TCGEN05
+
+_NP = {1: np.uint8, 4: np.int32, 8: np.int64}
+
+
+class SelfPlayEngine:
+    def __init__(self, game, games: int, trees_per_game: int = 1, max_batch: int = 8, node_capacity: int = 4096,
+                 replay_capacity: int = 0, c_puct: float = 1.0, alpha: float = 0.30, explore: float = 0.25,
+                 seed: int = 0, device: Optional[str] = None):
+        _cabi.require_cuda()
+        self.game = game
+        self.G = int(games)
+        self.A = game.action_space
+        self.max_batch = int(max_batch)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.cfg = _cabi.EngineConfig(game.game_kind, game.n, game.k, self.G, trees_per_game, max_batch, node_capacity,
+                                      replay_capacity, c_puct, alpha, explore, seed)
+        lib = _cabi.lib()
+        nbytes = lib.caro_engine_workspace_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            raise _cabi.CaroError("bad engine config: " + lib.caro_last_error().decode())
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            handle = C.c_void_p()
+            _cabi.check(lib.caro_engine_create(C.byref(self.cfg), self.workspace.data_ptr(), nbytes, C.byref(handle),
+                                               self._stream()))
+        self.handle = handle
+        self.workspace_bytes = nbytes
+        self._views: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def region(self, name: str) -> torch.Tensor:
+        """Zero-copy torch view of a named workspace region (see include/caro_b200.h)."""
+        if name not in self._views:
+            off, nbytes, elem = C.c_size_t(), C.c_size_t(), C.c_int32()
+            dims = (C.c_int64 * 4)()
+            _cabi.check(_cabi.lib().caro_engine_region(self.handle, name.encode(), C.byref(off), C.byref(nbytes),
+                                                       C.byref(elem), C.byref(dims)))
+            raw = self.workspace[off.value:off.value + nbytes.value]
+            shape = [d for d in dims if d > 0]
+            e = elem.value
+            if e == 1:
+                t = raw.view(shape)
+            elif e == 4:
+                t = raw.view(torch.int32).view(shape)
+            elif e == 8:
+                t = raw.view(torch.int64).view(shape)
+            else:  # boards / hash slots: expose as int64 words
+                t = raw.view(torch.int64).view(shape + [e // 8])
+            self._views[name] = t
+        return self._views[name]
+
+    def fregion(self, name: str) -> torch.Tensor:
+        return self.region(name).view(torch.float32)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _cabi.lib().caro_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ game control
+    def reset(self, mask: Optional[Sequence[int]] = None, first_player: int = -1):
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8))
+            assert m.size == self.G
+        _cabi.check(_cabi.lib().caro_engine_reset(self.handle, m.ctypes.data if m is not None else None, first_player,
+                                                  self._stream()))
+        if m is not None:
+            torch.cuda.current_stream(self.device).synchronize()  # host mask buffer must outlive the copy
+
+    def set_roots(self, states: Sequence[int], players: Sequence[int]):
+        """search_batch's (state_int, player) arguments for every game (host ints -> one H2D copy)."""
+        assert len(states) == self.G and len(players) == self.G
+        boards = np.ascontiguousarray(self.game.boards_from_states(states))
+        pl = np.ascontiguousarray(np.asarray(players, dtype=np.uint8))
+        _cabi.check(_cabi.lib().caro_engine_set_roots(self.handle, boards.ctypes.data, pl.ctypes.data, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def set_roots_pinned(self, boards_pinned: torch.Tensor, players_pinned: torch.Tensor):
+        """Same, from caller-owned pinned host tensors (no sync; used by the end-to-end bench)."""
+        _cabi.check(_cabi.lib().caro_engine_set_roots(self.handle, boards_pinned.data_ptr(), players_pinned.data_ptr(),
+                                                      self._stream()))
+
+    # ------------------------------------------------------------------ one minibatch, split
+    def select(self, batch: int, minibatch_index: int = 0, noise: Optional[torch.Tensor] = None,
+               noise_out: Optional[torch.Tensor] = None):
+        _cabi.check(_cabi.lib().caro_engine_select(self.handle, batch, minibatch_index,
+                                                   noise.data_ptr() if noise is not None else None,
+                                                   noise_out.data_ptr() if noise_out is not None else None, self._stream()))
+
+    def plan(self, batch: int):
+        _cabi.check(_cabi.lib().caro_engine_plan(self.handle, batch, self._stream()))
+
+    def leaf_count(self) -> int:
+        return int(self.region("leaf_count").item())
+
+    def leaf_planes(self, count: Optional[int] = None) -> torch.Tensor:
+        """float32 [L,2,H,W] planes of the compact leaf batch (== states_to_training_batch)."""
+        count = self.leaf_count() if count is None else count
+        return self.game.planes_device(self.region("leaf_board"), self.region("leaf_player"), count)
+
+    def expand_backup(self, batch: int, probs: torch.Tensor, values: torch.Tensor):
+        assert probs.dtype == torch.float32 and values.dtype == torch.float32 and probs.is_contiguous()
+        _cabi.check(_cabi.lib().caro_engine_expand_backup(self.handle, batch, probs.data_ptr(), values.data_ptr(),
+                                                          self._stream()))
+
+    # ------------------------------------------------------------------ fused paths
+    def search(self, net: DeviceNet, count: int, batch: int, impl: int = IMPL_TCGEN05):
+        """MCTS.search_batch(count, batch, ...) for all games with the built-in network."""
+        _cabi.check(_cabi.lib().caro_engine_search(self.handle, net.handle, count, batch, impl, self._stream()))
+
+    def search_with(self, evaluate, count: int, batch: int, noise_fn=None):
+        """Same, with a caller-supplied evaluator ``evaluate(planes[L,2,H,W]) -> (priors[L,A], values[L])``
+        (CUDA tensors).  One host sync per minibatch (the leaf count)."""
+        for i in range(count):
+            noise = noise_fn(i) if noise_fn is not None else None
+            self.select(batch, i, noise)
+            self.plan(batch)
+            n = self.leaf_count()
+            if n:
+                pri, val = evaluate(self.leaf_planes(n))
+                self.expand_backup(batch, pri.contiguous().float(), val.contiguous().float())
+            else:
+                dummy = torch.zeros(1, dtype=torch.float32, device=self.device)
+                self.expand_backup(batch, dummy, dummy)
+
+    def root_policy(self, tau_mode: int = 1, tau_plies: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        pi = torch.empty((self.G, self.A), dtype=torch.float64, device=self.device)
+        q = torch.empty((self.G, self.A), dtype=torch.float32, device=self.device)
+        n = torch.empty((self.G, self.A), dtype=torch.int32, device=self.device)
+        _cabi.check(_cabi.lib().caro_engine_root_policy(self.handle, tau_mode, tau_plies, pi.data_ptr(), q.data_ptr(),
+                                                        n.data_ptr(), self._stream()))
+        return pi, q, n
+
+    def advance(self, tau_plies: int, uniform: Optional[torch.Tensor] = None, auto_restart: bool = False,
+                first_player: int = -1, want_actions: bool = True) -> Optional[torch.Tensor]:
+        actions = torch.empty(self.G, dtype=torch.int32, device=self.device) if want_actions else None
+        _cabi.check(_cabi.lib().caro_engine_advance(self.handle, tau_plies,
+                                                    uniform.data_ptr() if uniform is not None else None,
+                                                    1 if auto_restart else 0, first_player,
+                                                    actions.data_ptr() if actions is not None else None, self._stream()))
+        return actions
+
+    def play(self, net_p0: DeviceNet, net_p1: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
+             auto_restart: bool = True, first_player: int = -1, impl: int = IMPL_TCGEN05):
+        _cabi.check(_cabi.lib().caro_engine_play(self.handle, net_p0.handle, net_p1.handle, moves, count, batch, tau_plies,
+                                                 1 if auto_restart else 0, first_player, impl, self._stream()))
+
+    # ------------------------------------------------------------------ read-back
+    COUNTER_NAMES = ("leaf_evals", "games", "plies", "wins_p0", "wins_p1", "draws", "descents", "errors")
+
+    def counters(self) -> Dict[str, int]:
+        out = (C.c_uint64 * 8)()
+        _cabi.check(_cabi.lib().caro_engine_counters(self.handle, C.byref(out), self._stream()))
+        return dict(zip(self.COUNTER_NAMES, [int(v) for v in out]))
+
+    def roots(self) -> Tuple[List[int], List[int]]:
+        boards = self.region("root_board").cpu().numpy().view(np.uint64)
+        return self.game.states_from_boards(boards), [int(p) for p in self.region("root_player").cpu().numpy()]
+
+    def export_tree(self, tree: int) -> Dict[int, dict]:
+        """{state_int: {"N","W","Q","P","f32"}} of one arena -- the dict view of lib/mcts.py:29-36."""
+        n_nodes = int(self.region("node_count")[tree].item())
+        cap = self.cfg.node_capacity
+        lo, hi = tree * cap, tree * cap + n_nodes
+        A = self.A
+        N = self.region("N")[lo:hi, :A].cpu().numpy()
+        W = self.fregion("W")[lo:hi, :A].cpu().numpy()
+        Q = self.fregion("Q")[lo:hi, :A].cpu().numpy()
+        P = self.fregion("P")[lo:hi, :A].cpu().numpy()
+        F = self.region("flags")[lo:hi].cpu().numpy().view(np.uint32)
+        boards = self.region("node_board")[lo:hi].cpu().numpy().view(np.uint64)
+        states = self.game.states_from_boards(boards)
+        out = {}
+        for i, s in enumerate(states):
+            f32 = [bool((int(F[i, a >> 5]) >> (a & 31)) & 1) for a in range(A)]
+            out[s] = {"N": N[i].tolist(), "W": W[i].copy(), "Q": Q[i].copy(), "P": P[i].copy(), "f32": f32}
+        return out
+
+    def drain_replay(self, start: int = 0):
+        """Replay entries [start, cursor) as reference tuples (state_int, player, probs, z)
+        (lib/utils.py:101-106).  Returns (entries, cursor)."""
+        cursor = int(self.region("replay_cursor").item())
+        cap = self.cfg.replay_capacity
+        if cap <= 0 or cursor == start:
+            return [], cursor
+        start = max(start, cursor - cap)
+        idx = torch.arange(start, cursor, device=self.device) % cap
+        boards = self.region("replay_board")[idx].cpu().numpy().view(np.uint64)
+        players = self.region("replay_player")[idx].cpu().numpy()
+        pi = self.fregion("replay_pi")[idx].cpu().numpy()
+        z = self.fregion("replay_z")[idx].cpu().numpy()
+        states = self.game.states_from_boards(boards)
+        return [(states[i], int(players[i]), pi[i].tolist(), int(z[i])) for i in range(len(states))], cursor

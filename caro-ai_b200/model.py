@@ -1,0 +1,170 @@
+"""Policy/value network: the reference's ``Net`` surface (lib/model.py:10-107) and its device twin.
+
+* ``Net`` is a plain ``nn.Module`` with the reference's ``state_dict`` key set / shapes, so the
+  shipped ``saves/*/best_*.dat`` checkpoints load unchanged and new ones are written in the same
+  format.  It is what the SGD step trains (autograd, plain PyTorch -- out of scope for hand kernels).
+* ``fold_state_dict`` merges eval-mode BatchNorm into the convolutions and lays the
+  result out as the float32 blob ``caro_net_create`` expects (include/caro_b200.h).
+* ``DeviceNet`` owns a ``caro_net`` handle: the fused bf16 tcgen05 tower used on the search path.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+NUM_FILTERS = 64  # lib/model.py:7
+BN_EPS = 1e-5
+
+
+def _block(cin: int, cout: int, ksize: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=ksize, padding=ksize // 2), nn.BatchNorm2d(cout),
+                         nn.LeakyReLU())
+
+
+class Net(nn.Module):
+    """lib/model.py:10-94.  ``forward`` returns (policy logits [B,A], value [B,1])."""
+
+    def __init__(self, input_shape, actions_n):
+        super().__init__()
+        self.input_shape = tuple(input_shape)
+        self.actions_n = int(actions_n)
+        _, h, w = self.input_shape
+        self.conv_in = _block(self.input_shape[0], NUM_FILTERS, 3)
+        self.conv_1 = _block(NUM_FILTERS, NUM_FILTERS, 3)
+        self.conv_2 = _block(NUM_FILTERS, NUM_FILTERS, 3)
+        self.conv_3 = _block(NUM_FILTERS, NUM_FILTERS, 3)
+        self.conv_4 = _block(NUM_FILTERS, NUM_FILTERS, 3)
+        self.conv_5 = _block(NUM_FILTERS, NUM_FILTERS, 3)
+        self.conv_val = _block(NUM_FILTERS, 1, 1)
+        # the reference sizes its heads by pushing zeros through them in train mode
+        # (lib/model.py:55,69,74-80), leaving one BatchNorm running-stat update behind; kept so that
+        # a fresh Net() here equals a fresh reference Net() under the same seed.
+        probe = torch.zeros(1, NUM_FILTERS, h, w)
+        val_size = int(np.prod(self.conv_val(probe).size()))
+        self.value = nn.Sequential(nn.Linear(val_size, 20), nn.LeakyReLU(), nn.Linear(20, 1), nn.Tanh())
+        self.conv_policy = _block(NUM_FILTERS, 2, 1)
+        pol_size = int(np.prod(self.conv_policy(probe).size()))
+        self.policy = nn.Sequential(nn.Linear(pol_size, self.actions_n))
+
+    def forward(self, x):
+        b = x.size()[0]
+        v = self.conv_in(x)
+        v = v + self.conv_1(v)
+        v = v + self.conv_2(v)
+        v = v + self.conv_3(v)
+        v = v + self.conv_4(v)
+        v = v + self.conv_5(v)
+        val = self.value(self.conv_val(v).view(b, -1))
+        pol = self.policy(self.conv_policy(v).view(b, -1))
+        return pol, val
+
+
+class NetWrapper:
+    """lib/model.py:97-107."""
+
+    def __init__(self, model):
+        self.model = model
+        self.target_model = copy.deepcopy(model)
+
+    def sync(self):
+        self.target_model.load_state_dict(self.model.state_dict())
+
+
+def _fold(conv_w, conv_b, bn_w, bn_b, mean, var):
+    scale = bn_w / torch.sqrt(var + BN_EPS)
+    return conv_w * scale.view(-1, 1, 1, 1), (conv_b - mean) * scale + bn_b
+
+
+def fold_state_dict(sd: Dict[str, torch.Tensor], rows: int, cols: int, actions: int) -> np.ndarray:
+    """Eval-mode BN folding + flattening into the blob layout of include/caro_b200.h."""
+    sd = {k: v.detach().double().cpu() for k, v in sd.items() if v.dtype.is_floating_point}
+    parts = []
+
+    def folded(name):
+        return _fold(sd[name + ".0.weight"], sd[name + ".0.bias"], sd[name + ".1.weight"], sd[name + ".1.bias"],
+                     sd[name + ".1.running_mean"], sd[name + ".1.running_var"])
+
+    for name in ("conv_in", "conv_1", "conv_2", "conv_3", "conv_4", "conv_5"):
+        w, b = folded(name)
+        parts += [w.reshape(-1), b.reshape(-1)]
+    w, b = folded("conv_val")
+    parts += [w.reshape(-1), b.reshape(-1), sd["value.0.weight"].reshape(-1), sd["value.0.bias"].reshape(-1),
+              sd["value.2.weight"].reshape(-1), sd["value.2.bias"].reshape(-1)]
+    w, b = folded("conv_policy")
+    parts += [w.reshape(-1), b.reshape(-1), sd["policy.0.weight"].reshape(-1), sd["policy.0.bias"].reshape(-1)]
+    blob = torch.cat(parts).float().numpy()
+    hw = rows * cols
+    expect = 64 * 2 * 9 + 64 + 5 * (64 * 64 * 9 + 64) + 64 + 1 + 20 * hw + 20 + 20 + 1 + 2 * 64 + 2 + actions * 2 * hw + actions
+    assert blob.size == expect, (blob.size, expect)
+    return np.ascontiguousarray(blob)
+
+
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+
+
+class DeviceNet:
+    """Folded network resident on the GPU (``caro_net`` handle)."""
+
+    def __init__(self, net_or_state_dict, game):
+        _cabi.require_cuda()
+        sd = net_or_state_dict.state_dict() if isinstance(net_or_state_dict, nn.Module) else net_or_state_dict
+        _, self.rows, self.cols = game.obs_shape
+        self.actions = game.action_space
+        self.game = game
+        blob = fold_state_dict(sd, self.rows, self.cols, self.actions)
+        handle = C.c_void_p()
+        _cabi.check(_cabi.lib().caro_net_create(self.rows, self.cols, self.actions, blob.ctypes.data, blob.size,
+                                                C.byref(handle)))
+        self.handle = handle
+
+    def update(self, net_or_state_dict):
+        """NetWrapper.sync() on the device side: re-fold and re-upload."""
+        sd = net_or_state_dict.state_dict() if isinstance(net_or_state_dict, nn.Module) else net_or_state_dict
+        blob = fold_state_dict(sd, self.rows, self.cols, self.actions)
+        _cabi.check(_cabi.lib().caro_net_update(self.handle, blob.ctypes.data, blob.size))
+
+    def forward_boards(self, d_boards, d_who, count: int, impl: int = IMPL_TCGEN05):
+        """(priors [count,A], values [count]) float32 CUDA tensors for device boards."""
+        probs = torch.empty((count, self.actions), dtype=torch.float32, device="cuda")
+        values = torch.empty((count,), dtype=torch.float32, device="cuda")
+        if count:
+            g = self.game
+            _cabi.check(_cabi.lib().caro_net_forward(self.handle, g.game_kind, g.n, g.k, d_boards.data_ptr(),
+                                                     d_who.data_ptr(), None, count, probs.data_ptr(), values.data_ptr(),
+                                                     impl, torch.cuda.current_stream().cuda_stream))
+        return probs, values
+
+    def forward_states(self, states, players, impl: int = IMPL_TCGEN05):
+        d_boards = torch.from_numpy(self.game.boards_from_states(states).view(np.int64)).cuda()
+        d_who = torch.tensor(list(players), dtype=torch.uint8, device="cuda")
+        return self.forward_boards(d_boards, d_who, len(states), impl)
+
+    def close(self):
+        if self.handle:
+            _cabi.lib().caro_net_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_checkpoint(path: str, game) -> Net:
+    """play.py:29-35 / play_session.py:13-16: ``torch.load`` of a reference ``.dat`` state_dict."""
+    net = Net(game.obs_shape, game.action_space)
+    net.load_state_dict(torch.load(path, map_location=lambda storage, loc: storage))
+    return net
+
+
+def save_checkpoint(net: Net, path: str) -> None:
+    """train.py:214-216."""
+    torch.save(net.state_dict(), path)

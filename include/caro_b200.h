@@ -1,0 +1,196 @@
+/* caro_b200.h -- C ABI of the B200-native MCTS self-play engine (libcaro_b200.so).
+ *
+ * Drop-in boundary for the hot path of nh273/caro-ai.  The reference has no
+ * FFI layer of its own -- its seam is the Python API of lib/mcts.py, lib/game/ and lib/model.py --
+ * so every entry point below names the reference function(s) whose work it replaces
+ * (paths relative to the reference tree) and INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add at each of those call sites.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - `d_` parameters are DEVICE pointers (sm_100a, same device as the engine's workspace);
+ *     `h_` parameters are HOST pointers.  `stream` is a cudaStream_t passed as void* (NULL =
+ *     default stream).  All launches are asynchronous on `stream` unless stated otherwise.
+ *   - every function returns 0 on success, a negative CARO_E_* code otherwise;
+ *     caro_last_error() gives the message for the calling thread.  There is NO CPU fallback:
+ *     without a CUDA device the compute entry points fail with CARO_E_CUDA.
+ *   - an engine handle is not thread-safe; distinct handles are independent.
+ *
+ * Board encodings (device side; the reference's state integers are converted on the host by
+ * caro_ai_b200.game):
+ *   Connect4 : caro_c4_board  {mask, black}, bit = 7*col + row (row 0 = bottom, bit 6 of each
+ *              column is an always-empty sentinel).
+ *   m,n,k    : caro_mnk_board {w[4], b[4]}, bit = row*n + col (= the action index), n <= 15.
+ */
+#ifndef CARO_B200_H_
+#define CARO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARO_ABI_VERSION 1
+
+enum { CARO_OK = 0, CARO_E_ARG = -1, CARO_E_CUDA = -2, CARO_E_STATE = -3, CARO_E_CAPACITY = -4 };
+
+enum { CARO_GAME_CONNECT4 = 0, CARO_GAME_MNK = 1 };
+
+typedef struct { uint64_t mask, black; } caro_c4_board;
+typedef struct { uint64_t w[4], b[4]; } caro_mnk_board;
+
+int caro_abi_version(void);
+const char* caro_last_error(void);
+/* Number of CUDA devices visible to the library (0 when there is none; never throws). */
+int caro_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone board kernels -- rows a11..a16 of SURVEY.md section 8.
+ * `d_boards` is an array of `count` caro_c4_board (game = CONNECT4) or caro_mnk_board (MNK).
+ * ------------------------------------------------------------------------------------------ */
+
+/* game.move for a batch: lib/game/connect_four/connect_four.py:241-265 (+ _check_won :206-239),
+ * lib/game/tictactoe/tictactoe.py:210-235 (+ tictactoe_helpers.check_win :7-56).
+ * d_won[i] = 1 if the move wins, d_draw[i] = 1 if it does not win and leaves no legal move
+ * (lib/utils.py:92-96, lib/mcts.py:145-146).  In-place is allowed (d_out == d_boards). */
+int caro_boards_apply(int game, int n, int k, const void* d_boards, const int32_t* d_actions,
+                      const uint8_t* d_players, int64_t count, void* d_out, uint8_t* d_won,
+                      uint8_t* d_draw, void* stream);
+
+/* game.possible_moves / invalid_moves as a bitmask per board (bit a set = action a legal):
+ * connect_four.py:157-173, tictactoe.py:137-162.  d_mask is [count][mask_words] uint32,
+ * mask_words = (A + 31) / 32. */
+int caro_boards_legal_mask(int game, int n, int k, const void* d_boards, int64_t count,
+                           uint32_t* d_mask, void* stream);
+
+/* game.states_to_training_batch: connect_four.py:175-204, tictactoe.py:164-208.
+ * d_planes is float32 [count][2][H][W], plane 0 = tokens of d_who[i], row 0 = top. */
+int caro_boards_encode_planes(int game, int n, int k, const void* d_boards, const uint8_t* d_who,
+                              int64_t count, float* d_planes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Policy/value network -- row a17 (lib/model.py:10-94) + the softmax of lib/mcts.py:216.
+ * Weights are handed over ALREADY FOLDED (eval-mode BatchNorm merged into the convolutions,
+ * done on the host by caro_ai_b200.model.fold_state_dict) as one float32 blob:
+ *   conv_in  w[64][2][3][3] b[64] | 5 x ( w[64][64][3][3] b[64] ) |
+ *   conv_val w[64] b[1] | value.0 w[20][HW] b[20] | value.2 w[20] b[1] |
+ *   conv_policy w[2][64] b[2] | policy.0 w[A][2*HW] b[A]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct caro_net caro_net;
+
+size_t caro_net_blob_floats(int rows, int cols, int actions);
+/* Copies and re-packs the blob into device memory owned by the handle (bf16 UMMA operand images
+ * for the tensor-core tower + fp32 copies for the heads).  Synchronous. */
+int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t n_floats,
+                    caro_net** out);
+int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats);
+void caro_net_destroy(caro_net* net);
+
+/* Forward pass over a compact batch of leaf positions given as boards + side to move.
+ *   d_count : device int32 holding the number of valid leaves (<= max_count); read on device, so
+ *             no host synchronisation is needed between search steps.  May be NULL, then
+ *             max_count leaves are evaluated.
+ *   d_probs : float32 [max_count][A] softmax priors (over ALL actions, like the reference).
+ *   d_values: float32 [max_count]    tanh value head.
+ *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path), 1 = fp32 SIMT tower (numerics
+ *             reference kernel used by the tests). */
+int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards,
+                     const uint8_t* d_who, const int32_t* d_count, int64_t max_count,
+                     float* d_probs, float* d_values, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-play / search engine -- rows a1..a10, a18, a19.
+ * G games advance in lock-step; every game owns `trees_per_game` private arenas
+ * (1 = one tree shared by both sides, train.py:185; 2 = one tree per side, lib/utils.py:58-59).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct caro_engine caro_engine;
+
+typedef struct {
+  int32_t game;            /* CARO_GAME_* */
+  int32_t n, k;            /* m,n,k only */
+  int32_t games;           /* G */
+  int32_t trees_per_game;  /* 1 or 2 */
+  int32_t max_batch;       /* largest batch_size (descents per minibatch) that will be used */
+  int32_t node_capacity;   /* nodes per tree arena */
+  int32_t replay_capacity; /* entries in the device replay ring (0 = no replay recording) */
+  double c_puct;           /* config.py:26 */
+  double alpha;            /* config.py:27 */
+  double explore;          /* config.py:28 */
+  uint64_t seed;           /* Philox key */
+} caro_engine_config;
+
+/* Bytes of device workspace the engine needs; the caller allocates it (e.g. a torch uint8 CUDA
+ * tensor) and keeps it alive for the life of the handle. */
+size_t caro_engine_workspace_bytes(const caro_engine_config* cfg);
+int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t bytes,
+                       caro_engine** out, void* stream);
+void caro_engine_destroy(caro_engine* e);
+
+/* Offset/size of a named region of the workspace (for zero-copy views from the host language):
+ * "N","W","Q","P","flags","node_board","node_count","root_board","root_player","status","ply",
+ * "result","leaf_board","leaf_player","leaf_count","desc_kind","desc_value","desc_board",
+ * "desc_player","desc_path_len","desc_path_node","desc_path_action","desc_slot","queue_len",
+ * "queue_order","counters","replay_board","replay_player","replay_pi","replay_z","replay_cursor".
+ * elem_bytes receives the element size, dims[0..3] the logical shape (unused dims = 0). */
+int caro_engine_region(const caro_engine* e, const char* name, size_t* offset, size_t* bytes,
+                       int32_t* elem_bytes, int64_t dims[4]);
+
+/* MCTS.clear (lib/mcts.py:39-43) for the trees of the games selected by h_game_mask (NULL = all),
+ * and re-seating of the games at the initial position.  first_player: 0/1 fixed, -1 = random per
+ * game (lib/utils.py:66). */
+int caro_engine_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player, void* stream);
+/* Sets root positions explicitly (host buffers; one H2D copy): the `state_int, player` arguments
+ * of MCTS.search_batch (lib/mcts.py:162-163).  Trees are kept. */
+int caro_engine_set_roots(caro_engine* e, const void* h_boards, const uint8_t* h_players,
+                          void* stream);
+
+/* One minibatch of descents, split so that a caller can supply the network outputs itself:
+ *   select : lib/mcts.py:97-148 find_leaf x batch_size on the frozen tree, incl. _add_noise
+ *            (:48-62), _calculate_upper_bound (:64-84), _mask_invalid_actions (:86-95).
+ *            d_noise = NULL -> Philox Dirichlet; else float64 [G][batch][A] injected noise.
+ *            d_noise_out (optional) receives the noise actually used, same shape.
+ *   plan   : lib/mcts.py:265-278 terminal / expand split + duplicate-leaf drop, and the gather of
+ *            the unique leaves into the compact batch (region "leaf_board"/"leaf_player"/"leaf_count").
+ *   expand_backup : lib/mcts.py:178-190,219-223 _create_node and :225-246 _backup in queue order.
+ *            d_probs float32 [leaf_count][A], d_values float32 [leaf_count]. */
+int caro_engine_select(caro_engine* e, int batch, int minibatch_index, const double* d_noise,
+                       double* d_noise_out, void* stream);
+int caro_engine_plan(caro_engine* e, int batch, void* stream);
+int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs,
+                              const float* d_values, void* stream);
+
+/* MCTS.search_batch (lib/mcts.py:162-176) with the built-in network: `count` x
+ * (select, plan, net forward, expand_backup), no host synchronisation inside. */
+int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl,
+                       void* stream);
+
+/* MCTS.get_policy_value (lib/mcts.py:289-313) for every game's root:
+ * d_pi float64 [G][A], d_q float32 [G][A], d_n int32 [G][A].  tau_mode: 0 -> tau = 0, 1 -> tau = 1,
+ * 2 -> per game, tau = 1 while ply < tau_plies else 0 (lib/utils.py:68,97-99). */
+int caro_engine_root_policy(caro_engine* e, int tau_mode, int tau_plies, double* d_pi, float* d_q,
+                            int32_t* d_n, void* stream);
+
+/* One ply of lib/utils.py:76-99 play_game for every active game: policy(tau) -> np.random.choice
+ * (d_uniform float64 [G] injected, or NULL -> Philox) -> game.move -> win / draw bookkeeping ->
+ * history; finished games are written to the replay ring with alternating z (:101-106) and, if
+ * auto_restart != 0, re-seated with a cleared tree (first player random, or fixed if >= 0).
+ * d_action_out (optional) int32 [G] receives the sampled actions (-1 for inactive games). */
+int caro_engine_advance(caro_engine* e, int tau_plies, const double* d_uniform, int auto_restart,
+                        int first_player, int32_t* d_action_out, void* stream);
+
+/* Convenience: `moves` x (search, advance) enqueued back to back. */
+int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int moves, int count,
+                     int batch, int tau_plies, int auto_restart, int first_player, int net_impl,
+                     void* stream);
+
+/* Host copies of the 64-bit counters (synchronises `stream`): [0] leaf evaluations, [1] finished
+ * games, [2] plies played, [3] wins of player 0, [4] wins of player 1, [5] draws, [6] descents,
+ * [7] error flags (bit 0 arena full, bit 1 replay overrun, bit 2 illegal action sampled). */
+int caro_engine_counters(caro_engine* e, uint64_t h_out[8], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARO_B200_H_ */

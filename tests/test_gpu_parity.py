@@ -1,0 +1,256 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of
+libcaro_b200.so; the oracle is only the checker."""
+import numpy as np
+import pytest
+
+from harness import StubOracleTree, diff_tree, np_choice, oracle_for, random_position
+from helpers import oracle_game, plane_checksum
+from oracle.stubs import stub_priors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def product_game(tag, nk=None):
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    if tag == "connect4":
+        return ConnectFour()
+    if tag.startswith("mnk:"):
+        _, n, k = tag.split(":")
+        return TicTacToe(int(n), int(k))
+    return TicTacToe(int(nk[0]), int(nk[1]))
+
+
+# ------------------------------------------------------------------ rows a11-a16: board kernels
+def test_board_kernels_match_reference_playouts(torch_cuda, golden_games):
+    """Every transition of the reference-generated play-outs: next state, win flag, draw flag,
+    legal-move list and network planes are bit-exact."""
+    for block in golden_games:
+        g = product_game(block["game"])
+        steps = [st for game_steps in block["games"] for st in game_steps]
+        new_states, won, draw = g.apply_batch([st["s"] for st in steps], [st["a"] for st in steps], [st["p"] for st in steps])
+        assert new_states == [st["s2"] for st in steps]
+        assert [bool(w) for w in won] == [st["won"] for st in steps]
+        assert [bool(d) for d in draw] == [(not st["won"]) and len(st["legal2"]) == 0 for st in steps]
+        masks = g.legal_masks([st["s2"] for st in steps])
+        for m, st in zip(masks, steps):
+            assert [int(a) for a in np.nonzero(m)[0]] == st["legal2"]
+        planes_a = g.states_to_training_batch([st["s2"] for st in steps], [st["p"] for st in steps])
+        planes_b = g.states_to_training_batch([st["s2"] for st in steps], [1 - st["p"] for st in steps])
+        for i, st in enumerate(steps):
+            assert plane_checksum(np.stack([planes_a[i], planes_b[i]])) == st["planes"]
+
+
+def test_reference_unit_vectors_through_cuda(torch_cuda):
+    """The reference's own unit-test vectors, evaluated by the CUDA kernels."""
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    g = ConnectFour()
+    f = g.encode_lists([[0, 1, 1], [1, 0], [0, 1], [0, 0, 1], [0, 0], [1, 1, 1, 0], []])
+    s, won = g.move(f, 4, 0)  # test_connect_four.py:129-141
+    assert won is True and s == 3531389463375529686
+    f = g.encode_lists([[0, 0, 0, 1], [0, 0, 1], [0], [1], [], [], []])  # :106-116
+    assert g.move(f, 2, 1)[1] is True and g.move(f, 2, 0)[1] is False
+    assert g.possible_moves(0) == [] and g.possible_moves(g.initial_state) == [0, 1, 2, 3, 4, 5, 6]
+    with pytest.raises(AssertionError):
+        g.move(0, 3, 1)  # full column (connect_four.py:255)
+    t = TicTacToe(3, 3)
+    for board, mv, pl, expect in [("002112122", 2, 0, "000112122"), ("021012212", 6, 0, "021012012"),
+                                  ("021102212", 8, 0, "021102210"), ("120122012", 4, 0, "120102012"),
+                                  ("120102222", 6, 1, "120102122")]:  # test_tictactoe.py:121-144
+        nb, won = t.move(int(board), mv, pl)
+        assert won is True and nb == int(expect)
+    s = t.encode_game_state([[0, 1, 0], [2, 2, 0], [0, 1, 1]])
+    assert t.possible_moves(s) == [3, 4] and t.invalid_moves(s) == [0, 1, 2, 5, 6, 7, 8]
+    batch = t.states_to_training_batch([int("001010221"), int("101222001")], [1, 0])  # :61-98
+    b1 = [[[0, 0, 1], [0, 1, 0], [0, 0, 1]], [[1, 1, 0], [1, 0, 1], [0, 0, 0]]]
+    b2 = [[[0, 1, 0], [0, 0, 0], [1, 1, 0]], [[1, 0, 1], [0, 0, 0], [0, 0, 1]]]
+    np.testing.assert_equal(batch, [b1, b2])
+
+
+# ------------------------------------------------------------------ rows a1-a10: search parity
+def run_search_parity(torch, game, G, count, batch, plies_list, moves, seed, trees_per_game=1):
+    from caro_ai_b200.engine import SelfPlayEngine
+    rng = np.random.default_rng(seed)
+    og = oracle_for(game)
+    A = game.action_space
+    roots = [random_position(og, rng, int(plies_list[i % len(plies_list)])) for i in range(G)]
+    eng = SelfPlayEngine(game, G, trees_per_game=trees_per_game, max_batch=batch, node_capacity=count * batch * moves + 8, seed=seed)
+    eng.set_roots([r[0] for r in roots], [r[1] for r in roots])
+    trees = [[StubOracleTree(og) for _ in range(trees_per_game)] for _ in range(G)]
+    states = [r[0] for r in roots]
+    players = [r[1] for r in roots]
+    alive = [True] * G
+    for move in range(moves):
+        for i in range(count):
+            noise = rng.dirichlet([0.3] * A, size=(G, batch))
+            eng.select(batch, i, torch.from_numpy(noise).cuda())
+            eng.plan(batch)
+            n = eng.leaf_count()
+            planes = eng.leaf_planes(n).cpu().numpy()
+            pri, val = stub_priors(planes, A) if n else (np.zeros((1, A), np.float32), np.zeros(1, np.float32))
+            eng.expand_backup(batch, torch.from_numpy(np.ascontiguousarray(pri)).cuda(), torch.from_numpy(np.ascontiguousarray(val)).cuda())
+            for g in range(G):
+                if alive[g]:
+                    trees[g][players[g] if trees_per_game == 2 else 0].minibatch(batch, states[g], players[g], noise[g])
+        # trees
+        for g in range(G):
+            if not alive[g]:
+                continue
+            for t in range(trees_per_game):
+                errs = diff_tree(eng.export_tree(g * trees_per_game + t), trees[g][t], A)
+                assert not errs, "game %d move %d tree %d: %s" % (g, move, t, errs[:5])
+        # policy + sampling with injected uniforms (lib/utils.py:80-83)
+        tau_plies = 1
+        pi_d, q_d, n_d = eng.root_policy(2, tau_plies)
+        pi_d, q_d = pi_d.cpu().numpy(), q_d.cpu().numpy()
+        plies_dev = eng.region("ply").cpu().numpy()
+        u = rng.random(G)
+        actions = eng.advance(tau_plies, torch.from_numpy(u).cuda()).cpu().numpy()
+        for g in range(G):
+            if not alive[g]:
+                assert actions[g] == -1
+                continue
+            tree = trees[g][players[g] if trees_per_game == 2 else 0]
+            tau = 1 if plies_dev[g] < tau_plies else 0
+            pi, q = tree.get_policy_value(states[g], tau=tau)
+            assert [float(x) for x in pi] == pi_d[g].tolist(), "policy differs, game %d" % g
+            np.testing.assert_allclose(np.array([float(x) for x in q]), q_d[g], atol=1e-6)
+            a = np_choice(pi, u[g])
+            assert a == actions[g], "sampled action differs, game %d" % g
+            states[g], won = og.move(states[g], a, players[g])
+            players[g] = 1 - players[g]
+            if won or not og.possible_moves(states[g]):
+                alive[g] = False
+        st_dev, pl_dev = eng.roots()
+        status = eng.region("status").cpu().numpy()
+        for g in range(G):
+            assert st_dev[g] == states[g]
+            assert (status[g] == 0) == alive[g]
+            if alive[g]:
+                assert pl_dev[g] == players[g]
+    assert eng.counters()["errors"] == 0
+    eng.close()
+
+
+def test_search_parity_connect4(torch_cuda):
+    from caro_ai_b200.game import ConnectFour
+    run_search_parity(torch_cuda, ConnectFour(), G=24, count=10, batch=8, plies_list=[0, 1, 4, 9, 16, 25, 32, 36], moves=3, seed=11)
+
+
+def test_search_parity_connect4_two_trees(torch_cuda):
+    from caro_ai_b200.game import ConnectFour
+    run_search_parity(torch_cuda, ConnectFour(), G=8, count=6, batch=8, plies_list=[0, 6, 20], moves=4, seed=12, trees_per_game=2)
+
+
+def test_search_parity_tictactoe(torch_cuda):
+    from caro_ai_b200.game import TicTacToe
+    run_search_parity(torch_cuda, TicTacToe(3, 3), G=24, count=12, batch=8, plies_list=[0, 1, 2, 3, 4, 5], moves=4, seed=13)
+
+
+def test_search_parity_mnk_5_4(torch_cuda):
+    from caro_ai_b200.game import TicTacToe
+    run_search_parity(torch_cuda, TicTacToe(5, 4), G=8, count=8, batch=8, plies_list=[0, 4, 10, 16], moves=2, seed=14)
+
+
+def test_search_parity_caro_15_5(torch_cuda):
+    from caro_ai_b200.game import TicTacToe
+    run_search_parity(torch_cuda, TicTacToe(15, 5), G=4, count=4, batch=8, plies_list=[0, 30, 120], moves=2, seed=15)
+
+
+def test_search_parity_batch16(torch_cuda):
+    """evaluate()'s 20x16 shape (train.py:141)."""
+    from caro_ai_b200.game import ConnectFour
+    run_search_parity(torch_cuda, ConnectFour(), G=6, count=5, batch=16, plies_list=[0, 8], moves=2, seed=16)
+
+
+# ------------------------------------------------------------------ row a17: network
+CKPT = {"connect4": "connect4_best_026_12000.dat", "mnk": "tictactoe_best_005_00900.dat"}
+
+
+def _net_cases():
+    import os
+    import torch
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import Net
+    from conftest import GOLDEN
+    cases = []
+    for tag, game, ck in [("c4-trained", ConnectFour(), CKPT["connect4"]), ("c4-random", ConnectFour(), None),
+                          ("ttt-trained", TicTacToe(3, 3), CKPT["mnk"]), ("mnk54-random", TicTacToe(5, 4), None),
+                          ("caro-random", TicTacToe(15, 5), None)]:
+        torch.manual_seed(0)
+        net = Net(game.obs_shape, game.action_space)
+        if ck:
+            net.load_state_dict(torch.load(os.path.join(GOLDEN, "checkpoints", ck), map_location="cpu"))
+        else:  # make BatchNorm statistics non-trivial so that folding is actually exercised
+            with torch.no_grad():
+                for m in net.modules():
+                    if isinstance(m, torch.nn.BatchNorm2d):
+                        m.running_mean.uniform_(-0.3, 0.3)
+                        m.running_var.uniform_(0.5, 1.5)
+                        m.weight.uniform_(0.5, 1.5)
+                        m.bias.uniform_(-0.2, 0.2)
+        net.eval()
+        cases.append((tag, game, net))
+    return cases
+
+
+def _reference_outputs(game, net, states, players):
+    """Plain PyTorch fp32 (eval-mode) reference: lib/model.py forward + softmax of lib/mcts.py:216."""
+    import torch
+    og = oracle_for(game)
+    planes = torch.tensor(og.states_to_training_batch(states, players))
+    with torch.no_grad():
+        logits, val = net(planes)
+        return torch.softmax(logits, dim=1).numpy(), val.numpy()[:, 0]
+
+
+@pytest.mark.parametrize("impl,atol", [(1, 2e-5), (0, 1e-3)])
+def test_net_matches_fp32_reference(torch_cuda, impl, atol):
+    """impl 1: fp32 SIMT tower (tolerance 2e-5); impl 0: bf16 tcgen05 tower, tolerance 1e-3 absolute on
+    priors and values as stated in BASELINE.json north_star."""
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(3)
+    for tag, game, net in _net_cases():
+        og = oracle_for(game)
+        cells = game.obs_shape[1] * game.obs_shape[2]
+        count = 300 if cells < 100 else 40
+        pos = [random_position(og, rng, int(rng.integers(0, max(1, cells - 4)))) for _ in range(count)]
+        states, players = [p[0] for p in pos], [p[1] for p in pos]
+        ref_p, ref_v = _reference_outputs(game, net, states, players)
+        dn = DeviceNet(net, game)
+        p, v = dn.forward_states(states, players, impl=impl)
+        p, v = p.cpu().numpy(), v.cpu().numpy()
+        assert np.isfinite(p).all() and np.isfinite(v).all(), tag
+        np.testing.assert_allclose(p, ref_p, atol=atol, rtol=0, err_msg=tag)
+        np.testing.assert_allclose(v, ref_v, atol=atol, rtol=0, err_msg=tag)
+        np.testing.assert_allclose(p.sum(axis=1), 1.0, atol=1e-5)
+        dn.close()
+
+
+def test_checkpoint_format_roundtrip(torch_cuda, tmp_path, golden_net):
+    """saves/*.dat contract: the product Net has the reference's key set / shapes, loads a reference
+    checkpoint, and writes one the reference layout accepts (train.py:214-216, play.py:29-35)."""
+    import os
+    import torch
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import Net, load_checkpoint, save_checkpoint
+    from conftest import GOLDEN
+    g = ConnectFour()
+    net = load_checkpoint(os.path.join(GOLDEN, "checkpoints", CKPT["connect4"]), g)
+    case = [c for c in golden_net if c["checkpoint"] and c["game"] == "connect4"][0]
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == case["keys"]
+    net.eval()
+    ref_p, ref_v = _reference_outputs(g, net, case["states"], case["players"])
+    want = torch.softmax(torch.tensor(case["logits"]), dim=1).numpy()
+    np.testing.assert_allclose(ref_p, want, atol=1e-5)  # same numbers the reference's Net produced
+    np.testing.assert_allclose(ref_v, np.array(case["values"]), atol=1e-5)
+    path = str(tmp_path / "best_001_00100.dat")
+    save_checkpoint(net, path)
+    sd = torch.load(path, map_location="cpu")
+    assert list(sd.keys()) == list(case["keys"].keys())
