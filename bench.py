@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""Benchmark of the MCTS self-play hot path (BASELINE.json: Connect4 leaf evals/s + games/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA engine (this repo)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU algorithm
+
+One "step" = one ply of lock-step self-play for every game of the batch: MCTS.search_batch(100, 8)
+(= 800 descents, lib/mcts.py:162-176) on each of the G games, then the policy / sampling / move of
+lib/utils.py:76-99, finished games re-seated immediately.  Workload = BASELINE.json configs[1]:
+Connect4 6x7, 800 sims/move, 4096 concurrent games per B200, random-init 5x64 residual network,
+tau = 1 for 10 plies, c_puct 1.0, Dirichlet(0.3) eps 0.25.  Synthetic: no dataset, seeded weights.
+
+Prints ONE JSON line (see the keys in DESIGN.md section 7).  Multi-GPU: one process per GPU under
+torchrun, games sharded by rank, no data-path collective (weak scaling); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_LEAF_C4 = 15598672  # conv_in 96,768*... + 5 x 3,096,576*... + heads (2 x MAC)
+SIMS_COUNT, SIMS_BATCH, TAU_PLIES = 100, 8, 10
+GAMES_PER_GPU = 4096
+NODE_CAPACITY = 24576
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons of one GPU during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_worker(args):
+    """One process of the reference arm / cpu_baseline: the oracle port of lib/utils.py:play_game +
+    lib/mcts.py + lib/model.py (train-mode BatchNorm and autograd left on, exactly as the reference
+    runs its self-play), timed per ply.  Returns (leaf_evals, plies, games, seconds)."""
+    seed, steps, warmup, threads = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(threads)
+    from oracle.games import ConnectFourOracle
+    from oracle.mcts import OracleMCTS
+    from oracle.net import OracleNet
+    np.random.seed(seed)
+    torch.manual_seed(0)
+    game = ConnectFourOracle()
+    net = OracleNet(game.obs_shape, game.action_space)
+    counter = {"rows": 0}
+    fwd = net.forward
+
+    def counting_forward(x):
+        counter["rows"] += int(x.shape[0])
+        return fwd(x)
+
+    net.forward = counting_forward
+    state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), OracleMCTS(game), 0
+    leaf = plies = games = 0
+    t0 = None
+    for step in range(warmup + steps):
+        if step == warmup:
+            t0 = time.perf_counter()
+            counter["rows"] = 0
+            plies = games = 0
+        tree.search_batch(SIMS_COUNT, SIMS_BATCH, state, cur, net)
+        pi, _ = tree.get_policy_value(state, tau=1 if ply < TAU_PLIES else 0)
+        action = int(np.random.choice(game.action_space, p=pi))
+        state, won = game.move(state, action, cur)
+        cur = 1 - cur
+        plies += 1
+        ply += 1
+        if won or not game.possible_moves(state):
+            games += 1
+            state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), OracleMCTS(game), 0
+    dt = time.perf_counter() - t0
+    leaf = counter["rows"]
+    return leaf, plies, games, dt
+
+
+def run_cpu_reference(steps, warmup, procs, threads):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(1000 + i, steps, warmup, threads) for i in range(procs)]
+    if procs == 1:
+        res = [cpu_reference_worker(jobs[0])]
+    else:
+        with ctx.Pool(procs) as pool:
+            res = pool.map(cpu_reference_worker, jobs)
+    leaf = sum(r[0] for r in res)
+    plies = sum(r[1] for r in res)
+    games = sum(r[2] for r in res)
+    dt = max(r[3] for r in res)
+    return {"leaf_evals_per_s": leaf / dt, "plies_per_s": plies / dt, "games_per_s": games / dt, "seconds": dt,
+            "leaf_evals": leaf, "plies": plies}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    procs = max(1, cores)
+    r = run_cpu_reference(args.steps, args.warmup, procs, 1)
+    line = {
+        "impl": "reference", "metric": "connect4_mcts_leaf_evals_per_sec", "value": r["leaf_evals_per_s"], "unit": "leaf_evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, random-init 5x64 net, CPU",
+                   "games": procs, "sims_per_move": SIMS_COUNT * SIMS_BATCH},
+        "games_per_sec": r["games_per_s"], "plies_per_sec": r["plies_per_s"],
+        "cpu_baseline": {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": procs, "kind": "port",
+                         "sample": "%d processes x %d plies of oracle self-play (search_batch(100,8) per ply), 1 torch thread each"
+                                   % (procs, args.steps)},
+        "e2e": {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------- CUDA engine
+def engine_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import DeviceNet, Net
+
+    game = ConnectFour()
+    torch.manual_seed(0)
+    net = Net(game.obs_shape, game.action_space).eval()
+    dnet = DeviceNet(net, game)
+    G = args.games
+    eng = SelfPlayEngine(game, G, trees_per_game=1, max_batch=SIMS_BATCH, node_capacity=args.node_capacity,
+                         replay_capacity=1 << 20, seed=1234 + rank)
+    # stagger game phases so that the timed window sees the steady-state mix of plies, not 4096 openings
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def kernel_steps(n):
+        eng.play(dnet, dnet, moves=n, count=SIMS_COUNT, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+
+    # untimed pre-roll with a cheap search so that the games de-synchronise (finished games re-seat at once):
+    # the timed window then sees a mix of openings, middle games and endgames instead of 4096 identical plies
+    eng.play(dnet, dnet, moves=args.preroll, count=8, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+    kernel_steps(args.warmup)
+    barrier()
+    c0 = eng.counters()
+    eng.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    kernel_steps(args.steps)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    c1 = eng.counters()
+
+    # ---- end-to-end: same plies driven through HOST buffers (pinned H2D of the roots, D2H of the results)
+    boards_h = torch.empty((G, 2), dtype=torch.int64).pin_memory()
+    players_h = torch.empty((G,), dtype=torch.uint8).pin_memory()
+    out_h = {"pi": torch.empty((G, 7), dtype=torch.float64).pin_memory(), "actions": torch.empty((G,), dtype=torch.int32).pin_memory(),
+             "boards": boards_h, "players": players_h}
+    boards_h.copy_(eng.region("root_board"))
+    players_h.copy_(eng.region("root_player"))
+    torch.cuda.synchronize()
+    e2e_steps = max(1, args.steps // 2)
+    barrier()
+    ce0 = eng.counters()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(stream)
+    for _ in range(e2e_steps):
+        eng.step_host(boards_h, players_h, dnet, SIMS_COUNT, SIMS_BATCH, TAU_PLIES, out_h)
+        stream.synchronize()  # the host owns the buffers between plies (it reads pi / actions, re-submits roots)
+    ee1.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    e2e_ms = ee0.elapsed_time(ee1)
+    ce1 = eng.counters()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    leaf = allsum(c1["leaf_evals"] - c0["leaf_evals"])
+    games = allsum(c1["games"] - c0["games"])
+    plies = allsum(c1["plies"] - c0["plies"])
+    desc = allsum(c1["descents"] - c0["descents"])
+    ms_max = allmax(ms)
+    e2e_leaf = allsum(ce1["leaf_evals"] - ce0["leaf_evals"])
+    e2e_max = allmax(e2e_ms)
+    errors = allsum(c1["errors"])
+    if rank == 0:
+        peaks = measured_peaks()
+        sec = ms_max / 1000.0
+        my_leaf = c1["leaf_evals"] - c0["leaf_evals"]
+        net_s = prof["net_ms"] / 1000.0
+        n_net_launches = args.steps * SIMS_COUNT
+        achieved_tflops = my_leaf * FLOP_PER_LEAF_C4 / net_s / 1e12 if net_s > 0 else 0.0
+        line = {
+            "metric": "connect4_mcts_leaf_evals_per_sec", "value": leaf / sec, "unit": "leaf_evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, %d concurrent games per GPU, "
+                                   "random-init 5x64 residual net (bf16 tcgen05, fp32 accumulate), tau=1 for 10 plies" % G,
+                       "games_per_gpu": G, "sims_per_move": SIMS_COUNT * SIMS_BATCH, "node_capacity": args.node_capacity,
+                       "cache": "tree arenas %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                                % (eng.workspace_bytes / 1e9)},
+            "games_per_sec": games / sec, "plies_per_sec": plies / sec, "descents_per_sec": desc / sec,
+            "e2e": {"value": e2e_leaf / (e2e_max / 1000.0), "unit": "leaf_evals/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(world * (boards_h.numel() * 8 + players_h.numel())),
+                    "d2h_bytes_per_step": int(world * (out_h["pi"].numel() * 8 + out_h["actions"].numel() * 4 + boards_h.numel() * 8 + players_h.numel()))},
+            "gpu_launches": int(prof["launches"]),
+            "roofline": {"kernel": "net_tc_kernel (tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
+                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),
+                         "avg_launch_ms": prof["net_ms"] / max(1, n_net_launches)},
+            "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")},
+            "clocks": sampler.summary(), "engine_errors": int(errors),
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            r = run_cpu_reference(args.cpu_plies, 1, 1, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "games_per_sec": r["games_per_s"],
+                                    "sample": "1 process, torch default threads, %d plies of oracle self-play "
+                                              "(search_batch(100,8) per ply) after 1 warm-up ply" % args.cpu_plies}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--node-capacity", type=int, default=NODE_CAPACITY)
+    ap.add_argument("--cpu-plies", type=int, default=20)
+    ap.add_argument("--preroll", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return engine_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

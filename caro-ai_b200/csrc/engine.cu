@@ -55,6 +55,19 @@ struct caro_engine {
   View<C4Board> v_c4;
   View<MnkBoard> v_mnk;
   MnkRules mnk;
+  // optional per-phase CUDA-event timing of the search loop (bench / roofline accounting)
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+  unsigned long long launches = 0;
+  cudaEvent_t next_event() {
+    if (events_used == events.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      events.push_back(ev);
+    }
+    return events[events_used++];
+  }
 };
 
 namespace {
@@ -222,7 +235,37 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
   return do_reset(e, nullptr, -1, 0, stream);
 }
 
-void caro_engine_destroy(caro_engine* e) { delete e; }
+void caro_engine_destroy(caro_engine* e) {
+  if (!e) return;
+  for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
+  delete e;
+}
+
+int caro_engine_profile(caro_engine* e, int enable) {
+  if (!e) return caro_fail(CARO_E_ARG, "null engine");
+  e->profiling = enable != 0;
+  e->events_used = 0;
+  e->launches = 0;
+  return CARO_OK;
+}
+
+int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launches, void* stream) {
+  if (!e || !h_ms) return caro_fail(CARO_E_ARG, "null argument");
+  cudaError_t ce = cudaStreamSynchronize(S(stream));
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  for (int i = 0; i < 4; ++i) h_ms[i] = 0.0;
+  for (size_t i = 0; i + 5 <= e->events_used; i += 5) {
+    for (int ph = 0; ph < 4; ++ph) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, e->events[i + ph], e->events[i + ph + 1]);
+      h_ms[ph] += (double)ms;
+    }
+  }
+  if (h_launches) *h_launches = e->launches;
+  e->events_used = 0;
+  e->launches = 0;
+  return CARO_OK;
+}
 
 int caro_engine_region(const caro_engine* e, const char* name, size_t* offset, size_t* bytes, int32_t* elem_bytes,
                        int64_t dims[4]) {
@@ -314,13 +357,20 @@ int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int 
   const int32_t* lc = c4 ? e->v_c4.leaf_count : e->v_mnk.leaf_count;
   float* pr = c4 ? e->v_c4.probs : e->v_mnk.probs;
   float* va = c4 ? e->v_c4.values : e->v_mnk.values;
+  const bool prof = e->profiling;
   for (int i = 0; i < count; ++i) {
+    if (prof) cudaEventRecord(e->next_event(), S(stream));
     int rc = caro_engine_select(e, batch, i, nullptr, nullptr, stream);
+    if (prof) cudaEventRecord(e->next_event(), S(stream));
     if (rc == CARO_OK) rc = caro_engine_plan(e, batch, stream);
+    if (prof) cudaEventRecord(e->next_event(), S(stream));
     if (rc == CARO_OK)
       rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, lb, lp, lc, (int64_t)e->dm.G * batch, pr, va, net_impl, stream);
+    if (prof) cudaEventRecord(e->next_event(), S(stream));
     if (rc == CARO_OK) rc = caro_engine_expand_backup(e, batch, pr, va, stream);
+    if (prof) cudaEventRecord(e->next_event(), S(stream));
     if (rc != CARO_OK) return rc;
+    e->launches += 4;
   }
   return CARO_OK;
 }
@@ -359,6 +409,7 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
     int rc = caro_engine_search(e, net, count, batch, net_impl, stream);
     if (rc == CARO_OK) rc = caro_engine_advance(e, tau_plies, nullptr, auto_restart, first_player, nullptr, stream);
     if (rc != CARO_OK) return rc;
+    e->launches += 1;
   }
   return CARO_OK;
 }

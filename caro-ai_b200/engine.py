@@ -172,6 +172,30 @@ class SelfPlayEngine:
         _cabi.check(_cabi.lib().caro_engine_play(self.handle, net_p0.handle, net_p1.handle, moves, count, batch, tau_plies,
                                                  1 if auto_restart else 0, first_player, impl, self._stream()))
 
+    def profile(self, enable: bool = True):
+        _cabi.check(_cabi.lib().caro_engine_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self) -> Dict[str, float]:
+        """Summed CUDA-event milliseconds per search phase since the last read (+ kernel launches)."""
+        ms = (C.c_double * 4)()
+        launches = C.c_uint64()
+        _cabi.check(_cabi.lib().caro_engine_profile_read(self.handle, C.byref(ms), C.byref(launches), self._stream()))
+        return {"select_ms": ms[0], "plan_ms": ms[1], "net_ms": ms[2], "expand_backup_ms": ms[3],
+                "launches": int(launches.value)}
+
+    def step_host(self, boards_pinned: torch.Tensor, players_pinned: torch.Tensor, net: DeviceNet, count: int, batch: int,
+                  tau_plies: int, out_pinned: Dict[str, torch.Tensor], impl: int = IMPL_TCGEN05):
+        """One ply for all games through HOST buffers (the end-to-end path): roots H2D from pinned memory,
+        search + advance on the device, then policy / actions / new roots D2H into pinned buffers."""
+        self.set_roots_pinned(boards_pinned, players_pinned)
+        self.search(net, count, batch, impl)
+        pi, q, n = self.root_policy(2, tau_plies)
+        actions = self.advance(tau_plies, None, auto_restart=True)
+        out_pinned["pi"].copy_(pi, non_blocking=True)
+        out_pinned["actions"].copy_(actions, non_blocking=True)
+        out_pinned["boards"].copy_(self.region("root_board"), non_blocking=True)
+        out_pinned["players"].copy_(self.region("root_player"), non_blocking=True)
+
     # ------------------------------------------------------------------ read-back
     COUNTER_NAMES = ("leaf_evals", "games", "plies", "wins_p0", "wins_p1", "draws", "descents", "errors")
 

@@ -185,6 +185,13 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
                      int batch, int tau_plies, int auto_restart, int first_player, int net_impl,
                      void* stream);
 
+/* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
+ * profile_read synchronises `stream` and returns the summed milliseconds of
+ * [0] select, [1] plan, [2] network forward, [3] expand+backup kernels since the last read, plus
+ * the number of engine kernels launched by search/play in that window. */
+int caro_engine_profile(caro_engine* e, int enable);
+int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launches, void* stream);
+
 /* Host copies of the 64-bit counters (synchronises `stream`): [0] leaf evaluations, [1] finished
  * games, [2] plies played, [3] wins of player 0, [4] wins of player 1, [5] draws, [6] descents,
  * [7] error flags (bit 0 arena full, bit 1 replay overrun, bit 2 illegal action sampled). */
