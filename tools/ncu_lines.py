@@ -1,0 +1,58 @@
+"""Attribute the warp-stall samples of an ncu report (--page source --csv) to CUDA source lines.
+Usage: python tools/ncu_lines.py <source.csv> <kernel-substring> [top]   (needs the built .so)"""
+import csv
+import os
+import re
+import subprocess
+import sys
+from collections import Counter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    src_csv, kern = sys.argv[1], sys.argv[2]
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+    tmp = "/tmp/sass_lines"
+    os.makedirs(tmp, exist_ok=True)
+    subprocess.run("cd %s && rm -f *.cubin && cuobjdump -xelf all %s/caro-ai_b200/libcaro_b200.so >/dev/null 2>&1" % (tmp, ROOT), shell=True)
+    off2line = {}
+    for f in os.listdir(tmp):
+        if not f.endswith(".cubin"):
+            continue
+        out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if kern not in out:
+            continue
+        cur, infn = None, False
+        for line in out.split("\n"):
+            if line.startswith(".text.") or line.strip().startswith(".section"):
+                infn = kern in line
+            m = re.search(r'//## File ".*?/([^/"]+)", line (\d+)', line)
+            if m:
+                cur = (m.group(1), int(m.group(2)))
+            m = re.search(r"/\*([0-9a-f]{4,5})\*/", line)
+            if m and infn and cur:
+                off2line.setdefault(int(m.group(1), 16), cur)
+    rows = list(csv.reader(open(src_csv)))
+    hdr = rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    data = rows[2:]
+    base = int(data[0][idx["Address"]], 16)
+    c, tot = Counter(), 0
+    for r in data:
+        s = int(r[idx["# Samples"]] or 0)
+        c[off2line.get(int(r[idx["Address"]], 16) - base, ("?", 0))] += s
+        tot += s
+    cache = {}
+    for (f, ln), s in c.most_common(top):
+        text = ""
+        for d in ("caro-ai_b200/csrc",):
+            p = os.path.join(ROOT, d, f)
+            if os.path.exists(p):
+                cache.setdefault(p, open(p).read().split("\n"))
+                text = cache[p][ln - 1].strip()[:100] if ln > 0 else ""
+        print("%7d %5.1f%% %s:%d  %s" % (s, 100.0 * s / max(1, tot), f, ln, text))
+
+
+if __name__ == "__main__":
+    main()
