@@ -32,16 +32,17 @@ namespace caro {
 constexpr int kTilesPerGroup = 4;
 constexpr int kTileRows = 128;
 constexpr int kGroupRows = kTilesPerGroup * kTileRows;  // 512 padded positions per CTA pass
-constexpr int kHalo = 32;                                // zero positions before / after (>= pitch + 1)
-constexpr int kActRows = kGroupRows + 2 * kHalo;         // 576
+constexpr int kHalo = 24;                                // zero positions before / after (>= pitch + 1)
+constexpr int kActRows = kGroupRows + 2 * kHalo;         // 560
 constexpr int kChunkBytes = kActRows * 16;               // one 8-channel chunk of all positions
-constexpr int kActBytes = 8 * kChunkBytes;               // 73,728
+constexpr int kActBytes = 8 * kChunkBytes;               // 71,680
 constexpr int kTapBytes = 8 * 64 * 16;                   // 8,192: one tap of a 64->64 layer
 constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of conv_in (K padded to 16)
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
 constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
-constexpr int kThreads = 128;
+constexpr int kEpiThreads = 128;                         // warps 0-3: epilogue (TMEM lane quarter = warp index)
+constexpr int kThreads = kEpiThreads + 32;               // warp 4: TMEM owner, weight producer, MMA issuer
 constexpr uint32_t kTmemCols = 512;
 
 struct TcGeom {
@@ -57,6 +58,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -70,6 +74,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
@@ -83,6 +88,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -117,21 +123,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N=64, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ float lrelu_tc(float x) { return x > 0.0f ? x : kLeaky * x; }
+__device__ __forceinline__ float lrelu_tc(float x) { return fmaxf(x, kLeaky * x); }
 
 struct TcSmem {
   // dynamic shared memory carve-up (byte offsets from a 128-aligned base)
   static constexpr int kAct = 0;
-  static constexpr int kWgt = kAct + kActBytes;
-  static constexpr int kBias = kWgt + kLayerBytes;                 // float [6][64]
+  static constexpr int kWgt = kAct + kActBytes;                    // 2 layer images (double buffer)
+  static constexpr int kBias = kWgt + 2 * kLayerBytes;             // float [6][64]
   static constexpr int kHeadW = kBias + kNumLayers * 64 * 4;       // float [3][64] + [3] biases (+pad)
   static constexpr int kHeadF = kHeadW + 4 * 64 * 4;               // float [512][3] head features
-  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float scratch: hidden[32 boards][20] / logits
-  static constexpr int kBars = kFc + 32 * 20 * 4 + 2 * 256 * 4;    // 2 mbarriers + tmem base
-  static constexpr int kTotal = kBars + 64;
+  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[32][20] then logits[512]... (640 floats)
+  static constexpr int kBars = kFc + 640 * 4;                      // mbarriers + tmem base
+  static constexpr int kTotal = kBars + 128;
 };
+static_assert(TcSmem::kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // ------------------------------------------------------------------------------------- kernel
+// Roles: warps 0-3 = epilogue (warp w owns TMEM lanes [32w, 32w+32) = rows 32w.. of every tile),
+//        warp 4    = TMEM allocation, weight streaming (cp.async.bulk) and single-thread MMA issue.
+// Pipeline per layer L (tiles t = 0..3, in-place activation buffer):
+//   MMA(L,t)  needs act_ready[t-1..t+1] of the previous stage (their bf16 rows + tile t's accumulator drained)
+//   EPI(L,t)  needs acc_full[min(t+1,3)]  (tile t+1 reads the last rows of tile t as its halo)
+// so the epilogue of tile t runs underneath the MMAs of tile t+2 / the next layer's tile t-1.
 template <class R>
 __global__ void __launch_bounds__(kThreads, 1)
 net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
@@ -145,9 +158,10 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   float* headw_s = reinterpret_cast<float*>(smem + TcSmem::kHeadW);
   float* headf_s = reinterpret_cast<float*>(smem + TcSmem::kHeadF);
   float* fc_s = reinterpret_cast<float*>(smem + TcSmem::kFc);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + TcSmem::kBars);
-  uint64_t* bar_mma = bar_w + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + TcSmem::kBars);  // [2] weights buffer filled
+  uint64_t* bar_acc = bar_w + 2;                                        // [4] accumulator tile complete
+  uint64_t* bar_act = bar_w + 6;                                        // [4] activation tile rewritten / accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 10);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -155,6 +169,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   const int nb = gm.boards_per_group;
   const long long n_groups = (count + nb - 1) / nb;
   if ((long long)blockIdx.x >= n_groups) return;  // uniform per CTA, before any barrier / TMEM use
+  const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
@@ -168,220 +183,243 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     headw_s[192] = blob[L.val_conv_b];
     headw_s[193] = blob[L.pol_conv_b];
     headw_s[194] = blob[L.pol_conv_b + 1];
-    mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(bar_w + 0, 1);
+    mbar_init(bar_w + 1, 1);
+    for (int t = 0; t < 4; ++t) {
+      mbar_init(bar_acc + t, 1);
+      mbar_init(bar_act + t, kEpiThreads);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 4) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t act_addr = smem_u32(act);
-  const uint32_t wgt_addr = smem_u32(wgt);
-  uint32_t ph_w = 0, ph_mma = 0;
 
-  // per-thread geometry of its 4 rows (row p = 128*t + tid)
-  int row_board[kTilesPerGroup], row_cell[kTilesPerGroup];  // board index in group, r*W+c (or -1 if padding)
+  if (warp == 4) {
+    // =============================== producer / MMA issuer (one thread) ===============================
+    if ((tid & 31) == 0) {
+      const uint32_t act_addr = smem_u32(act);
+      const uint32_t wgt_addr = smem_u32(wgt);
+      const int total_layers = my_groups * kNumLayers;
+      auto load_layer = [&](int gl) {  // global layer index -> buffer gl & 1
+        const int l = gl % kNumLayers;
+        uint8_t* dst = wgt + (gl & 1) * kLayerBytes;
+        uint64_t* bar = bar_w + (gl & 1);
+        if (l == 0) {
+          mbar_expect_tx(bar, kLayerBytesIn);
+          for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar);
+        } else {
+          mbar_expect_tx(bar, kLayerBytes);
+          const uint8_t* src = wimg + kLayerBytesIn + (size_t)(l - 1) * kLayerBytes;
+          for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar);
+        }
+      };
+      load_layer(0);
+      if (total_layers > 1) load_layer(1);
+      int shift[9];
 #pragma unroll
-  for (int t = 0; t < kTilesPerGroup; ++t) {
-    const int p = t * kTileRows + tid;
-    const int b = p / gm.block, within = p - b * gm.block;
-    const int r = within / gm.pitch, c = within - r * gm.pitch;
-    const bool real = b < nb && r < gm.H && c < gm.W;
-    row_board[t] = b;
-    row_cell[t] = real ? r * gm.W + c : -1;
-  }
-
-  // first layer's weights for the first group
-  if (tid == 0) {
-    mbar_expect_tx(bar_w, kLayerBytesIn);
-    for (int tap = 0; tap < 9; ++tap) bulk_g2s(wgt + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar_w);
-  }
-
-  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const long long leaf0 = grp * nb;
-    // ---- input planes -> bf16 activations, channels 0/1 (chunk 0), chunk 1 = zeros ---------
-#pragma unroll
-    for (int t = 0; t < kTilesPerGroup; ++t) {
-      const int p = t * kTileRows + tid;
-      uint32_t lo = 0u;
-      const long long leaf = leaf0 + row_board[t];
-      if (row_cell[t] >= 0 && leaf < count) {
-        const typename R::Board s = boards[leaf];
-        const int wm = who[leaf];
-        const int r = row_cell[t] / gm.W, c = row_cell[t] - r * gm.W;
-        const uint32_t mine = rules.plane_value(s, wm, 0, r, c) ? 0x3F80u : 0u;   // bf16(1.0)
-        const uint32_t other = rules.plane_value(s, wm, 1, r, c) ? 0x3F80u : 0u;
-        lo = mine | (other << 16);
-      }
-      *reinterpret_cast<uint4*>(act + (size_t)(0 * kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(act + (size_t)(1 * kActRows + kHalo + p) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    float hv[kTilesPerGroup], hp0[kTilesPerGroup], hp1[kTilesPerGroup];
-    for (int layer = 0; layer < kNumLayers; ++layer) {
-      const int ksteps = layer == 0 ? 1 : 4;
-      const int tap_bytes = layer == 0 ? kTapBytesIn : kTapBytes;
-      // ---- MMA issue (one thread) ---------------------------------------------------------
-      if (tid == 0) {
-        mbar_wait(bar_w, ph_w);
-        tc_fence_after();
+      for (int tap = 0; tap < 9; ++tap) shift[tap] = (tap / 3 - 1) * gm.pitch + (tap % 3 - 1);
+      for (int gl = 0; gl < total_layers; ++gl) {
+        const int l = gl % kNumLayers;
+        const int ksteps = l == 0 ? 1 : 4;
+        const uint32_t tap_bytes = l == 0 ? kTapBytesIn : kTapBytes;
+        const uint32_t wbase = wgt_addr + (uint32_t)(gl & 1) * kLayerBytes;
+        mbar_wait(bar_w + (gl & 1), (uint32_t)(gl >> 1) & 1u);
+        const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
         for (int t = 0; t < kTilesPerGroup; ++t) {
+          if (t == 0) {
+            mbar_wait(bar_act + 0, act_par);
+            mbar_wait(bar_act + 1, act_par);
+          } else if (t < kTilesPerGroup - 1) {
+            mbar_wait(bar_act + t + 1, act_par);
+          }
+          tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * 64);
           uint32_t acc = 0u;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int shift = (tap / 3 - 1) * gm.pitch + (tap % 3 - 1);
-            const uint32_t a_row = (uint32_t)(kHalo + t * kTileRows + shift);
+            const uint32_t a0 = act_addr + (uint32_t)(kHalo + t * kTileRows + shift[tap]) * 16u;
+            const uint32_t b0 = wbase + (uint32_t)tap * tap_bytes;
             for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t adesc = make_desc(act_addr + (uint32_t)((2 * kk) * kActRows + a_row) * 16u, kChunkBytes, 128u);
-              const uint64_t bdesc = make_desc(wgt_addr + (uint32_t)(tap * tap_bytes + kk * 2048), 1024u, 128u);
-              umma_bf16(d_tmem, adesc, bdesc, kIdesc, acc);
+              umma_bf16(d_tmem, make_desc(a0 + (uint32_t)kk * (2u * kChunkBytes), kChunkBytes, 128u),
+                        make_desc(b0 + (uint32_t)kk * 2048u, 1024u, 128u), kIdesc, acc);
               acc = 1u;
             }
           }
-        }
-        umma_commit(bar_mma);
-      }
-      ph_w ^= 1u;
-      // ---- wait for the accumulators ------------------------------------------------------
-      mbar_wait(bar_mma, ph_mma);
-      ph_mma ^= 1u;
-      tc_fence_after();
-      // weights buffer is free again: stream in the next layer (or next group's conv_in)
-      if (tid == 0) {
-        const int nl = layer + 1;
-        const bool more_groups = grp + gridDim.x < n_groups;
-        if (nl < kNumLayers) {
-          mbar_expect_tx(bar_w, kLayerBytes);
-          const uint8_t* src = wimg + kLayerBytesIn + (size_t)(nl - 1) * kLayerBytes;
-          for (int tap = 0; tap < 9; ++tap) bulk_g2s(wgt + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar_w);
-        } else if (more_groups) {
-          mbar_expect_tx(bar_w, kLayerBytesIn);
-          for (int tap = 0; tap < 9; ++tap) bulk_g2s(wgt + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar_w);
+          umma_commit(bar_acc + t);
+          // after tile 1 has been issued every MMA of layer gl-1 is known complete (tile 1 waited on the
+          // epilogue of tile 2, which waited on the last commit of layer gl-1): its weight buffer is free
+          if (t == 1 && gl >= 1 && gl + 1 < total_layers) load_layer(gl + 1);
         }
       }
-      __syncwarp();  // tcgen05.ld/st are .sync.aligned: re-converge after the single-thread branches / spin waits
-      // ---- epilogue: bias + LeakyReLU (+ residual), fp32 stream -> TMEM, bf16 copy -> smem ---
-      const bool last = layer == kNumLayers - 1;
-      const float* bl = bias_s + layer * 64;
-#pragma unroll
-      for (int t = 0; t < kTilesPerGroup; ++t) {
-        const int p = t * kTileRows + tid;
-        const bool real = row_cell[t] >= 0;
-        float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-          const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + ch * 16);
-          const uint32_t a_res = tmem_base + lane_base + (uint32_t)(256 + t * 64 + ch * 16);
-          uint32_t ra[16], rr[16];
-          TMEM_LD16(a_acc, ra);
-          if (layer > 0) TMEM_LD16(a_res, rr);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t packed[8];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = lrelu_tc(__uint_as_float(ra[j]) + bl[ch * 16 + j]);
-            if (layer > 0) v += __uint_as_float(rr[j]);
-            rr[j] = __float_as_uint(v);
-            if (last) {
-              av = fmaf(v, headw_s[ch * 16 + j], av);
-              ap0 = fmaf(v, headw_s[64 + ch * 16 + j], ap0);
-              ap1 = fmaf(v, headw_s[128 + ch * 16 + j], ap1);
-            }
-          }
-          if (!last) {
-            TMEM_ST16(a_res, rr);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
-              packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
-            }
-            *reinterpret_cast<uint4*>(act + (size_t)((2 * ch) * kActRows + kHalo + p) * 16) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(act + (size_t)((2 * ch + 1) * kActRows + kHalo + p) * 16) =
-                make_uint4(packed[4], packed[5], packed[6], packed[7]);
-          }
-        }
-        hv[t] = av;
-        hp0[t] = ap0;
-        hp1[t] = ap1;
-      }
-      if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
     }
-
-    // ---- heads ------------------------------------------------------------------------------
-    const int HW = gm.H * gm.W;
+  } else {
+    // ========================================= epilogue warps =========================================
+    // geometry of this thread's row in each tile (row p = 128*t + tid)
+    int row_board[kTilesPerGroup], row_cell[kTilesPerGroup];
 #pragma unroll
     for (int t = 0; t < kTilesPerGroup; ++t) {
       const int p = t * kTileRows + tid;
-      headf_s[p * 3 + 0] = lrelu_tc(hv[t] + headw_s[192]);
-      headf_s[p * 3 + 1] = lrelu_tc(hp0[t] + headw_s[193]);
-      headf_s[p * 3 + 2] = lrelu_tc(hp1[t] + headw_s[194]);
+      const int b = p / gm.block, within = p - b * gm.block;
+      const int r = within / gm.pitch, c = within - r * gm.pitch;
+      const bool real = b < nb && r < gm.H && c < gm.W;
+      row_board[t] = b;
+      row_cell[t] = real ? r * gm.W + c : -1;
     }
-    __syncthreads();
-    const int nvalid = (int)min((long long)nb, count - leaf0);
-    float* hid = fc_s;                 // [nb][20]
-    float* logit = fc_s + 32 * 20;     // [<=512] logits, processed board by board
-    // value head FC1 (HW -> 20) for all boards of the group
-    for (int o = tid; o < nvalid * 20; o += kThreads) {
-      const int b = o / 20, i = o - b * 20;
-      float acc = blob[L.val_fc1_b + i];
-      const float* wrow = blob + L.val_fc1_w + (size_t)i * HW;
-      for (int cell = 0; cell < HW; ++cell) {
-        const int r = cell / gm.W, c = cell - r * gm.W;
-        acc = fmaf(wrow[cell], headf_s[(b * gm.block + r * gm.pitch + c) * 3], acc);
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int HW = gm.H * gm.W;
+
+    auto write_inputs = [&](long long leaf0) {
+#pragma unroll
+      for (int t = 0; t < kTilesPerGroup; ++t) {
+        const int p = t * kTileRows + tid;
+        uint32_t lo = 0u;
+        const long long leaf = leaf0 + row_board[t];
+        if (row_cell[t] >= 0 && leaf < count) {
+          const typename R::Board s = boards[leaf];
+          const int wm = who[leaf];
+          const int r = row_cell[t] / gm.W, c = row_cell[t] - r * gm.W;
+          const uint32_t mine = rules.plane_value(s, wm, 0, r, c) ? 0x3F80u : 0u;  // bf16(1.0)
+          const uint32_t other = rules.plane_value(s, wm, 1, r, c) ? 0x3F80u : 0u;
+          lo = mine | (other << 16);
+        }
+        *reinterpret_cast<uint4*>(act + (size_t)(0 * kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + (size_t)(1 * kActRows + kHalo + p) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        fence_async_smem();
+        mbar_arrive(bar_act + t);
       }
-      hid[o] = lrelu_tc(acc);
-    }
-    __syncthreads();
-    for (int b = tid; b < nvalid; b += kThreads) {
-      float acc = blob[L.val_fc2_b];
-      for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
-      values[leaf0 + b] = tanhf(acc);
-    }
-    // policy head FC (2*HW -> A) + softmax, one board at a time (A can be 225)
-    for (int b = 0; b < nvalid; ++b) {
-      for (int a = tid; a < gm.A; a += kThreads) {
-        float acc = blob[L.pol_fc_b + a];
-        for (int chn = 0; chn < 2; ++chn)
-          for (int cell = 0; cell < HW; ++cell) {
-            const int r = cell / gm.W, c = cell - r * gm.W;
-            acc = fmaf(pol_fc_t[(size_t)(chn * HW + cell) * gm.A + a], headf_s[(b * gm.block + r * gm.pitch + c) * 3 + 1 + chn], acc);
+    };
+
+    write_inputs((long long)blockIdx.x * nb);
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const long long grp = blockIdx.x + (long long)gi * gridDim.x;
+      const long long leaf0 = grp * nb;
+      float hv[kTilesPerGroup], hp0[kTilesPerGroup], hp1[kTilesPerGroup];
+      for (int layer = 0; layer < kNumLayers; ++layer) {
+        const int gl = gi * kNumLayers + layer;
+        const uint32_t acc_par = (uint32_t)gl & 1u;
+        const bool last = layer == kNumLayers - 1;
+        const float* bl = bias_s + layer * 64;
+#pragma unroll
+        for (int t = 0; t < kTilesPerGroup; ++t) {
+          mbar_wait(bar_acc + (t + 1 < kTilesPerGroup ? t + 1 : kTilesPerGroup - 1), acc_par);
+          __syncwarp();
+          tc_fence_after();
+          const int p = t * kTileRows + tid;
+          const bool real = row_cell[t] >= 0;
+          float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + ch * 16);
+            const uint32_t a_res = tmem_base + lane_base + (uint32_t)(256 + t * 64 + ch * 16);
+            uint32_t ra[16], rr[16];
+            TMEM_LD16(a_acc, ra);
+            if (layer > 0) TMEM_LD16(a_res, rr);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = lrelu_tc(__uint_as_float(ra[j]) + bl[ch * 16 + j]);
+              if (layer > 0) v += __uint_as_float(rr[j]);
+              rr[j] = __float_as_uint(v);
+              if (last) {
+                av = fmaf(v, headw_s[ch * 16 + j], av);
+                ap0 = fmaf(v, headw_s[64 + ch * 16 + j], ap0);
+                ap1 = fmaf(v, headw_s[128 + ch * 16 + j], ap1);
+              }
+            }
+            if (!last) {
+              TMEM_ST16(a_res, rr);
+              uint32_t packed[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
+                packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+              }
+              *reinterpret_cast<uint4*>(act + (size_t)((2 * ch) * kActRows + kHalo + p) * 16) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              *reinterpret_cast<uint4*>(act + (size_t)((2 * ch + 1) * kActRows + kHalo + p) * 16) =
+                  make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
           }
-        logit[a] = acc;
+          if (!last) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_act + t);
+          } else {
+            hv[t] = av;
+            hp0[t] = ap0;
+            hp1[t] = ap1;
+          }
+        }
       }
-      __syncthreads();
-      if (warp == 0) {
+      // ---- 1x1 head convolutions (per row), then hand the tensor pipe its next group -----------
+#pragma unroll
+      for (int t = 0; t < kTilesPerGroup; ++t) {
+        const int p = t * kTileRows + tid;
+        headf_s[p * 3 + 0] = lrelu_tc(hv[t] + headw_s[192]);
+        headf_s[p * 3 + 1] = lrelu_tc(hp0[t] + headw_s[193]);
+        headf_s[p * 3 + 2] = lrelu_tc(hp1[t] + headw_s[194]);
+      }
+      tc_fence_before();  // the last layer's accumulators have been read (wait::ld above)
+      if (gi + 1 < my_groups) write_inputs((blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb);
+      epi_bar_sync();
+      // ---- fully connected heads: all (board, output) pairs in parallel ----------------------------
+      const int nvalid = (int)min((long long)nb, count - leaf0);
+      const int per_board = 20 + gm.A;
+      float* hid = fc_s;  // [nb][20] value hidden units, then reused? no: logits live behind it when they fit
+      for (int o = tid; o < nvalid * per_board; o += kEpiThreads) {
+        const int b = o / per_board, i = o - b * per_board;
+        const float* feat = headf_s + (size_t)b * gm.block * 3;
+        if (i < 20) {
+          float acc = blob[L.val_fc1_b + i];
+          const float* wrow = blob + L.val_fc1_w + (size_t)i * HW;
+          for (int r = 0, cell = 0; r < gm.H; ++r)
+            for (int c = 0; c < gm.W; ++c, ++cell) acc = fmaf(wrow[cell], feat[(r * gm.pitch + c) * 3], acc);
+          hid[b * 20 + i] = lrelu_tc(acc);
+        } else {
+          const int a = i - 20;
+          float acc = blob[L.pol_fc_b + a];
+          for (int chn = 0; chn < 2; ++chn)
+            for (int r = 0, cell = 0; r < gm.H; ++r)
+              for (int c = 0; c < gm.W; ++c, ++cell)
+                acc = fmaf(pol_fc_t[(size_t)(chn * HW + cell) * gm.A + a], feat[(r * gm.pitch + c) * 3 + 1 + chn], acc);
+          probs[(size_t)(leaf0 + b) * gm.A + a] = acc;  // raw logit, normalised below
+        }
+      }
+      __threadfence_block();
+      epi_bar_sync();
+      for (int b = warp; b < nvalid; b += 4) {
         const int lane = tid & 31;
+        if (lane == 0) {
+          float acc = blob[L.val_fc2_b];
+          for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
+          values[leaf0 + b] = tanhf(acc);
+        }
+        float* row = probs + (size_t)(leaf0 + b) * gm.A;  // softmax over all A actions (lib/mcts.py:216)
         float mx = -INFINITY;
-        for (int a = lane; a < gm.A; a += 32) mx = fmaxf(mx, logit[a]);
+        for (int a = lane; a < gm.A; a += 32) mx = fmaxf(mx, row[a]);
         for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
         float sum = 0.0f;
-        for (int a = lane; a < gm.A; a += 32) sum += expf(logit[a] - mx);
+        for (int a = lane; a < gm.A; a += 32) sum += expf(row[a] - mx);
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        for (int a = lane; a < gm.A; a += 32) probs[(size_t)(leaf0 + b) * gm.A + a] = expf(logit[a] - mx) / sum;
+        for (int a = lane; a < gm.A; a += 32) row[a] = expf(row[a] - mx) / sum;
       }
-      __syncthreads();
     }
   }
 
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
