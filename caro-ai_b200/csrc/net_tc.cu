@@ -204,54 +204,64 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // =============================== producer / MMA issuer (one thread) ===============================
-    if ((tid & 31) == 0) {
-      const uint32_t act_addr = smem_u32(act);
-      const uint32_t wgt_addr = smem_u32(wgt);
-      const int total_layers = my_groups * kNumLayers;
-      auto load_layer = [&](int gl) {  // global layer index -> buffer gl & 1
-        const int l = gl % kNumLayers;
-        uint8_t* dst = wgt + (gl & 1) * kLayerBytes;
-        uint64_t* bar = bar_w + (gl & 1);
-        if (l == 0) {
-          mbar_expect_tx(bar, kLayerBytesIn);
-          for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar);
-        } else {
-          mbar_expect_tx(bar, kLayerBytes);
-          const uint8_t* src = wimg + kLayerBytesIn + (size_t)(l - 1) * kLayerBytes;
-          for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar);
-        }
-      };
+    // ===================== producer / MMA issuer: the whole warp runs the loop (so that the descriptor
+    // arithmetic stays warp-uniform -> uniform registers), one elected lane issues TMA / MMA / commit ==========
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+    const uint32_t act_addr = smem_u32(act);
+    const uint32_t wgt_addr = smem_u32(wgt);
+    const int total_layers = my_groups * kNumLayers;
+    auto load_layer = [&](int gl) {  // global layer index -> buffer gl & 1
+      const int l = gl % kNumLayers;
+      uint8_t* dst = wgt + (gl & 1) * kLayerBytes;
+      uint64_t* bar = bar_w + (gl & 1);
+      if (l == 0) {
+        mbar_expect_tx(bar, kLayerBytesIn);
+        for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar);
+      } else {
+        mbar_expect_tx(bar, kLayerBytes);
+        const uint8_t* src = wimg + kLayerBytesIn + (size_t)(l - 1) * kLayerBytes;
+        for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar);
+      }
+    };
+    if (elected) {
       load_layer(0);
       if (total_layers > 1) load_layer(1);
-      int shift[9];
+    }
+    // descriptor templates: only the 14-bit start-address field (units of 16 B) changes per MMA
+    const uint64_t a_desc0 = make_desc(act_addr + (uint32_t)kHalo * 16u, kChunkBytes, 128u);
+    const uint64_t b_desc0 = make_desc(wgt_addr, 1024u, 128u);
+    const int pitch = gm.pitch;
+    for (int gl = 0; gl < total_layers; ++gl) {
+      const bool first = (gl % kNumLayers) == 0;
+      const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl & 1) * (kLayerBytes / 16));
+      mbar_wait(bar_w + (gl & 1), (uint32_t)(gl >> 1) & 1u);
+      const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
+      for (int t = 0; t < kTilesPerGroup; ++t) {
+        if (t == 0) {
+          mbar_wait(bar_act + 0, act_par);
+          mbar_wait(bar_act + 1, act_par);
+        } else if (t < kTilesPerGroup - 1) {
+          mbar_wait(bar_act + t + 1, act_par);
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * 64);
+        const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(t * kTileRows);
+        if (elected) {
+          if (first) {
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) shift[tap] = (tap / 3 - 1) * gm.pitch + (tap % 3 - 1);
-      for (int gl = 0; gl < total_layers; ++gl) {
-        const int l = gl % kNumLayers;
-        const int ksteps = l == 0 ? 1 : 4;
-        const uint32_t tap_bytes = l == 0 ? kTapBytesIn : kTapBytes;
-        const uint32_t wbase = wgt_addr + (uint32_t)(gl & 1) * kLayerBytes;
-        mbar_wait(bar_w + (gl & 1), (uint32_t)(gl >> 1) & 1u);
-        const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
-        for (int t = 0; t < kTilesPerGroup; ++t) {
-          if (t == 0) {
-            mbar_wait(bar_act + 0, act_par);
-            mbar_wait(bar_act + 1, act_par);
-          } else if (t < kTilesPerGroup - 1) {
-            mbar_wait(bar_act + t + 1, act_par);
-          }
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 64);
-          uint32_t acc = 0u;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int sh = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+              umma_bf16(d_tmem, a_tile + (uint64_t)(int64_t)sh, b_layer + (uint64_t)(tap * (kTapBytesIn / 16)), kIdesc, tap > 0 ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a0 = act_addr + (uint32_t)(kHalo + t * kTileRows + shift[tap]) * 16u;
-            const uint32_t b0 = wbase + (uint32_t)tap * tap_bytes;
-            for (int kk = 0; kk < ksteps; ++kk) {
-              umma_bf16(d_tmem, make_desc(a0 + (uint32_t)kk * (2u * kChunkBytes), kChunkBytes, 128u),
-                        make_desc(b0 + (uint32_t)kk * 2048u, 1024u, 128u), kIdesc, acc);
-              acc = 1u;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int sh = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(d_tmem, a_tile + (uint64_t)(int64_t)(sh + kk * 2 * kActRows),
+                          b_layer + (uint64_t)(tap * (kTapBytes / 16) + kk * (2048 / 16)), kIdesc, (tap | kk) ? 1u : 0u);
             }
           }
           umma_commit(bar_acc + t);
@@ -259,6 +269,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
           // epilogue of tile 2, which waited on the last commit of layer gl-1): its weight buffer is free
           if (t == 1 && gl >= 1 && gl + 1 < total_layers) load_layer(gl + 1);
         }
+        __syncwarp();
       }
     }
   } else {
