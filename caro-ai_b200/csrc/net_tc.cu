@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
-              const float* __restrict__ pol_fc_t, float* __restrict__ probs, float* __restrict__ values) {
+              const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
+              float* __restrict__ values) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + TcSmem::kAct;
   uint8_t* wgt = smem + TcSmem::kWgt;
@@ -274,30 +275,31 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     }
   } else {
     // ========================================= epilogue warps =========================================
-    // geometry of this thread's row in each tile (row p = 128*t + tid)
-    int row_board[kTilesPerGroup], row_cell[kTilesPerGroup];
-#pragma unroll
-    for (int t = 0; t < kTilesPerGroup; ++t) {
-      const int p = t * kTileRows + tid;
-      const int b = p / gm.block, within = p - b * gm.block;
-      const int r = within / gm.pitch, c = within - r * gm.pitch;
-      const bool real = b < nb && r < gm.H && c < gm.W;
-      row_board[t] = b;
-      row_cell[t] = real ? r * gm.W + c : -1;
-    }
+    // Code size matters here (the v1 kernel was 127 KB of SASS and lived in instruction-cache misses):
+    // tiles and 32-channel chunks are real loops, only the 32-element body is unrolled.
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int HW = gm.H * gm.W;
+    float* featc = headf_s;  // dense head features [board][3][HW]
+
+    auto row_cell = [&](int p, int& b) -> int {  // r*W + c of padded position p, or -1 for padding
+      b = p / gm.block;
+      const int within = p - b * gm.block;
+      const int r = within / gm.pitch, c = within - r * gm.pitch;
+      return (b < nb && r < gm.H && c < gm.W) ? r * gm.W + c : -1;
+    };
 
     auto write_inputs = [&](long long leaf0) {
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < kTilesPerGroup; ++t) {
         const int p = t * kTileRows + tid;
+        int b;
+        const int cell = row_cell(p, b);
         uint32_t lo = 0u;
-        const long long leaf = leaf0 + row_board[t];
-        if (row_cell[t] >= 0 && leaf < count) {
+        const long long leaf = leaf0 + b;
+        if (cell >= 0 && leaf < count) {
           const typename R::Board s = boards[leaf];
           const int wm = who[leaf];
-          const int r = row_cell[t] / gm.W, c = row_cell[t] - r * gm.W;
+          const int r = cell / gm.W, c = cell - r * gm.W;
           const uint32_t mine = rules.plane_value(s, wm, 0, r, c) ? 0x3F80u : 0u;  // bf16(1.0)
           const uint32_t other = rules.plane_value(s, wm, 1, r, c) ? 0x3F80u : 0u;
           lo = mine | (other << 16);
@@ -313,51 +315,73 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     for (int gi = 0; gi < my_groups; ++gi) {
       const long long grp = blockIdx.x + (long long)gi * gridDim.x;
       const long long leaf0 = grp * nb;
-      float hv[kTilesPerGroup], hp0[kTilesPerGroup], hp1[kTilesPerGroup];
+#pragma unroll 1
       for (int layer = 0; layer < kNumLayers; ++layer) {
         const int gl = gi * kNumLayers + layer;
         const uint32_t acc_par = (uint32_t)gl & 1u;
         const bool last = layer == kNumLayers - 1;
-        const float* bl = bias_s + layer * 64;
-#pragma unroll
+        const bool has_res = layer > 0;
+        const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64);
+#pragma unroll 1
         for (int t = 0; t < kTilesPerGroup; ++t) {
           mbar_wait(bar_acc + (t + 1 < kTilesPerGroup ? t + 1 : kTilesPerGroup - 1), acc_par);
           __syncwarp();
           tc_fence_after();
           const int p = t * kTileRows + tid;
-          const bool real = row_cell[t] >= 0;
+          int b;
+          const int cell = row_cell(p, b);
+          const bool real = cell >= 0;
           float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + ch * 16);
-            const uint32_t a_res = tmem_base + lane_base + (uint32_t)(256 + t * 64 + ch * 16);
-            uint32_t ra[16], rr[16];
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + half * 32);
+            const uint32_t a_res = a_acc + 256u;
+            uint32_t ra[32], rr[32];
             TMEM_LD16(a_acc, ra);
-            if (layer > 0) TMEM_LD16(a_res, rr);
+            TMEM_LD16(a_acc + 16u, (ra + 16));
+            if (has_res) {
+              TMEM_LD16(a_res, rr);
+              TMEM_LD16(a_res + 16u, (rr + 16));
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = lrelu_tc(__uint_as_float(ra[j]) + bl[ch * 16 + j]);
-              if (layer > 0) v += __uint_as_float(rr[j]);
-              rr[j] = __float_as_uint(v);
-              if (last) {
-                av = fmaf(v, headw_s[ch * 16 + j], av);
-                ap0 = fmaf(v, headw_s[64 + ch * 16 + j], ap0);
-                ap1 = fmaf(v, headw_s[128 + ch * 16 + j], ap1);
+            for (int q = 0; q < 8; ++q) {
+              const float4 bq = bl4[half * 8 + q];
+              const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = q * 4 + e;
+                float v = lrelu_tc(__uint_as_float(ra[j]) + bb[e]);
+                if (has_res) v += __uint_as_float(rr[j]);
+                rr[j] = __float_as_uint(v);
               }
             }
             if (!last) {
               TMEM_ST16(a_res, rr);
-              uint32_t packed[8];
+              TMEM_ST16(a_res + 16u, (rr + 16));
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
-                packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+              for (int c8 = 0; c8 < 4; ++c8) {
+                uint32_t packed[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h =
+                      __floats2bfloat162_rn(__uint_as_float(rr[c8 * 8 + 2 * j]), __uint_as_float(rr[c8 * 8 + 2 * j + 1]));
+                  packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+                }
+                *reinterpret_cast<uint4*>(act + (size_t)((half * 4 + c8) * kActRows + kHalo + p) * 16) =
+                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
               }
-              *reinterpret_cast<uint4*>(act + (size_t)((2 * ch) * kActRows + kHalo + p) * 16) =
-                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              *reinterpret_cast<uint4*>(act + (size_t)((2 * ch + 1) * kActRows + kHalo + p) * 16) =
-                  make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            } else {
+              const float4* hw4 = reinterpret_cast<const float4*>(headw_s + half * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
+                const float v0 = __uint_as_float(rr[q * 4]), v1 = __uint_as_float(rr[q * 4 + 1]);
+                const float v2 = __uint_as_float(rr[q * 4 + 2]), v3 = __uint_as_float(rr[q * 4 + 3]);
+                av = fmaf(v0, w0.x, fmaf(v1, w0.y, fmaf(v2, w0.z, fmaf(v3, w0.w, av))));
+                ap0 = fmaf(v0, w1.x, fmaf(v1, w1.y, fmaf(v2, w1.z, fmaf(v3, w1.w, ap0))));
+                ap1 = fmaf(v0, w2.x, fmaf(v1, w2.y, fmaf(v2, w2.z, fmaf(v3, w2.w, ap1))));
+              }
             }
           }
           if (!last) {
@@ -365,49 +389,51 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_act + t);
-          } else {
-            hv[t] = av;
-            hp0[t] = ap0;
-            hp1[t] = ap1;
+          } else if (real) {  // 1x1 head convolutions -> dense features (channel-major like lib/model.py:93)
+            featc[(b * 3 + 0) * HW + cell] = lrelu_tc(av + headw_s[192]);
+            featc[(b * 3 + 1) * HW + cell] = lrelu_tc(ap0 + headw_s[193]);
+            featc[(b * 3 + 2) * HW + cell] = lrelu_tc(ap1 + headw_s[194]);
           }
         }
-      }
-      // ---- 1x1 head convolutions (per row), then hand the tensor pipe its next group -----------
-#pragma unroll
-      for (int t = 0; t < kTilesPerGroup; ++t) {
-        const int p = t * kTileRows + tid;
-        headf_s[p * 3 + 0] = lrelu_tc(hv[t] + headw_s[192]);
-        headf_s[p * 3 + 1] = lrelu_tc(hp0[t] + headw_s[193]);
-        headf_s[p * 3 + 2] = lrelu_tc(hp1[t] + headw_s[194]);
       }
       tc_fence_before();  // the last layer's accumulators have been read (wait::ld above)
       if (gi + 1 < my_groups) write_inputs((blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb);
       epi_bar_sync();
-      // ---- fully connected heads: all (board, output) pairs in parallel ----------------------------
+      // ---- fully connected heads: all (board, output) pairs in parallel, coalesced transposed weights ----
       const int nvalid = (int)min((long long)nb, count - leaf0);
       const int per_board = 20 + gm.A;
-      float* hid = fc_s;  // [nb][20] value hidden units, then reused? no: logits live behind it when they fit
+      float* hid = fc_s;  // [nb][20] value hidden units
+#pragma unroll 1
       for (int o = tid; o < nvalid * per_board; o += kEpiThreads) {
         const int b = o / per_board, i = o - b * per_board;
-        const float* feat = headf_s + (size_t)b * gm.block * 3;
+        const float* feat = featc + (size_t)b * 3 * HW;
         if (i < 20) {
-          float acc = blob[L.val_fc1_b + i];
-          const float* wrow = blob + L.val_fc1_w + (size_t)i * HW;
-          for (int r = 0, cell = 0; r < gm.H; ++r)
-            for (int c = 0; c < gm.W; ++c, ++cell) acc = fmaf(wrow[cell], feat[(r * gm.pitch + c) * 3], acc);
-          hid[b * 20 + i] = lrelu_tc(acc);
+          float a0 = blob[L.val_fc1_b + i], a1 = 0.0f;
+          const float* wt = val_fc1_t + i;
+          int cell = 0;
+          for (; cell + 1 < HW; cell += 2) {
+            a0 = fmaf(wt[(size_t)cell * 20], feat[cell], a0);
+            a1 = fmaf(wt[(size_t)(cell + 1) * 20], feat[cell + 1], a1);
+          }
+          if (cell < HW) a0 = fmaf(wt[(size_t)cell * 20], feat[cell], a0);
+          hid[b * 20 + i] = lrelu_tc(a0 + a1);
         } else {
           const int a = i - 20;
-          float acc = blob[L.pol_fc_b + a];
-          for (int chn = 0; chn < 2; ++chn)
-            for (int r = 0, cell = 0; r < gm.H; ++r)
-              for (int c = 0; c < gm.W; ++c, ++cell)
-                acc = fmaf(pol_fc_t[(size_t)(chn * HW + cell) * gm.A + a], feat[(r * gm.pitch + c) * 3 + 1 + chn], acc);
-          probs[(size_t)(leaf0 + b) * gm.A + a] = acc;  // raw logit, normalised below
+          float a0 = blob[L.pol_fc_b + a], a1 = 0.0f;
+          const float* wt = pol_fc_t + a;
+          const float* f2 = feat + HW;
+          int k2 = 0;
+          for (; k2 + 1 < 2 * HW; k2 += 2) {
+            a0 = fmaf(wt[(size_t)k2 * gm.A], f2[k2], a0);
+            a1 = fmaf(wt[(size_t)(k2 + 1) * gm.A], f2[k2 + 1], a1);
+          }
+          if (k2 < 2 * HW) a0 = fmaf(wt[(size_t)k2 * gm.A], f2[k2], a0);
+          probs[(size_t)(leaf0 + b) * gm.A + a] = a0 + a1;  // raw logit, normalised below
         }
       }
       __threadfence_block();
       epi_bar_sync();
+#pragma unroll 1
       for (int b = warp; b < nvalid; b += 4) {
         const int lane = tid & 31;
         if (lane == 0) {
@@ -417,11 +443,14 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         }
         float* row = probs + (size_t)(leaf0 + b) * gm.A;  // softmax over all A actions (lib/mcts.py:216)
         float mx = -INFINITY;
+#pragma unroll 1
         for (int a = lane; a < gm.A; a += 32) mx = fmaxf(mx, row[a]);
         for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
         float sum = 0.0f;
+#pragma unroll 1
         for (int a = lane; a < gm.A; a += 32) sum += expf(row[a] - mx);
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll 1
         for (int a = lane; a < gm.A; a += 32) row[a] = expf(row[a] - mx) / sum;
       }
     }
@@ -473,9 +502,12 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
   for (int l = 0; l < kBlocks; ++l)
     for (int co = 0; co < 64; ++co) bias[(size_t)(l + 1) * 64 + co] = h[L.conv_b[l] + co];
   const int HW = net->H * net->W, A = net->A;
-  std::vector<float> polt((size_t)2 * HW * A);
+  // transposed FC weights, policy [2*HW][A] followed by value-FC1 [HW][20]: a warp's outputs read contiguous floats
+  std::vector<float> polt((size_t)2 * HW * A + (size_t)HW * 20);
   for (int a = 0; a < A; ++a)
     for (int i = 0; i < 2 * HW; ++i) polt[(size_t)i * A + a] = h[L.pol_fc_w + (size_t)a * 2 * HW + i];
+  for (int i = 0; i < 20; ++i)
+    for (int c = 0; c < HW; ++c) polt[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
   cudaError_t ce = cudaSuccess;
   if (!net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
   if (ce == cudaSuccess && !net->d_tc_bias) ce = cudaMalloc(&net->d_tc_bias, bias.size() * sizeof(float));
@@ -521,7 +553,7 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
   kern<<<grid, kThreads, TcSmem::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
                                                (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                               net->d_pol_fc_t, probs, values);
+                                               net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values);
   return caro_check_launch("net_tc_kernel");
 }
 
