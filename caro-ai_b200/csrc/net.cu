@@ -163,6 +163,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_tc_weights = nullptr;
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
+  net->d_trace = nullptr;
   if (n_floats != net->layout.total) {
     delete net;
     return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
@@ -178,6 +179,12 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
     return rc;
   }
   *out = net;
+  return CARO_OK;
+}
+
+int caro_net_set_trace(caro_net* net, void* d_trace) {
+  if (!net) return caro_fail(CARO_E_ARG, "null net");
+  net->d_trace = d_trace;
   return CARO_OK;
 }
 

@@ -53,7 +53,8 @@ struct caro_net {
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   float* d_tc_bias;     // [6][64] folded conv biases
-  float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] for coalesced reads in the TC epilogue
+  float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
+  void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
 };
 
 // net_tc.cu

@@ -32,8 +32,8 @@ namespace caro {
 constexpr int kTilesPerGroup = 4;
 constexpr int kTileRows = 128;
 constexpr int kGroupRows = kTilesPerGroup * kTileRows;  // 512 padded positions per CTA pass
-constexpr int kHalo = 24;                                // zero positions before / after (>= pitch + 1)
-constexpr int kActRows = kGroupRows + 2 * kHalo;         // 560
+constexpr int kHalo = 20;                                // zero positions before / after (>= pitch + 1)
+constexpr int kActRows = kGroupRows + 2 * kHalo;         // 552
 constexpr int kChunkBytes = kActRows * 16;               // one 8-channel chunk of all positions
 constexpr int kActBytes = 8 * kChunkBytes;               // 71,680
 constexpr int kTapBytes = 8 * 64 * 16;                   // 8,192: one tap of a 64->64 layer
@@ -41,8 +41,14 @@ constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of co
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
 constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
-constexpr int kEpiThreads = 128;                         // warps 0-3: epilogue (TMEM lane quarter = warp index)
-constexpr int kThreads = kEpiThreads + 32;               // warp 4: TMEM owner, weight producer, MMA issuer
+constexpr int kEpiWarps = 8;                             // warps 0-7: epilogue; TMEM lane quarter = warp & 3, column half = warp >> 2
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = kEpiWarps;                      // warp 8: TMEM owner + MMA issue for tiles 0,2
+constexpr int kMmaWarps = 2;                             // warp 9: MMA issue for tiles 1,3 + weight streaming
+constexpr int kHeadWarp = kMmaWarp + kMmaWarps;          // warps 10-11: FC heads + softmax, off the critical path
+constexpr int kHeadWarps = 2;
+constexpr int kHeadThreads = 32 * kHeadWarps;
+constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kHeadThreads;
 constexpr uint32_t kTmemCols = 512;
 
 struct TcGeom {
@@ -88,7 +94,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void head_bar_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -125,6 +131,13 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 
 
 __device__ __forceinline__ float lrelu_tc(float x) { return fmaxf(x, kLeaky * x); }
 
+// Optional timeline (debug): CTA 0 stores clock64() into a fixed slot per event (fire-and-forget store,
+// no atomics, so the pipeline is not perturbed): slot = kind * 1000 + gl * 4 + t.
+#define TC_TRACE(kind, idx)                                                                      \
+  do {                                                                                           \
+    if (trace != nullptr && blockIdx.x == 0 && (idx) < 1000) trace[(kind) * 1000 + (idx)] = clock64(); \
+  } while (0)
+
 struct TcSmem {
   // dynamic shared memory carve-up (byte offsets from a 128-aligned base)
   static constexpr int kAct = 0;
@@ -132,15 +145,19 @@ struct TcSmem {
   static constexpr int kBias = kWgt + 2 * kLayerBytes;             // float [6][64]
   static constexpr int kHeadW = kBias + kNumLayers * 64 * 4;       // float [3][64] + [3] biases (+pad)
   static constexpr int kHeadF = kHeadW + 4 * 64 * 4;               // float [512][3] head features
-  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[32][20] then logits[512]... (640 floats)
-  static constexpr int kBars = kFc + 640 * 4;                      // mbarriers + tmem base
+  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[nb][20] + logits[nb][A]  (<= 1024 floats)
+  static constexpr int kCellTab = kFc + 1024 * 4;                  // uint16 [512]: (board << 9) | (cell + 1), 0 = padding
+  static constexpr int kBars = kCellTab + kGroupRows * 2;          // mbarriers + tmem base
   static constexpr int kTotal = kBars + 128;
 };
 static_assert(TcSmem::kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // ------------------------------------------------------------------------------------- kernel
-// Roles: warps 0-3 = epilogue (warp w owns TMEM lanes [32w, 32w+32) = rows 32w.. of every tile),
-//        warp 4    = TMEM allocation, weight streaming (cp.async.bulk) and single-thread MMA issue.
+// Roles: warps 0-7 = epilogue (warp w owns TMEM lanes [32(w&3), +32) = rows of every tile, channels 32(w>>2)..+32),
+//        warp 8    = TMEM allocation, elected-lane MMA issue for tiles 0 and 2,
+//        warp 9    = elected-lane MMA issue for tiles 1 and 3, weight streaming (cp.async.bulk).
+//        Two issuing warps so that one tile's barrier waits overlap the other tile's MMAs (the tensor pipe's
+//        queue is shallow: with one issuer the waits showed up as ~25 % idle gaps in the timeline).
 // Pipeline per layer L (tiles t = 0..3, in-place activation buffer):
 //   MMA(L,t)  needs act_ready[t-1..t+1] of the previous stage (their bf16 rows + tile t's accumulator drained)
 //   EPI(L,t)  needs acc_full[min(t+1,3)]  (tile t+1 reads the last rows of tile t as its halo)
@@ -151,7 +168,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
-              float* __restrict__ values) {
+              float* __restrict__ values, long long* __restrict__ trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + TcSmem::kAct;
   uint8_t* wgt = smem + TcSmem::kWgt;
@@ -162,7 +179,9 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + TcSmem::kBars);  // [2] weights buffer filled
   uint64_t* bar_acc = bar_w + 2;                                        // [4] accumulator tile complete
   uint64_t* bar_act = bar_w + 6;                                        // [4] activation tile rewritten / accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 10);
+  uint64_t* bar_feat = bar_w + 10;                                      // [0] head features complete, [1] consumed + re-zeroed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 12);
+  uint16_t* cell_tab = reinterpret_cast<uint16_t*>(smem + TcSmem::kCellTab);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -175,6 +194,12 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < kNumLayers * 64; i += kThreads) bias_s[i] = bias_g[i];
+  for (int p = tid; p < kGroupRows; p += kThreads) {  // padded position -> (board, cell) once, no divisions in the hot loop
+    const int b = p / gm.block, within = p - b * gm.block;
+    const int r = within / gm.pitch, c = within - r * gm.pitch;
+    cell_tab[p] = (b < nb && r < gm.H && c < gm.W) ? (uint16_t)((b << 9) | (r * gm.W + c + 1)) : (uint16_t)0;
+  }
+  for (int i = tid; i < kGroupRows * 3; i += kThreads) headf_s[i] = 0.0f;
   for (int i = tid; i < 64; i += kThreads) {
     headw_s[i] = blob[L.val_conv_w + i];
     headw_s[64 + i] = blob[L.pol_conv_w + i];
@@ -190,9 +215,11 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       mbar_init(bar_acc + t, 1);
       mbar_init(bar_act + t, kEpiThreads);
     }
+    mbar_init(bar_feat + 0, kEpiThreads);
+    mbar_init(bar_feat + 1, kHeadThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
                  : "memory");
@@ -204,9 +231,90 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ===================== producer / MMA issuer: the whole warp runs the loop (so that the descriptor
-    // arithmetic stays warp-uniform -> uniform registers), one elected lane issues TMA / MMA / commit ==========
+  if (warp >= kHeadWarp) {
+    // ===================== head warps: FC layers + tanh + softmax of group g while the pipeline runs g+1 ==========
+    const int htid = tid - kHeadWarp * 32;
+    const int hwarp = warp - kHeadWarp;
+    const int HW = gm.H * gm.W;
+    const float* featc = headf_s;
+    const int per_board = 20 + gm.A;
+    float* hid = fc_s;  // [nb][20] value hidden units, logits behind them
+    float* logit = fc_s + nb * 20;
+    const float hb0 = headw_s[192], hb1 = headw_s[193], hb2 = headw_s[194];
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
+      const int nvalid = (int)min((long long)nb, count - leaf0);
+      mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
+      // all (board, output) pairs in parallel, coalesced transposed weights; bias + LeakyReLU of the 1x1 head
+      // convolutions are applied on the fly
+#pragma unroll 1
+      for (int o = htid; o < nvalid * per_board; o += kHeadThreads) {
+        const int b = o / per_board, i = o - b * per_board;
+        const float* feat = featc + (size_t)b * 3 * HW;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (i < 20) {
+          const float* wt = val_fc1_t + i;
+          int cell = 0;
+          for (; cell + 3 < HW; cell += 4) {
+            a0 = fmaf(__ldg(wt + (size_t)cell * 20), lrelu_tc(feat[cell] + hb0), a0);
+            a1 = fmaf(__ldg(wt + (size_t)(cell + 1) * 20), lrelu_tc(feat[cell + 1] + hb0), a1);
+            a2 = fmaf(__ldg(wt + (size_t)(cell + 2) * 20), lrelu_tc(feat[cell + 2] + hb0), a2);
+            a3 = fmaf(__ldg(wt + (size_t)(cell + 3) * 20), lrelu_tc(feat[cell + 3] + hb0), a3);
+          }
+          for (; cell < HW; ++cell) a0 = fmaf(__ldg(wt + (size_t)cell * 20), lrelu_tc(feat[cell] + hb0), a0);
+          hid[b * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + (a0 + a1) + (a2 + a3));
+        } else {
+          const int a = i - 20;
+          const float* wt = pol_fc_t + a;
+          const float* f2 = feat + HW;
+          for (int chn = 0; chn < 2; ++chn) {
+            const float hb = chn ? hb2 : hb1;
+            const float* w2 = wt + (size_t)chn * HW * gm.A;
+            const float* fc = f2 + chn * HW;
+            int cell = 0;
+            for (; cell + 3 < HW; cell += 4) {
+              a0 = fmaf(__ldg(w2 + (size_t)cell * gm.A), lrelu_tc(fc[cell] + hb), a0);
+              a1 = fmaf(__ldg(w2 + (size_t)(cell + 1) * gm.A), lrelu_tc(fc[cell + 1] + hb), a1);
+              a2 = fmaf(__ldg(w2 + (size_t)(cell + 2) * gm.A), lrelu_tc(fc[cell + 2] + hb), a2);
+              a3 = fmaf(__ldg(w2 + (size_t)(cell + 3) * gm.A), lrelu_tc(fc[cell + 3] + hb), a3);
+            }
+            for (; cell < HW; ++cell) a0 = fmaf(__ldg(w2 + (size_t)cell * gm.A), lrelu_tc(fc[cell] + hb), a0);
+          }
+          logit[b * gm.A + a] = blob[L.pol_fc_b + a] + (a0 + a1) + (a2 + a3);
+        }
+      }
+      head_bar_sync();
+#pragma unroll 1
+      for (int i = htid; i < nvalid * 3 * HW; i += kHeadThreads) headf_s[i] = 0.0f;  // re-arm the accumulation slots
+      mbar_arrive(bar_feat + 1);
+#pragma unroll 1
+      for (int b = hwarp; b < nvalid; b += kHeadWarps) {
+        const int lane = tid & 31;
+        if (lane == 0) {
+          float acc = blob[L.val_fc2_b];
+          for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
+          values[leaf0 + b] = tanhf(acc);
+        }
+        const float* lrow = logit + b * gm.A;  // softmax over all A actions (lib/mcts.py:216)
+        float* prow = probs + (size_t)(leaf0 + b) * gm.A;
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int a = lane; a < gm.A; a += 32) mx = fmaxf(mx, lrow[a]);
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int a = lane; a < gm.A; a += 32) sum += expf(lrow[a] - mx);
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll 1
+        for (int a = lane; a < gm.A; a += 32) prow[a] = expf(lrow[a] - mx) / sum;
+      }
+      head_bar_sync();  // hid / logit are rewritten by the next group
+      if (htid == 0) TC_TRACE(5, gi);  // heads done
+    }
+  } else if (warp >= kMmaWarp) {
+    // ===================== MMA issuers: the whole warp runs the loop (so that the descriptor arithmetic
+    // stays warp-uniform -> uniform registers), one elected lane issues TMA / MMA / commit ====================
+    const int mw = warp - kMmaWarp;  // 0: tiles 0,2   1: tiles 1,3 + weights
     uint32_t elected;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
     const uint32_t act_addr = smem_u32(act);
@@ -225,7 +333,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar);
       }
     };
-    if (elected) {
+    if (mw == 1 && elected) {
       load_layer(0);
       if (total_layers > 1) load_layer(1);
     }
@@ -237,15 +345,16 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       const bool first = (gl % kNumLayers) == 0;
       const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl & 1) * (kLayerBytes / 16));
       mbar_wait(bar_w + (gl & 1), (uint32_t)(gl >> 1) & 1u);
+      if (elected) TC_TRACE(6, gl * 2 + mw);  // weights present
       const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
-      for (int t = 0; t < kTilesPerGroup; ++t) {
-        if (t == 0) {
-          mbar_wait(bar_act + 0, act_par);
-          mbar_wait(bar_act + 1, act_par);
-        } else if (t < kTilesPerGroup - 1) {
-          mbar_wait(bar_act + t + 1, act_par);
-        }
+#pragma unroll 1
+      for (int t = mw; t < kTilesPerGroup; t += 2) {
+        // MMA(gl,t) reads the rows of tiles t-1..t+1 as rewritten by the previous stage
+        if (t > 0) mbar_wait(bar_act + t - 1, act_par);
+        mbar_wait(bar_act + t, act_par);
+        if (t + 1 < kTilesPerGroup) mbar_wait(bar_act + t + 1, act_par);
         tc_fence_after();
+        if (elected) TC_TRACE(0, gl * 4 + t);  // MMA issue start
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * 64);
         const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(t * kTileRows);
         if (elected) {
@@ -266,8 +375,9 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             }
           }
           umma_commit(bar_acc + t);
-          // after tile 1 has been issued every MMA of layer gl-1 is known complete (tile 1 waited on the
-          // epilogue of tile 2, which waited on the last commit of layer gl-1): its weight buffer is free
+          TC_TRACE(1, gl * 4 + t);  // MMA issued + committed
+          // tile 1 waited on the rewritten rows of tiles 0..2, whose epilogues waited on every commit of layer
+          // gl-1: all MMAs of layer gl-1 are complete, its weight buffer is free for layer gl+1
           if (t == 1 && gl >= 1 && gl + 1 < total_layers) load_layer(gl + 1);
         }
         __syncwarp();
@@ -276,36 +386,32 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   } else {
     // ========================================= epilogue warps =========================================
     // Code size matters here (the v1 kernel was 127 KB of SASS and lived in instruction-cache misses):
-    // tiles and 32-channel chunks are real loops, only the 32-element body is unrolled.
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // tiles are a real loop, only the 32-channel body is unrolled.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + (tid & 31);               // row of the tile = TMEM lane
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int HW = gm.H * gm.W;
-    float* featc = headf_s;  // dense head features [board][3][HW]
-
-    auto row_cell = [&](int p, int& b) -> int {  // r*W + c of padded position p, or -1 for padding
-      b = p / gm.block;
-      const int within = p - b * gm.block;
-      const int r = within / gm.pitch, c = within - r * gm.pitch;
-      return (b < nb && r < gm.H && c < gm.W) ? r * gm.W + c : -1;
-    };
+    float* featc = headf_s;  // dense head features [board][3][HW], accumulated by the two column halves
 
     auto write_inputs = [&](long long leaf0) {
 #pragma unroll 1
       for (int t = 0; t < kTilesPerGroup; ++t) {
-        const int p = t * kTileRows + tid;
-        int b;
-        const int cell = row_cell(p, b);
+        const int p = t * kTileRows + row;
         uint32_t lo = 0u;
-        const long long leaf = leaf0 + b;
-        if (cell >= 0 && leaf < count) {
-          const typename R::Board s = boards[leaf];
-          const int wm = who[leaf];
-          const int r = cell / gm.W, c = cell - r * gm.W;
-          const uint32_t mine = rules.plane_value(s, wm, 0, r, c) ? 0x3F80u : 0u;  // bf16(1.0)
-          const uint32_t other = rules.plane_value(s, wm, 1, r, c) ? 0x3F80u : 0u;
-          lo = mine | (other << 16);
+        if (half == 0) {
+          const uint32_t tab = cell_tab[p];
+          const long long leaf = leaf0 + (tab >> 9);
+          if (tab != 0u && leaf < count) {
+            const int cell = (int)(tab & 511u) - 1;
+            const typename R::Board s = boards[leaf];
+            const int wm = who[leaf];
+            const int r = cell / gm.W, c = cell - r * gm.W;
+            const uint32_t mine = rules.plane_value(s, wm, 0, r, c) ? 0x3F80u : 0u;  // bf16(1.0)
+            const uint32_t other = rules.plane_value(s, wm, 1, r, c) ? 0x3F80u : 0u;
+            lo = mine | (other << 16);
+          }
         }
-        *reinterpret_cast<uint4*>(act + (size_t)(0 * kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(act + (size_t)(1 * kActRows + kHalo + p) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + (size_t)(half * kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
         fence_async_smem();
         mbar_arrive(bar_act + t);
       }
@@ -321,145 +427,95 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         const uint32_t acc_par = (uint32_t)gl & 1u;
         const bool last = layer == kNumLayers - 1;
         const bool has_res = layer > 0;
-        const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64);
+        const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64 + half * 32);
 #pragma unroll 1
         for (int t = 0; t < kTilesPerGroup; ++t) {
-          mbar_wait(bar_acc + (t + 1 < kTilesPerGroup ? t + 1 : kTilesPerGroup - 1), acc_par);
+          // tile t's own accumulator AND tile t+1's (it reads the tail rows of tile t as its halo); the two
+          // tiles are issued by different warps, so neither commit implies the other
+          mbar_wait(bar_acc + t, acc_par);
+          if (t + 1 < kTilesPerGroup) mbar_wait(bar_acc + t + 1, acc_par);
           __syncwarp();
           tc_fence_after();
-          const int p = t * kTileRows + tid;
-          int b;
-          const int cell = row_cell(p, b);
-          const bool real = cell >= 0;
-          float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + half * 32);
-            const uint32_t a_res = a_acc + 256u;
-            uint32_t ra[32], rr[32];
-            TMEM_LD16(a_acc, ra);
-            TMEM_LD16(a_acc + 16u, (ra + 16));
-            if (has_res) {
-              TMEM_LD16(a_res, rr);
-              TMEM_LD16(a_res + 16u, (rr + 16));
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (tid == 0) TC_TRACE(2, gl * 4 + t);  // epilogue start (warp 0)
+          const int p = t * kTileRows + row;
+          const uint32_t tab = cell_tab[p];
+          const bool real = tab != 0u;
+          const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + half * 32);
+          const uint32_t a_res = a_acc + 256u;
+          uint32_t ra[32], rr[32];
+          TMEM_LD16(a_acc, ra);
+          TMEM_LD16(a_acc + 16u, (ra + 16));
+          if (has_res) {
+            TMEM_LD16(a_res, rr);
+            TMEM_LD16(a_res + 16u, (rr + 16));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 bq = bl4[half * 8 + q];
-              const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = bl4[q];
+            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = q * 4 + e;
-                float v = lrelu_tc(__uint_as_float(ra[j]) + bb[e]);
-                if (has_res) v += __uint_as_float(rr[j]);
-                rr[j] = __float_as_uint(v);
-              }
-            }
-            if (!last) {
-              TMEM_ST16(a_res, rr);
-              TMEM_ST16(a_res + 16u, (rr + 16));
-#pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                uint32_t packed[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const __nv_bfloat162 h =
-                      __floats2bfloat162_rn(__uint_as_float(rr[c8 * 8 + 2 * j]), __uint_as_float(rr[c8 * 8 + 2 * j + 1]));
-                  packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
-                }
-                *reinterpret_cast<uint4*>(act + (size_t)((half * 4 + c8) * kActRows + kHalo + p) * 16) =
-                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              }
-            } else {
-              const float4* hw4 = reinterpret_cast<const float4*>(headw_s + half * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
-                const float v0 = __uint_as_float(rr[q * 4]), v1 = __uint_as_float(rr[q * 4 + 1]);
-                const float v2 = __uint_as_float(rr[q * 4 + 2]), v3 = __uint_as_float(rr[q * 4 + 3]);
-                av = fmaf(v0, w0.x, fmaf(v1, w0.y, fmaf(v2, w0.z, fmaf(v3, w0.w, av))));
-                ap0 = fmaf(v0, w1.x, fmaf(v1, w1.y, fmaf(v2, w1.z, fmaf(v3, w1.w, ap0))));
-                ap1 = fmaf(v0, w2.x, fmaf(v1, w2.y, fmaf(v2, w2.z, fmaf(v3, w2.w, ap1))));
-              }
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 4 + e;
+              float v = lrelu_tc(__uint_as_float(ra[j]) + bb[e]);
+              if (has_res) v += __uint_as_float(rr[j]);
+              rr[j] = __float_as_uint(v);
             }
           }
           if (!last) {
+            TMEM_ST16(a_res, rr);
+            TMEM_ST16(a_res + 16u, (rr + 16));
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h =
+                    __floats2bfloat162_rn(__uint_as_float(rr[c8 * 8 + 2 * j]), __uint_as_float(rr[c8 * 8 + 2 * j + 1]));
+                packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+              }
+              *reinterpret_cast<uint4*>(act + (size_t)((half * 4 + c8) * kActRows + kHalo + p) * 16) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_act + t);
-          } else if (real) {  // 1x1 head convolutions -> dense features (channel-major like lib/model.py:93)
-            featc[(b * 3 + 0) * HW + cell] = lrelu_tc(av + headw_s[192]);
-            featc[(b * 3 + 1) * HW + cell] = lrelu_tc(ap0 + headw_s[193]);
-            featc[(b * 3 + 2) * HW + cell] = lrelu_tc(ap1 + headw_s[194]);
+            if (tid == 0) TC_TRACE(3, gl * 4 + t);  // epilogue done (warp 0)
+          } else {
+            // 1x1 head convolutions: this thread holds 32 of the 64 channels, the partner warp the rest
+            const float4* hw4 = reinterpret_cast<const float4*>(headw_s + half * 32);
+            float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
+              const float v0 = __uint_as_float(rr[q * 4]), v1 = __uint_as_float(rr[q * 4 + 1]);
+              const float v2 = __uint_as_float(rr[q * 4 + 2]), v3 = __uint_as_float(rr[q * 4 + 3]);
+              av = fmaf(v0, w0.x, fmaf(v1, w0.y, fmaf(v2, w0.z, fmaf(v3, w0.w, av))));
+              ap0 = fmaf(v0, w1.x, fmaf(v1, w1.y, fmaf(v2, w1.z, fmaf(v3, w1.w, ap0))));
+              ap1 = fmaf(v0, w2.x, fmaf(v1, w2.y, fmaf(v2, w2.z, fmaf(v3, w2.w, ap1))));
+            }
+            if (gi > 0 && t == 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // slots re-zeroed by the head warps
+            if (real) {  // two commutative contributions onto a zeroed slot: order-independent result
+              const int b = (int)(tab >> 9), cell = (int)(tab & 511u) - 1;
+              atomicAdd(&featc[(b * 3 + 0) * HW + cell], av);
+              atomicAdd(&featc[(b * 3 + 1) * HW + cell], ap0);
+              atomicAdd(&featc[(b * 3 + 2) * HW + cell], ap1);
+            }
           }
         }
       }
-      tc_fence_before();  // the last layer's accumulators have been read (wait::ld above)
+      mbar_arrive(bar_feat + 0);  // this thread's head features are in place (release)
+      tc_fence_before();          // the last layer's accumulators have been read (wait::ld above)
       if (gi + 1 < my_groups) write_inputs((blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb);
-      epi_bar_sync();
-      // ---- fully connected heads: all (board, output) pairs in parallel, coalesced transposed weights ----
-      const int nvalid = (int)min((long long)nb, count - leaf0);
-      const int per_board = 20 + gm.A;
-      float* hid = fc_s;  // [nb][20] value hidden units
-#pragma unroll 1
-      for (int o = tid; o < nvalid * per_board; o += kEpiThreads) {
-        const int b = o / per_board, i = o - b * per_board;
-        const float* feat = featc + (size_t)b * 3 * HW;
-        if (i < 20) {
-          float a0 = blob[L.val_fc1_b + i], a1 = 0.0f;
-          const float* wt = val_fc1_t + i;
-          int cell = 0;
-          for (; cell + 1 < HW; cell += 2) {
-            a0 = fmaf(wt[(size_t)cell * 20], feat[cell], a0);
-            a1 = fmaf(wt[(size_t)(cell + 1) * 20], feat[cell + 1], a1);
-          }
-          if (cell < HW) a0 = fmaf(wt[(size_t)cell * 20], feat[cell], a0);
-          hid[b * 20 + i] = lrelu_tc(a0 + a1);
-        } else {
-          const int a = i - 20;
-          float a0 = blob[L.pol_fc_b + a], a1 = 0.0f;
-          const float* wt = pol_fc_t + a;
-          const float* f2 = feat + HW;
-          int k2 = 0;
-          for (; k2 + 1 < 2 * HW; k2 += 2) {
-            a0 = fmaf(wt[(size_t)k2 * gm.A], f2[k2], a0);
-            a1 = fmaf(wt[(size_t)(k2 + 1) * gm.A], f2[k2 + 1], a1);
-          }
-          if (k2 < 2 * HW) a0 = fmaf(wt[(size_t)k2 * gm.A], f2[k2], a0);
-          probs[(size_t)(leaf0 + b) * gm.A + a] = a0 + a1;  // raw logit, normalised below
-        }
-      }
-      __threadfence_block();
-      epi_bar_sync();
-#pragma unroll 1
-      for (int b = warp; b < nvalid; b += 4) {
-        const int lane = tid & 31;
-        if (lane == 0) {
-          float acc = blob[L.val_fc2_b];
-          for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
-          values[leaf0 + b] = tanhf(acc);
-        }
-        float* row = probs + (size_t)(leaf0 + b) * gm.A;  // softmax over all A actions (lib/mcts.py:216)
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int a = lane; a < gm.A; a += 32) mx = fmaxf(mx, row[a]);
-        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        float sum = 0.0f;
-#pragma unroll 1
-        for (int a = lane; a < gm.A; a += 32) sum += expf(row[a] - mx);
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-#pragma unroll 1
-        for (int a = lane; a < gm.A; a += 32) row[a] = expf(row[a] - mx) / sum;
-      }
+      if (tid == 0) TC_TRACE(4, gi);  // last-layer epilogue + next inputs done
     }
   }
 
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -553,7 +609,8 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
   kern<<<grid, kThreads, TcSmem::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
                                                (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                               net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values);
+                                               net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values,
+                                               (long long*)net->d_trace);
   return caro_check_launch("net_tc_kernel");
 }
 

@@ -87,6 +87,9 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
                     caro_net** out);
 int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats);
 void caro_net_destroy(caro_net* net);
+/* Debug only: d_trace = device buffer of >= 8001 int64 (zeroed) that CTA 0 of the tensor-core kernel fills with
+ * (tag, clock64) pairs -- the pipeline timeline used to tune the kernel; NULL switches tracing off. */
+int caro_net_set_trace(caro_net* net, void* d_trace);
 
 /* Forward pass over a compact batch of leaf positions given as boards + side to move.
  *   d_count : device int32 holding the number of valid leaves (<= max_count); read on device, so

@@ -1,0 +1,50 @@
+"""GPU debug: pipeline timeline of CTA 0 of the tcgen05 tower (clock64 stamps)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+
+from caro_ai_b200 import _cabi
+from caro_ai_b200.game import ConnectFour
+from caro_ai_b200.model import DeviceNet, Net
+
+
+def main():
+    leaves = int(sys.argv[1]) if len(sys.argv) > 1 else 10368
+    game = ConnectFour()
+    torch.manual_seed(0)
+    dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
+    boards = torch.zeros((leaves, 2), dtype=torch.int64, device="cuda")
+    who = torch.zeros(leaves, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        dn.forward_boards(boards, who, leaves, 0)
+    trace = torch.zeros(8000, dtype=torch.int64, device="cuda")
+    _cabi.check(_cabi.lib().caro_net_set_trace(dn.handle, trace.data_ptr()))
+    dn.forward_boards(boards, who, leaves, 0)
+    torch.cuda.synchronize()
+    _cabi.check(_cabi.lib().caro_net_set_trace(dn.handle, None))
+    t = trace.cpu().numpy()
+    names = ["mma_start", "mma_issued", "epi_start", "epi_done", "lastepi+inputs", "heads_done", "weights_ok"]
+    ev = []
+    for kind in range(7):
+        for idx in range(1000):
+            v = int(t[kind * 1000 + idx])
+            if v:
+                ev.append((v, kind, idx))
+    ev.sort()
+    t0 = ev[0][0]
+    limit = int(sys.argv[2]) if len(sys.argv) > 2 else 140
+    for clk, kind, idx in ev[:limit]:
+        if kind == 6:
+            print("%8d  %-14s gl=%d mw=%d" % (clk - t0, names[kind], idx // 2, idx % 2))
+        elif kind < 4:
+            print("%8d  %-14s gl=%d t=%d" % (clk - t0, names[kind], idx // 4, idx % 4))
+        else:
+            print("%8d  %-14s group=%d" % (clk - t0, names[kind], idx))
+
+
+if __name__ == "__main__":
+    main()
