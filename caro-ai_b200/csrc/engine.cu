@@ -83,6 +83,7 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   CARVE(W, "W", float, nodes, dm.Apad);
   CARVE(Q, "Q", float, nodes, dm.Apad);
   CARVE(P, "P", float, nodes, dm.Apad);
+  CARVE(C, "C", int32_t, nodes, dm.Apad);
   CARVE(flags, "flags", uint32_t, nodes, dm.FW);
   CARVE(key_hi, "key_hi", uint64_t, nodes);
   CARVE(node_board, "node_board", Board, nodes);
@@ -115,6 +116,7 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   CARVE(leaf_board, "leaf_board", Board, GB);
   CARVE(leaf_player, "leaf_player", uint8_t, GB);
   CARVE(leaf_count, "leaf_count", int32_t, 1);
+  CARVE(noise, "noise", double, dm.G, dm.B, dm.A);
   CARVE(probs, "probs", float, GB, dm.A);
   CARVE(values, "values", float, GB);
   const int64_t rc = dm.replay_cap > 0 ? dm.replay_cap : 1;
@@ -160,19 +162,36 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// group width / actions per lane for the select kernel
+// group width / actions per lane for the select and noise kernels
 template <class R, class Board>
 int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const SearchParams& sp, int batch, int mb,
                   const double* noise, double* noise_out, cudaStream_t st) {
   const long long groups = (long long)dm.G * batch;
   auto grid = [&](int gw) { return (unsigned)((groups * gw + 255) / 256); };
   const int A = dm.A;
-  if (A <= 8) select_kernel<R, 8, 1><<<grid(8), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
-  else if (A <= 16) select_kernel<R, 16, 1><<<grid(16), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
-  else if (A <= 32) select_kernel<R, 32, 1><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
-  else if (A <= 64) select_kernel<R, 32, 2><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
-  else if (A <= 128) select_kernel<R, 32, 4><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
-  else select_kernel<R, 32, 8><<<grid(32), 256, 0, st>>>(v, rules, dm, sp, batch, mb, noise, noise_out);
+  const double* src = noise;
+  if (src == nullptr) {  // Philox path: generate this minibatch's Dirichlet vectors first
+    double* dst = noise_out ? noise_out : v.noise;
+#define NOISE(GW, APL) noise_kernel<GW, APL><<<grid(GW), 256, 0, st>>>(v.uid, v.ply, v.root_player, dm, sp, batch, mb, dst)
+    if (A <= 8) NOISE(8, 1);
+    else if (A <= 16) NOISE(16, 1);
+    else if (A <= 32) NOISE(32, 1);
+    else if (A <= 64) NOISE(32, 2);
+    else if (A <= 128) NOISE(32, 4);
+    else NOISE(32, 8);
+#undef NOISE
+    src = dst;
+  } else if (noise_out != nullptr) {
+    cudaMemcpyAsync(noise_out, noise, sizeof(double) * (size_t)groups * A, cudaMemcpyDeviceToDevice, st);
+  }
+#define SELECT(GW, APL) select_kernel<R, GW, APL><<<grid(GW), 256, 0, st>>>(v, rules, dm, sp, batch, src)
+  if (A <= 8) select_thread_kernel<R, 2><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
+  else if (A <= 16) select_thread_kernel<R, 4><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
+  else if (A <= 32) SELECT(32, 1);
+  else if (A <= 64) SELECT(32, 2);
+  else if (A <= 128) SELECT(32, 4);
+  else SELECT(32, 8);
+#undef SELECT
   return caro_check_launch("select_kernel");
 }
 
@@ -331,21 +350,43 @@ int caro_engine_select(caro_engine* e, int batch, int minibatch_index, const dou
 int caro_engine_plan(caro_engine* e, int batch, void* stream) {
   if (!e) return caro_fail(CARO_E_ARG, "null engine");
   if (batch <= 0 || batch > e->dm.B) return caro_fail(CARO_E_ARG, "batch exceeds max_batch");
-  const unsigned grid = (unsigned)((e->dm.G + 127) / 128);
-  if (e->cfg.game == CARO_GAME_CONNECT4)
-    plan_kernel<C4Board><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch);
-  else
-    plan_kernel<MnkBoard><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch);
+  const bool c4 = e->cfg.game == CARO_GAME_CONNECT4;
+  const int G = e->dm.G;
+#define LAUNCH_PLAN(GP)                                                                                     \
+  do {                                                                                                      \
+    const unsigned grid = (unsigned)(((long long)G * GP + 255) / 256);                                      \
+    if (c4) plan_kernel<C4Board, GP><<<grid, 256, 0, S(stream)>>>(e->v_c4, e->dm, batch);                   \
+    else plan_kernel<MnkBoard, GP><<<grid, 256, 0, S(stream)>>>(e->v_mnk, e->dm, batch);                    \
+  } while (0)
+  if (batch <= 8) LAUNCH_PLAN(8);
+  else if (batch <= 16) LAUNCH_PLAN(16);
+  else if (batch <= 32) LAUNCH_PLAN(32);
+  else {
+    const unsigned grid = (unsigned)((G + 127) / 128);
+    if (c4) plan_serial_kernel<C4Board><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch);
+    else plan_serial_kernel<MnkBoard><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch);
+  }
+#undef LAUNCH_PLAN
   return caro_check_launch("plan_kernel");
 }
 
 int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, const float* d_values, void* stream) {
   if (!e || !d_probs || !d_values) return caro_fail(CARO_E_ARG, "null argument");
   const unsigned grid = (unsigned)(((long long)e->dm.G * 32 + 127) / 128);
-  if (e->cfg.game == CARO_GAME_CONNECT4)
-    expand_backup_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
-  else
-    expand_backup_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch, d_probs, d_values);
+  const bool c4 = e->cfg.game == CARO_GAME_CONNECT4;
+#define LAUNCH_EB(BK)                                                                                               \
+  do {                                                                                                              \
+    if (c4) expand_backup_kernel<C4Rules, BK><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values); \
+    else expand_backup_kernel<MnkRules, BK><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch, d_probs, d_values);  \
+  } while (0)
+  if (batch <= 8) LAUNCH_EB(8);
+  else if (batch <= 16) LAUNCH_EB(16);
+  else if (batch <= 32) LAUNCH_EB(32);
+  else {
+    if (c4) expand_backup_serial_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
+    else expand_backup_serial_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch, d_probs, d_values);
+  }
+#undef LAUNCH_EB
   return caro_check_launch("expand_backup_kernel");
 }
 
@@ -370,7 +411,7 @@ int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int 
     if (rc == CARO_OK) rc = caro_engine_expand_backup(e, batch, pr, va, stream);
     if (prof) cudaEventRecord(e->next_event(), S(stream));
     if (rc != CARO_OK) return rc;
-    e->launches += 4;
+    e->launches += 5;
   }
   return CARO_OK;
 }

@@ -46,6 +46,8 @@ struct View {
   float* W;            // [..][Apad]              total value             (lib/mcts.py:32)
   float* Q;            // [..][Apad]              mean value, f32(W/N)    (lib/mcts.py:34)
   float* P;            // [..][Apad]              priors                  (lib/mcts.py:36)
+  int32_t* C;          // [..][Apad]  cached child node per edge (-1 = not linked yet): a pure cache of the
+                       //             transposition lookup, so an interior step of a descent is ONE dependent access
   uint32_t* flags;     // [..][FW] bit a: W(s,a) has absorbed a float32 net value (numpy promotion state)
   uint64_t* key_hi;    // [..]  upper 64 fingerprint bits (m,n,k only)
   Board* node_board;   // [..]  position of the node (export / dict views)
@@ -82,6 +84,7 @@ struct View {
   Board* leaf_board;   // [G*B]
   uint8_t* leaf_player;  // [G*B]
   int32_t* leaf_count; // [1]
+  double* noise;       // [G][B][A] Dirichlet noise of the coming minibatch (Philox path)
   float* probs;        // [G*B][A]  network outputs (built-in net path)
   float* values;       // [G*B]
   // ---- replay ring -------------------------------------------------------------------------

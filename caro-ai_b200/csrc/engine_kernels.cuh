@@ -94,12 +94,51 @@ struct RulesTraits<C4Rules> {
   static constexpr bool kHasKeyHi = false;
 };
 
+// ------------------------------------------------------------------------------- Dirichlet noise
+// np.random.dirichlet([alpha] * A) for every descent of the coming minibatch (lib/mcts.py:56), Philox-addressed by
+// (seed, game uid, ply, side to move, minibatch, descent, action).  Kept out of select_kernel: the sampler's
+// registers and code would otherwise halve that kernel's occupancy.  Layout float64 [G][batch][A].
+template <int GW, int APL>
+__global__ void __launch_bounds__(256)
+noise_kernel(const uint64_t* __restrict__ uid_g, const int32_t* __restrict__ ply_g, const uint8_t* __restrict__ player_g,
+             Dims dm, SearchParams sp, int batch, int mb_index, double* __restrict__ noise) {
+  const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long grp = gthread / GW;
+  if (grp >= (long long)dm.G * batch) return;
+  const int gl = threadIdx.x & (GW - 1);
+  const unsigned gmask = group_mask<GW>();
+  const int g = (int)(grp / batch), j = (int)(grp % batch);
+  const int A = dm.A;
+  const uint64_t uid = uid_g[g];
+  const uint32_t ply = (uint32_t)ply_g[g];
+  const uint32_t who = player_g[g];
+  float z[APL];
+  float zs = 0.0f;
+#pragma unroll
+  for (int i = 0; i < APL; ++i) {
+    const int a = gl + i * GW;
+    z[i] = 0.0f;
+    if (a < A)
+      z[i] = gamma_small((float)sp.alpha, sp.seed_lo ^ kStreamDirichlet, sp.seed_hi, (uint32_t)uid,
+                         (uint32_t)(uid >> 32) ^ (ply << 16) ^ who, ((uint32_t)(mb_index * batch + j) << 8) | (uint32_t)a);
+    zs += z[i];
+  }
+  double zd = (double)zs;
+#pragma unroll
+  for (int off = GW / 2; off > 0; off >>= 1) zd += __shfl_xor_sync(gmask, zd, off);
+#pragma unroll
+  for (int i = 0; i < APL; ++i) {
+    const int a = gl + i * GW;
+    if (a < A) noise[((size_t)g * batch + j) * A + a] = __ddiv_rn((double)z[i], zd);
+  }
+}
+
 // ---------------------------------------------------------------------------------- select
 // One group of GW lanes per descent, APL actions per lane (action = lane + i*GW).
 template <class R, int GW, int APL>
-__global__ void __launch_bounds__(256)
-select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch, int mb_index,
-              const double* __restrict__ noise_in, double* __restrict__ noise_out) {
+__global__ void __launch_bounds__(256, (APL == 1 && sizeof(typename R::Board) <= 16) ? 7 : 1)
+select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
+              const double* __restrict__ noise_in) {
   using Board = typename R::Board;
   const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gthread == 0) {
@@ -121,7 +160,6 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   const int A = dm.A;
   Board s = e.root_board[g];
   int who = e.root_player[g];
-  const int root_who = who;
   const int tree = g * dm.tpg + (dm.tpg == 2 ? who : 0);
   const uint32_t gen = e.tree_gen[tree];
   const HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
@@ -140,7 +178,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
 
   while (node >= 0) {
     const size_t row = (nb + (size_t)node) * dm.Apad;
-    int n_loc[APL];
+    int n_loc[APL], c_loc[APL];
     float q_loc[APL], p_loc[APL];
     int sum_n = 0;
 #pragma unroll
@@ -150,10 +188,12 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
         n_loc[i] = e.N[row + a];
         q_loc[i] = e.Q[row + a];
         p_loc[i] = e.P[row + a];
+        c_loc[i] = e.C[row + a];
       } else {
         n_loc[i] = 0;
         q_loc[i] = 0.0f;
         p_loc[i] = 0.0f;
+        c_loc[i] = -1;
       }
       sum_n += n_loc[i];
     }
@@ -165,38 +205,10 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
     if (depth == 0) {
       // ---- root: Dirichlet noise + float64 scores (lib/mcts.py:48-62,131-132) -------------
       double z[APL];
-      if (noise_in != nullptr) {
 #pragma unroll
-        for (int i = 0; i < APL; ++i) {
-          const int a = gl + i * GW;
-          z[i] = (a < A) ? noise_in[((size_t)g * batch + j) * A + a] : 0.0;
-        }
-      } else {
-        double zs = 0.0;
-        const uint64_t uid = e.uid[g];
-        const uint32_t ply = (uint32_t)e.ply[g];
-#pragma unroll
-        for (int i = 0; i < APL; ++i) {
-          const int a = gl + i * GW;
-          z[i] = 0.0;
-          if (a < A) {
-            z[i] = (double)gamma_small((float)sp.alpha, sp.seed_lo ^ kStreamDirichlet, sp.seed_hi,
-                                       (uint32_t)uid, (uint32_t)(uid >> 32) ^ (ply << 16) ^ (uint32_t)root_who,
-                                       ((uint32_t)(mb_index * batch + j) << 8) | (uint32_t)a);
-          }
-          zs += z[i];
-        }
-#pragma unroll
-        for (int off = GW / 2; off > 0; off >>= 1) zs += __shfl_xor_sync(gmask, zs, off);
-#pragma unroll
-        for (int i = 0; i < APL; ++i) z[i] = __ddiv_rn(z[i], zs);
-      }
-      if (noise_out != nullptr) {
-#pragma unroll
-        for (int i = 0; i < APL; ++i) {
-          const int a = gl + i * GW;
-          if (a < A) noise_out[((size_t)g * batch + j) * A + a] = z[i];
-        }
+      for (int i = 0; i < APL; ++i) {
+        const int a = gl + i * GW;
+        z[i] = (a < A) ? noise_in[((size_t)g * batch + j) * A + a] : 0.0;
       }
       const double sq = sqrt((double)sum_n);
 #pragma unroll
@@ -218,7 +230,9 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
       }
     } else {
       // ---- interior: float32 scores (lib/mcts.py:64-84 under NEP 50) ----------------------
-      const float sq = (float)sqrt((double)sum_n);
+      // float32(math.sqrt(sum N)): for integers below 2^24 the float64 root rounded to float32 equals the correctly
+      // rounded float32 root (no double-rounding case exists), so the cheap instruction is bit-identical
+      const float sq = __fsqrt_rn((float)sum_n);
 #pragma unroll
       for (int i = 0; i < APL; ++i) {
         const int a = gl + i * GW;
@@ -261,7 +275,18 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
       break;
     }
     key = rules.key(s);
-    node = ht_lookup<GW>(ht, dm.hash_cap, gen, key, khi, gl, gmask);
+    // child link cached on the edge?  (set the first time the lookup succeeds; nodes are never removed)
+    int mine = -1;
+#pragma unroll
+    for (int i = 0; i < APL; ++i)
+      if (i == a / GW) mine = c_loc[i];
+    const int linked = __shfl_sync(gmask, mine, ((threadIdx.x & 31) & ~(GW - 1)) + (a % GW));
+    if (linked >= 0) {
+      node = linked;
+    } else {
+      node = ht_lookup<GW>(ht, dm.hash_cap, gen, key, khi, gl, gmask);
+      if (node >= 0 && gl == 0) e.C[row + a] = node;
+    }
   }
   if (gl == 0) {
     e.d_kind[di] = (uint8_t)kind;
@@ -275,13 +300,137 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   }
 }
 
+// Thread-per-descent variant for small action spaces (A <= 16: Connect4, 3x3 / 4x4 boards).  The board update,
+// key and transposition probe are scalar work; with one lane-group per descent they are replicated on every
+// lane and the kernel becomes issue-bound (ncu: 12.7 M warp instructions per launch).  Here each lane owns a whole
+// descent and loops over the <= 16 actions; the arithmetic and its order are identical to select_kernel.
+template <class R, int ROWV>  // ROWV = Apad / 4 = number of 16-byte vectors per row
+__global__ void __launch_bounds__(128)
+select_thread_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
+                     const double* __restrict__ noise_in) {
+  using Board = typename R::Board;
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp == 0) *e.leaf_count = 0;
+  if (grp >= (long long)dm.G * batch) return;
+  const int g = (int)(grp / batch), j = (int)(grp % batch);
+  const size_t di = (size_t)g * dm.B + j;
+  if (e.status[g] != ST_ACTIVE) {
+    e.d_kind[di] = KIND_SKIP;
+    e.d_slot[di] = -1;
+    return;
+  }
+  const int A = dm.A;
+  Board s = e.root_board[g];
+  int who = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? who : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  const HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const uint64_t* khi = RulesTraits<R>::kHasKeyHi ? (e.key_hi + nb) : nullptr;
+  const float c_f = (float)sp.c_puct;
+  const float keep_f = (float)(1.0 - sp.explore);
+  Key128 key = rules.key(s);
+  int node = ht_lookup1(ht, dm.hash_cap, gen, key, khi);
+  int depth = 0, kind = KIND_EXPAND;
+  float term_value = 0.0f;
+  int32_t* path_node = e.d_path_node + di * dm.max_depth;
+  uint8_t* path_action = e.d_path_action + di * dm.max_depth;
+  while (node >= 0) {
+    const size_t row = (nb + (size_t)node) * dm.Apad;
+    int n_loc[ROWV * 4], c_loc[ROWV * 4];
+    float q_loc[ROWV * 4], p_loc[ROWV * 4];
+#pragma unroll
+    for (int v = 0; v < ROWV; ++v) {
+      const int4 nv = reinterpret_cast<const int4*>(e.N + row)[v];
+      const float4 qv = reinterpret_cast<const float4*>(e.Q + row)[v];
+      const float4 pv = reinterpret_cast<const float4*>(e.P + row)[v];
+      const int4 cv = reinterpret_cast<const int4*>(e.C + row)[v];
+      n_loc[4 * v] = nv.x; n_loc[4 * v + 1] = nv.y; n_loc[4 * v + 2] = nv.z; n_loc[4 * v + 3] = nv.w;
+      q_loc[4 * v] = qv.x; q_loc[4 * v + 1] = qv.y; q_loc[4 * v + 2] = qv.z; q_loc[4 * v + 3] = qv.w;
+      p_loc[4 * v] = pv.x; p_loc[4 * v + 1] = pv.y; p_loc[4 * v + 2] = pv.z; p_loc[4 * v + 3] = pv.w;
+      c_loc[4 * v] = cv.x; c_loc[4 * v + 1] = cv.y; c_loc[4 * v + 2] = cv.z; c_loc[4 * v + 3] = cv.w;
+    }
+    int sum_n = 0;
+#pragma unroll
+    for (int a = 0; a < ROWV * 4; ++a) sum_n += (a < A) ? n_loc[a] : 0;
+    double best = -INFINITY;
+    int best_a = 0, best_c = -1;
+    if (depth == 0) {  // root: Dirichlet noise + float64 scores (lib/mcts.py:48-62,131-132)
+      const double sq = sqrt((double)sum_n);
+      const uint32_t fl = e.flags[(nb + (size_t)node) * dm.FW];
+      const double* z = noise_in + ((size_t)g * batch + j) * A;
+#pragma unroll
+      for (int a = 0; a < ROWV * 4; ++a) {
+        if (a < A && rules.legal(s, a)) {
+          const double pn = __dadd_rn((double)__fmul_rn(keep_f, p_loc[a]), __dmul_rn(sp.explore, z[a]));
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq), (double)(1 + n_loc[a]));
+          double q64 = (double)q_loc[a];
+          if (!((fl >> a) & 1u) && n_loc[a] > 0) q64 = __ddiv_rn((double)e.W[row + a], (double)n_loc[a]);
+          const double sc = __dadd_rn(q64, u);
+          if (sc > best) {
+            best = sc;
+            best_a = a;
+            best_c = c_loc[a];
+          }
+        }
+      }
+    } else {  // interior: float32 scores (lib/mcts.py:64-84 under NEP 50)
+      const float sq = __fsqrt_rn((float)sum_n);
+      float bestf = -INFINITY;
+#pragma unroll
+      for (int a = 0; a < ROWV * 4; ++a) {
+        if (a < A && rules.legal(s, a)) {
+          const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p_loc[a]), sq), (float)(1 + n_loc[a]));
+          const float sc = __fadd_rn(q_loc[a], t);
+          if (sc > bestf) {
+            bestf = sc;
+            best_a = a;
+            best_c = c_loc[a];
+          }
+        }
+      }
+    }
+    const int a = best_a;
+    path_node[depth] = node;
+    path_action[depth] = (uint8_t)a;
+    ++depth;
+    const bool won = rules.apply(s, a, who);
+    who ^= 1;
+    if (won) {
+      kind = KIND_TERMINAL;
+      term_value = -1.0f;
+      break;
+    }
+    if (!rules.any_legal(s)) {
+      kind = KIND_TERMINAL;
+      term_value = 0.0f;
+      break;
+    }
+    key = rules.key(s);
+    if (best_c >= 0) {
+      node = best_c;
+    } else {
+      node = ht_lookup1(ht, dm.hash_cap, gen, key, khi);
+      if (node >= 0) e.C[row + a] = node;
+    }
+  }
+  e.d_kind[di] = (uint8_t)kind;
+  e.d_value[di] = term_value;
+  e.d_board[di] = s;
+  e.d_player[di] = (uint8_t)who;
+  e.d_key_lo[di] = key.lo;
+  e.d_key_hi[di] = key.hi;
+  e.d_path_len[di] = depth;
+  e.d_slot[di] = -1;
+}
+
 // ------------------------------------------------------------------------------------ plan
-// One thread per game: back-up queue = terminal descents in descent order, then the first
+// Serial variant (batch > 32), one thread per game: back-up queue = terminal descents in descent order, then the first
 // occurrence of every distinct new leaf (lib/mcts.py:265-278); unique leaves are appended to the
 // compact batch (order across games is arbitrary; results do not depend on it).
 template <class Board>
 __global__ void __launch_bounds__(128)
-plan_kernel(View<Board> e, Dims dm, int batch) {
+plan_serial_kernel(View<Board> e, Dims dm, int batch) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int n_term = 0, n_new = 0;
@@ -332,13 +481,82 @@ plan_kernel(View<Board> e, Dims dm, int batch) {
   atomicAdd(e.ctr + CTR_DESCENTS, (unsigned long long)batch);
 }
 
+// Lane-parallel variant (batch <= 32): GP lanes per game, lane j owns descent j, so every load of the
+// per-descent records is issued at once instead of as a dependent chain.
+template <class Board, int GP>
+__global__ void __launch_bounds__(256)
+plan_kernel(View<Board> e, Dims dm, int batch) {
+  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = gthread / GP;
+  const int j = threadIdx.x & (GP - 1);
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane & ~(GP - 1);
+  const unsigned gmask = group_mask<GP>();
+  const bool in_range = g < dm.G;
+  const bool live = in_range && e.status[g] == ST_ACTIVE;
+  const size_t d0 = (size_t)(in_range ? g : 0) * dm.B;
+  int kind = KIND_SKIP;
+  uint64_t lo = 0, hi = 0;
+  if (live && j < batch) {
+    kind = e.d_kind[d0 + j];
+    lo = e.d_key_lo[d0 + j];
+    hi = e.d_key_hi[d0 + j];
+  }
+  const unsigned below = (1u << j) - 1u;
+  const unsigned term_m = (__ballot_sync(gmask, kind == KIND_TERMINAL) >> gbase) & ((GP == 32) ? 0xffffffffu : ((1u << GP) - 1u));
+  bool dup = false;
+#pragma unroll
+  for (int i = 0; i < GP; ++i) {
+    const uint64_t olo = __shfl_sync(gmask, lo, gbase + i);
+    const uint64_t ohi = __shfl_sync(gmask, hi, gbase + i);
+    const int okind = __shfl_sync(gmask, kind, gbase + i);
+    dup = dup || (i < j && okind == KIND_EXPAND && olo == lo && ohi == hi);
+  }
+  const bool uniq = kind == KIND_EXPAND && !dup;
+  const unsigned uniq_m = (__ballot_sync(gmask, uniq) >> gbase) & ((GP == 32) ? 0xffffffffu : ((1u << GP) - 1u));
+  const int n_term = __popc(term_m), n_new = __popc(uniq_m);
+  // reservation in the compact leaf batch: one atomic per warp
+  int base = 0;
+  {
+    const int mine = (j == 0) ? n_new : 0;
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int wbase = 0;
+    if (lane == 31 && warp_total > 0) wbase = atomicAdd(e.leaf_count, warp_total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    base = __shfl_sync(0xffffffffu, wbase + incl - mine, gbase);  // exclusive prefix at the group leader
+  }
+  if (!in_range) return;
+  if (j == 0) e.q_len[g] = live ? n_term + n_new : 0;
+  if (!live) return;
+  if (kind == KIND_TERMINAL) {
+    e.q_order[d0 + __popc(term_m & below)] = (uint8_t)j;
+  } else if (uniq) {
+    const int r = __popc(uniq_m & below);
+    e.q_order[d0 + n_term + r] = (uint8_t)j;
+    const int slot = base + r;
+    e.d_slot[d0 + j] = slot;
+    e.leaf_board[slot] = e.d_board[d0 + j];
+    e.leaf_player[slot] = e.d_player[d0 + j];
+  }
+  if (j == 0) {
+    if (n_new) atomicAdd(e.ctr + CTR_LEAVES, (unsigned long long)n_new);
+    atomicAdd(e.ctr + CTR_DESCENTS, (unsigned long long)batch);
+  }
+}
+
 // --------------------------------------------------------------------------- expand + backup
 // One warp per game.  Queue entries are applied strictly in order (float32 W sums are order
 // dependent); inside an entry the lanes take one edge of the path each (edges of one path are
 // distinct nodes, and an edge always sits at the same depth, hence on the same lane).
 template <class R>
 __global__ void __launch_bounds__(128)
-expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
+expand_backup_serial_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
                      const float* __restrict__ values) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -368,6 +586,7 @@ expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float*
           e.N[row + a] = 0;
           e.W[row + a] = 0.0f;
           e.Q[row + a] = 0.0f;
+          e.C[row + a] = -1;
         }
         for (int w = lane; w < dm.FW; w += 32) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
         if (lane == 0) {
@@ -400,6 +619,144 @@ expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float*
     __syncwarp();
   }
   if (lane == 0) e.node_count[tree] = count;
+}
+
+// Claim a hash slot for `key_lo` with a CAS on the generation word, so that the (<= batch) insertions of one
+// minibatch can proceed concurrently from different lanes.  Keys of one minibatch are distinct (plan dedup).
+__device__ __forceinline__ void ht_insert_cas(HashSlot* __restrict__ ht, int cap, uint32_t gen, uint64_t key_lo, int node) {
+  uint32_t idx = slot_home(key_lo, cap);
+  for (int it = 0; it < cap; ++it) {
+    uint32_t* gword = reinterpret_cast<uint32_t*>(ht + idx) + 3;
+    const uint32_t seen = *gword;
+    if (seen != gen && atomicCAS(gword, seen, gen) == seen) {
+      ht[idx].key = key_lo;
+      ht[idx].node = node;
+      return;
+    }
+    idx = (idx + 1u) & (uint32_t)(cap - 1);
+  }
+}
+
+// Batched variant (batch <= BK <= 32).  One warp per game.
+//   phase 1: lane q owns queue entry q: its metadata chain (order -> kind/slot/value/path length) is loaded by all
+//            lanes at once; new nodes get their arena index by a warp prefix sum and their hash slot by CAS;
+//   phase 2: lane i owns path depth i (an edge always sits at the same depth, hence on the same lane): it loads
+//            N/W of its edge in EVERY queued path up front, then replays the queue IN ORDER in registers
+//            (float32 W sums are order dependent), forwarding values between entries that hit the same edge,
+//            and stores each distinct edge once.
+template <class R, int BK>
+__global__ void __launch_bounds__(128)
+expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
+                     const float* __restrict__ values) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= dm.G || e.status[g] != ST_ACTIVE) return;
+  const int who0 = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? who0 : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const size_t d0 = (size_t)g * dm.B;
+  const int qn = e.q_len[g];
+  const int count0 = e.node_count[tree];
+  // ---- phase 1 -------------------------------------------------------------------------------------
+  int my_di = 0, my_kind = KIND_SKIP, my_slot = -1, my_len = 0;
+  float my_val = 0.0f;
+  if (lane < qn) {
+    my_di = (int)e.q_order[d0 + lane];
+    my_kind = e.d_kind[d0 + my_di];
+    my_len = e.d_path_len[d0 + my_di];
+    if (my_kind == KIND_EXPAND) {
+      my_slot = e.d_slot[d0 + my_di];
+      my_val = values[my_slot];
+    } else {
+      my_val = e.d_value[d0 + my_di];
+    }
+  }
+  const unsigned exp_m = __ballot_sync(0xffffffffu, my_kind == KIND_EXPAND);
+  const int n_new = __popc(exp_m);
+  int my_node = count0 + __popc(exp_m & ((1u << lane) - 1u));
+  const bool creates = my_kind == KIND_EXPAND && my_node < dm.node_cap;
+  if (my_kind == KIND_EXPAND && !creates) atomicOr(e.ctr + CTR_ERRORS, ERR_ARENA_FULL);
+  if (creates) {  // _create_node, lib/mcts.py:178-190 (scalars + hash slot by the owning lane)
+    const size_t di = d0 + my_di;
+    e.node_board[nb + my_node] = e.d_board[di];
+    e.node_player[nb + my_node] = e.d_player[di];
+    if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + my_node] = e.d_key_hi[di];
+    ht_insert_cas(ht, dm.hash_cap, gen, e.d_key_lo[di], my_node);
+  }
+  // rows of the new nodes, all lanes cooperating
+  for (int q = 0; q < qn; ++q) {
+    const bool cr = __shfl_sync(0xffffffffu, (int)creates, q) != 0;
+    if (!cr) continue;
+    const int node = __shfl_sync(0xffffffffu, my_node, q);
+    const int slot = __shfl_sync(0xffffffffu, my_slot, q);
+    const size_t row = (nb + (size_t)node) * dm.Apad;
+    for (int a = lane; a < dm.Apad; a += 32) {
+      e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
+      e.N[row + a] = 0;
+      e.W[row + a] = 0.0f;
+      e.Q[row + a] = 0.0f;
+      e.C[row + a] = -1;
+    }
+    for (int w = lane; w < dm.FW; w += 32) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
+  }
+  if (lane == 0) e.node_count[tree] = min(count0 + n_new, dm.node_cap);
+  // ---- phase 2: _backup, lib/mcts.py:225-246 ---------------------------------------------------------
+  int max_len = my_len;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, off));
+  for (int i0 = 0; i0 < max_len; i0 += 32) {
+    const int i = i0 + lane;
+    long long idx[BK];
+    int n_v[BK];
+    float w_v[BK], cur[BK];
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      const int di = __shfl_sync(0xffffffffu, my_di, q);
+      const int len = __shfl_sync(0xffffffffu, my_len, q);
+      const float v = __shfl_sync(0xffffffffu, my_val, q);
+      const int kind = __shfl_sync(0xffffffffu, my_kind, q);
+      idx[q] = -1;
+      n_v[q] = 0;
+      w_v[q] = 0.0f;
+      cur[q] = 0.0f;
+      if (q < qn && i < len) {
+        const size_t pi = (d0 + di) * dm.max_depth + i;
+        const int node = e.d_path_node[pi];
+        const int a = e.d_path_action[pi];
+        idx[q] = (long long)((nb + (size_t)node) * dm.Apad + a);
+        n_v[q] = e.N[idx[q]];
+        w_v[q] = e.W[idx[q]];
+        cur[q] = ((len - 1 - i) & 1) ? v : -v;
+        if (kind == KIND_EXPAND) atomicOr(e.flags + (nb + (size_t)node) * dm.FW + (a >> 5), 1u << (a & 31));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      if (idx[q] < 0) continue;
+#pragma unroll
+      for (int p = 0; p < q; ++p)
+        if (idx[p] == idx[q]) {  // latest earlier entry on the same edge wins (p ascending)
+          n_v[q] = n_v[p];
+          w_v[q] = w_v[p];
+        }
+      n_v[q] += 1;
+      w_v[q] = __fadd_rn(w_v[q], cur[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      if (idx[q] < 0) continue;
+      bool last = true;
+#pragma unroll
+      for (int p = q + 1; p < BK; ++p) last = last && (idx[p] != idx[q]);
+      if (last) {
+        e.N[idx[q]] = n_v[q];
+        e.W[idx[q]] = w_v[q];
+        e.Q[idx[q]] = __fdiv_rn(w_v[q], (float)n_v[q]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ root policy

@@ -43,25 +43,38 @@ CARO_HD double u01d(uint32_t hi, uint32_t lo) {
 // Stream tags
 enum : uint32_t { kStreamDirichlet = 0x44495243u, kStreamChoice = 0x43484F49u, kStreamFirst = 0x46495253u };
 
-// Gamma(alpha, 1) for alpha < 1 via Marsaglia-Tsang on alpha+1 and the U^(1/alpha) boost.
-// `ctr_*` address the stream; the rejection loop walks c3.
+// Device code uses the fast-math intrinsics: the noise only has to be distributed correctly, and whatever is
+// generated is what both the engine and (through noise_out) the oracle consume.
+#if defined(__CUDA_ARCH__)
+#define CARO_LOGF(x) __logf(x)
+#define CARO_EXPF(x) __expf(x)
+#define CARO_COSF(x) __cosf(x)
+#else
+#define CARO_LOGF(x) logf(x)
+#define CARO_EXPF(x) expf(x)
+#define CARO_COSF(x) cosf(x)
+#endif
+
+// Gamma(alpha, 1) for alpha < 1 via Marsaglia-Tsang on alpha+1 (with the x^4 squeeze) and the U^(1/alpha)
+// boost.  `c0..c2` address the stream; the rejection loop walks c3.
 CARO_HD float gamma_small(float alpha, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
   const float d = alpha + 1.0f - 1.0f / 3.0f;
   const float c = 1.0f / sqrtf(9.0f * d);
+  const float inv_alpha = 1.0f / alpha;
   float g = d;  // fallback if the loop somehow exhausts
   for (uint32_t it = 0; it < 64u; ++it) {
     const Philox4 r = philox4x32_10(c0, c1, c2, it, k0, k1);
     // Box-Muller normal from r.v[0], r.v[1]
     const float u1 = u01(r.v[0]), u2 = u01(r.v[1]);
-    const float x = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+    const float x = sqrtf(-2.0f * CARO_LOGF(u1)) * CARO_COSF(6.283185307179586f * u2);
     float v = 1.0f + c * x;
     if (v <= 0.0f) continue;
     v = v * v * v;
     const float u = u01(r.v[2]);
-    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) {
+    const float x2 = x * x;
+    if (u < 1.0f - 0.0331f * x2 * x2 || CARO_LOGF(u) < 0.5f * x2 + d - d * v + d * CARO_LOGF(v)) {
       // boost: Gamma(alpha) = Gamma(alpha+1) * U^(1/alpha)
-      const float ub = u01(r.v[3]);
-      g = d * v * expf(logf(ub) / alpha);
+      g = d * v * CARO_EXPF(CARO_LOGF(u01(r.v[3])) * inv_alpha);
       break;
     }
   }

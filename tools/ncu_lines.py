@@ -33,10 +33,19 @@ def main():
             m = re.search(r"/\*([0-9a-f]{4,5})\*/", line)
             if m and infn and cur:
                 off2line.setdefault(int(m.group(1), 16), cur)
-    rows = list(csv.reader(open(src_csv)))
+    allrows = list(csv.reader(open(src_csv)))
+    # the csv holds one section per profiled kernel: "Kernel Name",<name> / header / rows
+    starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+    want = kern.split("INS_")[0].replace("_ZN4caro", "").lstrip("0123456789")
+    sec = None
+    for n, i in enumerate(starts):
+        if want in allrows[i][1] or len(starts) == 1:
+            sec = (i, starts[n + 1] if n + 1 < len(starts) else len(allrows))
+            break
+    rows = allrows[sec[0]:sec[1]]
     hdr = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    data = rows[2:]
+    data = [r for r in rows[2:] if len(r) == len(hdr)]
     base = int(data[0][idx["Address"]], 16)
     c, tot = Counter(), 0
     for r in data:
