@@ -7,7 +7,8 @@
 One "step" = one ply of lock-step self-play for every game of the batch: MCTS.search_batch(100, 8)
 (= 800 descents, lib/mcts.py:162-176) on each of the G games, then the policy / sampling / move of
 lib/utils.py:76-99, finished games re-seated immediately.  Workload = BASELINE.json configs[1]:
-Connect4 6x7, 800 sims/move, 4096 concurrent games per B200, random-init 5x64 residual network,
+Connect4 6x7, 800 sims/move, >= 4096 concurrent games per B200 (default 2 x 4096: two half-batches pipelined
+against each other), random-init 5x64 residual network,
 tau = 1 for 10 plies, c_puct 1.0, Dirichlet(0.3) eps 0.25.  Synthetic: no dataset, seeded weights.
 
 Prints ONE JSON line (see the keys in DESIGN.md section 7).  Multi-GPU: one process per GPU under
@@ -27,7 +28,7 @@ if ROOT not in sys.path:
 
 FLOP_PER_LEAF_C4 = 15598672  # conv_in 96,768*... + 5 x 3,096,576*... + heads (2 x MAC)
 SIMS_COUNT, SIMS_BATCH, TAU_PLIES = 100, 8, 10
-GAMES_PER_GPU = 4096
+GAMES_PER_GPU = 8192  # two software-pipelined half-batches of 4096 (north_star: >= 4096 concurrent games per GPU)
 NODE_CAPACITY = 24576
 
 
@@ -184,9 +185,11 @@ def engine_arm(args):
     net = Net(game.obs_shape, game.action_space).eval()
     dnet = DeviceNet(net, game)
     G = args.games
-    eng = SelfPlayEngine(game, G, trees_per_game=1, max_batch=SIMS_BATCH, node_capacity=args.node_capacity,
-                         replay_capacity=1 << 20, seed=1234 + rank)
-    # stagger game phases so that the timed window sees the steady-state mix of plies, not 4096 openings
+    # the game batch is split in two halves that are software-pipelined against each other (one half's tree kernels
+    # run on a side stream underneath the other half's network pass); --no-pipeline keeps one engine, one stream
+    halves = 1 if args.no_pipeline else 2
+    engs = [SelfPlayEngine(game, G // halves, trees_per_game=1, max_batch=SIMS_BATCH, node_capacity=args.node_capacity,
+                           replay_capacity=1 << 19, seed=1234 + 16 * rank + h) for h in range(halves)]
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -195,50 +198,70 @@ def engine_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def kernel_steps(n):
-        eng.play(dnet, dnet, moves=n, count=SIMS_COUNT, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+    def play(n, count=SIMS_COUNT):
+        if halves == 2:
+            engs[0].play_pair(engs[1], dnet, moves=n, count=count, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+        else:
+            engs[0].play(dnet, dnet, moves=n, count=count, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+
+    def counters():
+        tot = {}
+        for e in engs:
+            for k, v in e.counters().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
 
     # untimed pre-roll with a cheap search so that the games de-synchronise (finished games re-seat at once):
     # the timed window then sees a mix of openings, middle games and endgames instead of 4096 identical plies
-    eng.play(dnet, dnet, moves=args.preroll, count=8, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
-    kernel_steps(args.warmup)
+    play(args.preroll, count=8)
+    play(args.warmup)
     barrier()
-    c0 = eng.counters()
-    eng.profile(True)
+    c0 = counters()
+    for e in engs:
+        e.profile(args.profile_level)
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    kernel_steps(args.steps)
+    play(args.steps)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    prof = eng.profile_read()
-    eng.profile(False)
-    c1 = eng.counters()
+    prof = {}
+    for e in engs:
+        for k, v in e.profile_read().items():
+            prof[k] = prof.get(k, 0) + v
+        e.profile(0)
+    c1 = counters()
 
-    # ---- end-to-end: same plies driven through HOST buffers (pinned H2D of the roots, D2H of the results)
-    boards_h = torch.empty((G, 2), dtype=torch.int64).pin_memory()
-    players_h = torch.empty((G,), dtype=torch.uint8).pin_memory()
-    out_h = {"pi": torch.empty((G, 7), dtype=torch.float64).pin_memory(), "actions": torch.empty((G,), dtype=torch.int32).pin_memory(),
-             "boards": boards_h, "players": players_h}
-    boards_h.copy_(eng.region("root_board"))
-    players_h.copy_(eng.region("root_player"))
+    # ---- end-to-end: same plies driven through HOST buffers (pinned H2D of the roots, D2H of the new roots)
+    Gh = G // halves
+    boards_h = [torch.empty((Gh, 2), dtype=torch.int64).pin_memory() for _ in engs]
+    players_h = [torch.empty((Gh,), dtype=torch.uint8).pin_memory() for _ in engs]
+    for e, bh, ph in zip(engs, boards_h, players_h):
+        bh.copy_(e.region("root_board"))
+        ph.copy_(e.region("root_player"))
     torch.cuda.synchronize()
     e2e_steps = max(1, args.steps // 2)
     barrier()
-    ce0 = eng.counters()
+    ce0 = counters()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(stream)
     for _ in range(e2e_steps):
-        eng.step_host(boards_h, players_h, dnet, SIMS_COUNT, SIMS_BATCH, TAU_PLIES, out_h)
-        stream.synchronize()  # the host owns the buffers between plies (it reads pi / actions, re-submits roots)
+        for e, bh, ph in zip(engs, boards_h, players_h):
+            e.set_roots_pinned(bh, ph)                      # H2D: this ply's positions + side to move
+        play(1)
+        for e, bh, ph in zip(engs, boards_h, players_h):
+            bh.copy_(e.region("root_board"), non_blocking=True)   # D2H: positions after the move (re-seated if finished)
+            ph.copy_(e.region("root_player"), non_blocking=True)
+        stream.synchronize()  # the host owns the buffers between plies
     ee1.record(stream)
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     e2e_ms = ee0.elapsed_time(ee1)
-    ce1 = eng.counters()
+    ce1 = counters()
+    workspace_gb = sum(e.workspace_bytes for e in engs) / 1e9
 
     def allmax(x):
         if world == 1:
@@ -267,7 +290,7 @@ def engine_arm(args):
         sec = ms_max / 1000.0
         my_leaf = c1["leaf_evals"] - c0["leaf_evals"]
         net_s = prof["net_ms"] / 1000.0
-        n_net_launches = args.steps * SIMS_COUNT
+        n_net_launches = args.steps * SIMS_COUNT * halves
         achieved_tflops = my_leaf * FLOP_PER_LEAF_C4 / net_s / 1e12 if net_s > 0 else 0.0
         line = {
             "metric": "connect4_mcts_leaf_evals_per_sec", "value": leaf / sec, "unit": "leaf_evals/s", "n_gpus": world,
@@ -276,19 +299,20 @@ def engine_arm(args):
             "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, %d concurrent games per GPU, "
                                    "random-init 5x64 residual net (bf16 tcgen05, fp32 accumulate), tau=1 for 10 plies" % G,
                        "games_per_gpu": G, "sims_per_move": SIMS_COUNT * SIMS_BATCH, "node_capacity": args.node_capacity,
+                       "pipeline": "2 half-batches, tree kernels on side streams under the other half's network pass" if halves == 2 else "single stream",
                        "cache": "tree arenas %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
-                                % (eng.workspace_bytes / 1e9)},
+                                % workspace_gb},
             "games_per_sec": games / sec, "plies_per_sec": plies / sec, "descents_per_sec": desc / sec,
             "e2e": {"value": e2e_leaf / (e2e_max / 1000.0), "unit": "leaf_evals/s", "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(world * (boards_h.numel() * 8 + players_h.numel())),
-                    "d2h_bytes_per_step": int(world * (out_h["pi"].numel() * 8 + out_h["actions"].numel() * 4 + boards_h.numel() * 8 + players_h.numel()))},
+                    "h2d_bytes_per_step": int(world * G * 17), "d2h_bytes_per_step": int(world * G * 17)},
             "gpu_launches": int(prof["launches"]),
             "roofline": {"kernel": "net_tc_kernel (tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
                          "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),
                          "avg_launch_ms": prof["net_ms"] / max(1, n_net_launches)},
-            "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")},
+            "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
+                                  if args.profile_level >= 2 or k == "net_ms"},
             "clocks": sampler.summary(), "engine_errors": int(errors),
         }
         if not args.no_cpu_baseline and world >= 1:
@@ -306,13 +330,15 @@ def engine_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--node-capacity", type=int, default=NODE_CAPACITY)
     ap.add_argument("--cpu-plies", type=int, default=20)
     ap.add_argument("--preroll", type=int, default=30)
+    ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--profile-level", type=int, default=1, help="1: CUDA events around the network kernel only, 2: all phases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

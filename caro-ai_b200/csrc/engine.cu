@@ -56,17 +56,31 @@ struct caro_engine {
   View<MnkBoard> v_mnk;
   MnkRules mnk;
   // optional per-phase CUDA-event timing of the search loop (bench / roofline accounting)
-  bool profiling = false;
+  int profiling = 0;  // 0 off, 1 network spans only (cheap: 2 events per minibatch), 2 all four phases
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
+  std::vector<std::pair<size_t, size_t>> spans[4];  // (start, end) event indices per phase
+  size_t open_span[4] = {0, 0, 0, 0};
   unsigned long long launches = 0;
-  cudaEvent_t next_event() {
+  cudaEvent_t sync_a = nullptr, sync_b = nullptr;  // cross-stream hand-offs (pair pipeline)
+  size_t next_event() {
     if (events_used == events.size()) {
       cudaEvent_t ev;
       cudaEventCreate(&ev);
       events.push_back(ev);
     }
-    return events[events_used++];
+    return events_used++;
+  }
+  void span_begin(int ph, cudaStream_t st) {
+    if (profiling == 0 || (profiling == 1 && ph != 2)) return;
+    open_span[ph] = next_event();
+    cudaEventRecord(events[open_span[ph]], st);
+  }
+  void span_end(int ph, cudaStream_t st) {
+    if (profiling == 0 || (profiling == 1 && ph != 2)) return;
+    const size_t ev = next_event();
+    cudaEventRecord(events[ev], st);
+    spans[ph].push_back({open_span[ph], ev});
   }
 };
 
@@ -257,14 +271,17 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
 void caro_engine_destroy(caro_engine* e) {
   if (!e) return;
   for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
+  if (e->sync_a) cudaEventDestroy(e->sync_a);
+  if (e->sync_b) cudaEventDestroy(e->sync_b);
   delete e;
 }
 
 int caro_engine_profile(caro_engine* e, int enable) {
   if (!e) return caro_fail(CARO_E_ARG, "null engine");
-  e->profiling = enable != 0;
+  e->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   e->events_used = 0;
   e->launches = 0;
+  for (auto& v : e->spans) v.clear();
   return CARO_OK;
 }
 
@@ -272,13 +289,14 @@ int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launche
   if (!e || !h_ms) return caro_fail(CARO_E_ARG, "null argument");
   cudaError_t ce = cudaStreamSynchronize(S(stream));
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
-  for (int i = 0; i < 4; ++i) h_ms[i] = 0.0;
-  for (size_t i = 0; i + 5 <= e->events_used; i += 5) {
-    for (int ph = 0; ph < 4; ++ph) {
+  for (int ph = 0; ph < 4; ++ph) {
+    h_ms[ph] = 0.0;
+    for (const auto& sp : e->spans[ph]) {
       float ms = 0.0f;
-      cudaEventElapsedTime(&ms, e->events[i + ph], e->events[i + ph + 1]);
+      cudaEventElapsedTime(&ms, e->events[sp.first], e->events[sp.second]);
       h_ms[ph] += (double)ms;
     }
+    e->spans[ph].clear();
   }
   if (h_launches) *h_launches = e->launches;
   e->events_used = 0;
@@ -390,30 +408,89 @@ int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, c
   return caro_check_launch("expand_backup_kernel");
 }
 
-int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl, void* stream) {
-  if (!e || !net) return caro_fail(CARO_E_ARG, "null argument");
+}  // extern "C"
+
+// One minibatch.  `s_tree` runs noise/select/plan and expand+backup, `s_net` the network; when they differ the
+// hand-offs are CUDA events, so that another engine's tree kernels can run underneath this engine's network pass.
+static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_impl, cudaStream_t s_tree, cudaStream_t s_net) {
   const bool c4 = e->cfg.game == CARO_GAME_CONNECT4;
   const void* lb = c4 ? (const void*)e->v_c4.leaf_board : (const void*)e->v_mnk.leaf_board;
   const uint8_t* lp = c4 ? e->v_c4.leaf_player : e->v_mnk.leaf_player;
   const int32_t* lc = c4 ? e->v_c4.leaf_count : e->v_mnk.leaf_count;
   float* pr = c4 ? e->v_c4.probs : e->v_mnk.probs;
   float* va = c4 ? e->v_c4.values : e->v_mnk.values;
-  const bool prof = e->profiling;
+  const bool cross = s_tree != s_net;
+  if (cross && !e->sync_a) {
+    cudaEventCreateWithFlags(&e->sync_a, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->sync_b, cudaEventDisableTiming);
+  }
+  e->span_begin(0, s_tree);
+  int rc = caro_engine_select(e, batch, i, nullptr, nullptr, s_tree);
+  e->span_end(0, s_tree);
+  e->span_begin(1, s_tree);
+  if (rc == CARO_OK) rc = caro_engine_plan(e, batch, s_tree);
+  e->span_end(1, s_tree);
+  if (cross) {
+    cudaEventRecord(e->sync_a, s_tree);
+    cudaStreamWaitEvent(s_net, e->sync_a, 0);
+  }
+  e->span_begin(2, s_net);
+  if (rc == CARO_OK)
+    rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, lb, lp, lc, (int64_t)e->dm.G * batch, pr, va, net_impl, s_net);
+  e->span_end(2, s_net);
+  if (cross) {
+    cudaEventRecord(e->sync_b, s_net);
+    cudaStreamWaitEvent(s_tree, e->sync_b, 0);
+  }
+  e->span_begin(3, s_tree);
+  if (rc == CARO_OK) rc = caro_engine_expand_backup(e, batch, pr, va, s_tree);
+  e->span_end(3, s_tree);
+  e->launches += 5;
+  return rc;
+}
+
+extern "C" {
+
+int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl, void* stream) {
+  if (!e || !net) return caro_fail(CARO_E_ARG, "null argument");
   for (int i = 0; i < count; ++i) {
-    if (prof) cudaEventRecord(e->next_event(), S(stream));
-    int rc = caro_engine_select(e, batch, i, nullptr, nullptr, stream);
-    if (prof) cudaEventRecord(e->next_event(), S(stream));
-    if (rc == CARO_OK) rc = caro_engine_plan(e, batch, stream);
-    if (prof) cudaEventRecord(e->next_event(), S(stream));
-    if (rc == CARO_OK)
-      rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, lb, lp, lc, (int64_t)e->dm.G * batch, pr, va, net_impl, stream);
-    if (prof) cudaEventRecord(e->next_event(), S(stream));
-    if (rc == CARO_OK) rc = caro_engine_expand_backup(e, batch, pr, va, stream);
-    if (prof) cudaEventRecord(e->next_event(), S(stream));
+    const int rc = search_step(e, net, i, batch, net_impl, S(stream), S(stream));
     if (rc != CARO_OK) return rc;
-    e->launches += 5;
   }
   return CARO_OK;
+}
+
+int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch, int tau_plies,
+                          int auto_restart, int first_player, int net_impl, void* stream) {
+  if (!e0 || !e1 || !net) return caro_fail(CARO_E_ARG, "null argument");
+  static cudaStream_t s_side[2] = {nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  if (!s_side[0]) {
+    cudaStreamCreateWithFlags(&s_side[0], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&s_side[1], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join[1], cudaEventDisableTiming);
+  }
+  cudaStream_t s_net = S(stream);  // network passes stay on the caller's stream, tree kernels go to two side streams
+  cudaEventRecord(ev_fork, s_net);
+  cudaStreamWaitEvent(s_side[0], ev_fork, 0);
+  cudaStreamWaitEvent(s_side[1], ev_fork, 0);
+  caro_engine* es[2] = {e0, e1};
+  int rc = CARO_OK;
+  for (int m = 0; m < moves && rc == CARO_OK; ++m) {
+    for (int i = 0; i < count && rc == CARO_OK; ++i)
+      for (int h = 0; h < 2 && rc == CARO_OK; ++h) rc = search_step(es[h], net, i, batch, net_impl, s_side[h], s_net);
+    for (int h = 0; h < 2 && rc == CARO_OK; ++h) {
+      rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
+      es[h]->launches += 1;
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    cudaEventRecord(ev_join[h], s_side[h]);
+    cudaStreamWaitEvent(s_net, ev_join[h], 0);
+  }
+  return rc;
 }
 
 int caro_engine_root_policy(caro_engine* e, int tau_mode, int tau_plies, double* d_pi, float* d_q, int32_t* d_n, void* stream) {

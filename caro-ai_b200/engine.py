@@ -172,8 +172,9 @@ class SelfPlayEngine:
         _cabi.check(_cabi.lib().caro_engine_play(self.handle, net_p0.handle, net_p1.handle, moves, count, batch, tau_plies,
                                                  1 if auto_restart else 0, first_player, impl, self._stream()))
 
-    def profile(self, enable: bool = True):
-        _cabi.check(_cabi.lib().caro_engine_profile(self.handle, 1 if enable else 0))
+    def profile(self, level: int = 2):
+        """0 = off, 1 = network kernel spans only (cheap), 2 = all four phases."""
+        _cabi.check(_cabi.lib().caro_engine_profile(self.handle, int(level)))
 
     def profile_read(self) -> Dict[str, float]:
         """Summed CUDA-event milliseconds per search phase since the last read (+ kernel launches)."""
@@ -195,6 +196,13 @@ class SelfPlayEngine:
         out_pinned["actions"].copy_(actions, non_blocking=True)
         out_pinned["boards"].copy_(self.region("root_board"), non_blocking=True)
         out_pinned["players"].copy_(self.region("root_player"), non_blocking=True)
+
+    def play_pair(self, other: "SelfPlayEngine", net: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
+                  auto_restart: bool = True, first_player: int = -1, impl: int = IMPL_TCGEN05):
+        """Self-play of two engines (two halves of the game batch) as a software pipeline: one half's tree kernels
+        run on a side stream underneath the other half's network pass (caro_engine_play_pair)."""
+        _cabi.check(_cabi.lib().caro_engine_play_pair(self.handle, other.handle, net.handle, moves, count, batch, tau_plies,
+                                                      1 if auto_restart else 0, first_player, impl, self._stream()))
 
     # ------------------------------------------------------------------ read-back
     COUNTER_NAMES = ("leaf_evals", "games", "plies", "wins_p0", "wins_p1", "draws", "descents", "errors")

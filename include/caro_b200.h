@@ -188,10 +188,18 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
                      int batch, int tau_plies, int auto_restart, int first_player, int net_impl,
                      void* stream);
 
+/* Same for two engines (two halves of the game batch) as a software pipeline: the network passes of both run
+ * back to back on `stream`, the tree kernels (noise/select/plan, expand+backup, advance) of each engine on a
+ * private side stream, chained by CUDA events -- one half's tree kernels execute underneath the other half's
+ * network pass.  Self-play only (one network).  `stream` is joined with the side streams before returning. */
+int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch,
+                          int tau_plies, int auto_restart, int first_player, int net_impl, void* stream);
+
 /* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
  * profile_read synchronises `stream` and returns the summed milliseconds of
  * [0] select, [1] plan, [2] network forward, [3] expand+backup kernels since the last read, plus
  * the number of engine kernels launched by search/play in that window. */
+/* enable: 0 = off, 1 = network kernel only (2 events per minibatch), 2 = all four phases. */
 int caro_engine_profile(caro_engine* e, int enable);
 int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launches, void* stream);
 

@@ -22,7 +22,7 @@ def main():
     eng = SelfPlayEngine(game, games, max_batch=8, node_capacity=24576, seed=7)
     eng.play(dn, dn, moves=preroll, count=100, batch=8, tau_plies=10, auto_restart=True)
     torch.cuda.synchronize()
-    eng.profile(True)
+    eng.profile(2)
     eng.search(dn, n, 8)
     p = eng.profile_read()
     print({k: (v / n if k.endswith("_ms") else v) for k, v in p.items()}, eng.counters())
