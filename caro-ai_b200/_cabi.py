@@ -28,6 +28,7 @@ _SIGNATURES = {
     "caro_boards_apply": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "caro_boards_legal_mask": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),
     "caro_boards_encode_planes": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P, _P]),
+    "caro_backup_path": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, _P]),
     "caro_net_blob_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "caro_net_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
     "caro_net_update": (C.c_int, [_P, _P, C.c_size_t]),

@@ -51,6 +51,23 @@ __global__ void planes_kernel(R rules, const typename R::Board* __restrict__ in,
   planes[t] = (float)rules.plane_value(in[i], who[i], plane, row, col);
 }
 
+// MCTS._backup (lib/mcts.py:225-246) on caller-provided flat N/W/Q arrays: the dict-view facade of
+// caro_ai_b200.mcts.MCTS uses it when statistics were assigned from the host (lib/test_mcts.py:15-38).
+__global__ void backup_path_kernel(int32_t* __restrict__ N, float* __restrict__ W, float* __restrict__ Q,
+                                   const int64_t* __restrict__ edge, int depth, float value) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float cur = -value;
+  for (int i = depth - 1; i >= 0; --i) {
+    const int64_t idx = edge[i];
+    const int n = N[idx] + 1;
+    const float w = __fadd_rn(W[idx], cur);
+    N[idx] = n;
+    W[idx] = w;
+    Q[idx] = __fdiv_rn(w, (float)n);
+    cur = -cur;
+  }
+}
+
 }  // namespace caro
 
 using namespace caro;
@@ -92,6 +109,14 @@ int caro_boards_legal_mask(int game, int n, int k, const void* d_boards, int64_t
   else
     legal_kernel<MnkRules><<<grid, 256, 0, S(stream)>>>(MnkRules{n, k}, (const MnkBoard*)d_boards, count, (n * n + 31) / 32, d_mask);
   return caro_check_launch("legal_kernel");
+}
+
+int caro_backup_path(int32_t* d_n, float* d_w, float* d_q, const int64_t* d_edge_index, int depth, float value, void* stream) {
+  if (!d_n || !d_w || !d_q || (!d_edge_index && depth > 0) || depth < 0) return caro_fail(CARO_E_ARG, "null argument");
+  if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: no CPU fallback");
+  if (depth == 0) return CARO_OK;
+  backup_path_kernel<<<1, 32, 0, S(stream)>>>(d_n, d_w, d_q, d_edge_index, depth, value);
+  return caro_check_launch("backup_path_kernel");
 }
 
 int caro_boards_encode_planes(int game, int n, int k, const void* d_boards, const uint8_t* d_who, int64_t count,

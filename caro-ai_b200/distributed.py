@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing (one process per GPU, ``torch.distributed``; NCCL over NVLink on the box, gloo in the CPU
+tests).  Self-play needs no collective -- games shard by rank -- so the only exchanges are the ones SURVEY.md
+section 8(e) lists: a flattened-gradient all-reduce per SGD step, a weight broadcast after best-net promotion and the
+3-integer W/L/D reduction of the arena evaluation."""
+from __future__ import annotations
+
+from typing import Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_games(total_games: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """(first global game id, count) owned by ``rank``: contiguous, sizes differ by at most one."""
+    base, extra = divmod(total_games, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter]) -> int:
+    """Average the gradients over ranks with ONE all-reduce of a flattened fp32 bucket (188,301 elements for the
+    Connect4 network = 753 KB: latency-bound, no bucketing needed).  Returns the bucket length."""
+    plist: List[torch.nn.Parameter] = [p for p in params if p.grad is not None]
+    if not plist:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1).float() for p in plist])
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= ws
+    off = 0
+    for p in plist:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return int(flat.numel())
+
+
+def broadcast_state_dict(module: torch.nn.Module, src: int = 0) -> None:
+    """NetWrapper.sync() across ranks: every tensor of the state_dict (incl. BatchNorm running stats) from ``src``."""
+    _, ws = world()
+    if ws == 1:
+        return
+    for t in module.state_dict().values():
+        dist.broadcast(t, src=src)
+
+
+def reduce_tallies(wins: int, losses: int, draws: int, device=None) -> Tuple[int, int, int]:
+    """Sum of the arena W/L/D counters over ranks (train.py:120-149 sharded over GPUs)."""
+    _, ws = world()
+    if ws == 1:
+        return wins, losses, draws
+    t = torch.tensor([wins, losses, draws], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t[0]), int(t[1]), int(t[2])

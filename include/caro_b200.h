@@ -70,6 +70,12 @@ int caro_boards_legal_mask(int game, int n, int k, const void* d_boards, int64_t
 int caro_boards_encode_planes(int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                               int64_t count, float* d_planes, void* stream);
 
+/* MCTS._backup (lib/mcts.py:225-246) along one path on caller-owned flat arrays: for i = depth-1 .. 0,
+ * N[e_i] += 1; W[e_i] += v; Q[e_i] = W/N; v = -v, starting from v = -value (float32 arithmetic).
+ * d_edge_index[i] = flat index of (state_i, action_i).  Used by the dict-view facade (lib/test_mcts.py:15-38). */
+int caro_backup_path(int32_t* d_n, float* d_w, float* d_q, const int64_t* d_edge_index, int depth,
+                     float value, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Policy/value network -- row a17 (lib/model.py:10-94) + the softmax of lib/mcts.py:216.
  * Weights are handed over ALREADY FOLDED (eval-mode BatchNorm merged into the convolutions,

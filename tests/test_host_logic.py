@@ -1,0 +1,137 @@
+"""CPU tests of the product's host logic: C-ABI surface, loud failure without a GPU, checkpoint/fold algebra,
+small helpers.  No CUDA compute is invoked (there is no CPU fallback to invoke)."""
+import collections
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from caro_ai_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "caro_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # prototypes only, not the prose
+    declared = set(re.findall(r"\b(caro_[a-z0-9_]+)\s*\(", code))
+    lib = _cabi.lib()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(_cabi.exported_symbols()) <= declared, set(_cabi.exported_symbols()) - declared
+    assert lib.caro_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    from caro_ai_b200 import _cabi
+    from caro_ai_b200.game import ConnectFour
+    lib = _cabi.lib()
+    assert lib.caro_device_count() == 0
+    buf = (C.c_uint64 * 4)()
+    rc = lib.caro_boards_apply(0, 0, 0, buf, buf, buf, 1, buf, None, None, None)
+    assert rc == -2 and b"no CPU fallback" in lib.caro_last_error()
+    cfg = _cabi.EngineConfig(0, 0, 0, 4, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0)
+    assert lib.caro_engine_workspace_bytes(C.byref(cfg)) > 0  # pure arithmetic, allowed
+    handle = C.c_void_p()
+    assert lib.caro_engine_create(C.byref(cfg), buf, 1 << 40, C.byref(handle), None) == -2
+    with pytest.raises(_cabi.CaroError):
+        ConnectFour().move(ConnectFour().initial_state, 3, 1)  # the facade raises instead of computing on the CPU
+    with pytest.raises(_cabi.CaroError):
+        from caro_ai_b200.engine import SelfPlayEngine
+        SelfPlayEngine(ConnectFour(), 4)
+
+
+def test_engine_config_validation():
+    from caro_ai_b200 import _cabi
+    lib = _cabi.lib()
+    bad = [_cabi.EngineConfig(7, 0, 0, 4, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0),      # unknown game
+           _cabi.EngineConfig(1, 16, 5, 4, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0),     # n > 15
+           _cabi.EngineConfig(0, 0, 0, 4, 3, 8, 64, 0, 1.0, 0.3, 0.25, 0),      # trees_per_game
+           _cabi.EngineConfig(0, 0, 0, 4, 1, 65, 64, 0, 1.0, 0.3, 0.25, 0),     # max_batch
+           _cabi.EngineConfig(0, 0, 0, 0, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0)]      # no games
+    for cfg in bad:
+        assert lib.caro_engine_workspace_bytes(C.byref(cfg)) == 0
+    ok = _cabi.EngineConfig(0, 0, 0, 4096, 1, 8, 24576, 0, 1.0, 0.3, 0.25, 0)
+    gb = lib.caro_engine_workspace_bytes(C.byref(ok)) / 1e9
+    assert 15 < gb < 40  # DESIGN.md section 3 byte budget
+
+
+def test_net_state_dict_layout_and_fold(golden_net):
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import Net, fold_state_dict
+    import torch.nn.functional as F
+    for case in golden_net:
+        game = ConnectFour() if case["game"] == "connect4" else TicTacToe(3, 3)
+        torch.manual_seed(case["seed"])
+        net = Net(game.obs_shape, game.action_space)
+        assert {k: list(v.shape) for k, v in net.state_dict().items()} == case["keys"]
+        if case["checkpoint"]:
+            ck = "connect4_best_026_12000.dat" if case["game"] == "connect4" else "tictactoe_best_005_00900.dat"
+            net.load_state_dict(torch.load(os.path.join(GOLDEN, "checkpoints", ck), map_location="cpu"))
+        net.eval()
+        _, H, W = game.obs_shape
+        A = game.action_space
+        blob = torch.from_numpy(fold_state_dict(net.state_dict(), H, W, A))
+        assert blob.numel() == __import__("caro_ai_b200._cabi", fromlist=["x"]).lib().caro_net_blob_floats(H, W, A)
+        # evaluate the folded blob with plain torch ops and compare with the module (BN folding algebra)
+        x = torch.rand(5, 2, H, W).round()
+        o = [0]
+
+        def take(n):
+            r = blob[o[0]:o[0] + n]
+            o[0] += n
+            return r
+        v = F.leaky_relu(F.conv2d(x, take(64 * 2 * 9).view(64, 2, 3, 3), take(64), padding=1), 0.01)
+        for _ in range(5):
+            v = v + F.leaky_relu(F.conv2d(v, take(64 * 64 * 9).view(64, 64, 3, 3), take(64), padding=1), 0.01)
+        hw = H * W
+        val = F.leaky_relu(F.conv2d(v, take(64).view(1, 64, 1, 1), take(1)), 0.01).view(-1, hw)
+        val = torch.tanh(F.linear(F.leaky_relu(F.linear(val, take(20 * hw).view(20, hw), take(20)), 0.01), take(20).view(1, 20), take(1)))
+        pol = F.leaky_relu(F.conv2d(v, take(2 * 64).view(2, 64, 1, 1), take(2)), 0.01).view(-1, 2 * hw)
+        pol = F.linear(pol, take(A * 2 * hw).view(A, 2 * hw), take(A))
+        with torch.no_grad():
+            rp, rv = net(x)
+        scale = max(1.0, float(rp.abs().max()))
+        assert float((pol - rp).abs().max()) < 2e-4 * scale and float((val - rv).abs().max()) < 1e-4
+
+
+def test_small_helpers():
+    from caro_ai_b200.distributed import shard_games
+    from caro_ai_b200.utils import TBMeanTracker, update_counts
+    d = {}
+    update_counts(d, "a", (1, 2, 3))
+    update_counts(d, "a", (1, 0, 0))
+    update_counts(d, ("a", "b"), (0, 1, 0))
+    assert d == {"a": (2, 2, 3), ("a", "b"): (0, 1, 0)}
+
+    class W:
+        def __init__(self):
+            self.rows, self.closed = [], False
+
+        def add_scalar(self, *a):
+            self.rows.append(a)
+
+        def close(self):
+            self.closed = True
+    w = W()
+    with TBMeanTracker(w, batch_size=2) as tb:
+        tb.track("x", 1.0, 0)
+        tb.track("x", torch.tensor([3.0, 5.0]), 1)
+        tb.track("x", np.float32(9.0), 2)
+    assert w.rows == [("x", 2.5, 1)] and w.closed
+    for total, ws in [(4096, 8), (20, 8), (7, 2), (1, 4)]:
+        parts = [shard_games(total, r, ws) for r in range(ws)]
+        assert sum(c for _, c in parts) == total
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_config_matches_reference_values():
+    from caro_ai_b200 import config as cfg
+    assert (cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.STEPS_BEFORE_TAU_0) == (10, 8, 10)   # config.py:3-4,14
+    assert (cfg.C_PUCT, cfg.ALPHA, cfg.EXPLORE) == (1.0, 0.30, 0.25)                         # config.py:26-28
+    assert (cfg.REPLAY_BUFFER, cfg.BATCH_SIZE, cfg.TRAIN_ROUNDS, cfg.MIN_REPLAY_TO_TRAIN) == (5000, 256, 10, 2000)
+    assert (cfg.PLAY_MCTS_SEARCHES, cfg.PLAY_MCTS_BATCH_SIZE, cfg.BEST_NET_WIN_RATIO) == (40, 8, 0.60)
