@@ -287,6 +287,11 @@ def engine_arm(args):
     errors = allsum(c1["errors"])
     if rank == 0:
         peaks = measured_peaks()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "net_tc_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read + dram__bytes_write of one `ncu --set full` capture of this kernel
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
         sec = ms_max / 1000.0
         my_leaf = c1["leaf_evals"] - c0["leaf_evals"]
         net_s = prof["net_ms"] / 1000.0
@@ -308,7 +313,7 @@ def engine_arm(args):
             "gpu_launches": int(prof["launches"]),
             "roofline": {"kernel": "net_tc_kernel (tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
-                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),
                          "avg_launch_ms": prof["net_ms"] / max(1, n_net_launches)},
             "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
