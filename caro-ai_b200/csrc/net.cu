@@ -211,7 +211,8 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
     if (game == CARO_GAME_CONNECT4) return launch_simt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
     return launch_simt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   }
-  if (impl == 0) return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if (impl == 0 || impl == 2)
+    return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 2 ? 1 : 0, st);
   return caro_fail(CARO_E_ARG, "unknown net impl");
 }
 

@@ -61,4 +61,4 @@ struct caro_net {
 int caro_net_tc_pack(caro_net* net, const float* h_blob);
 void caro_net_tc_free(caro_net* net);
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int exact, cudaStream_t st);

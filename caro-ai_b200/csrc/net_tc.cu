@@ -29,13 +29,8 @@
 
 namespace caro {
 
-constexpr int kTilesPerGroup = 4;
 constexpr int kTileRows = 128;
-constexpr int kGroupRows = kTilesPerGroup * kTileRows;  // 512 padded positions per CTA pass
 constexpr int kHalo = 20;                                // zero positions before / after (>= pitch + 1)
-constexpr int kActRows = kGroupRows + 2 * kHalo;         // 552
-constexpr int kChunkBytes = kActRows * 16;               // one 8-channel chunk of all positions
-constexpr int kActBytes = 8 * kChunkBytes;               // 71,680
 constexpr int kTapBytes = 8 * 64 * 16;                   // 8,192: one tap of a 64->64 layer
 constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of conv_in (K padded to 16)
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
@@ -49,7 +44,6 @@ constexpr int kHeadWarp = kMmaWarp + kMmaWarps;          // warps 10-11: FC head
 constexpr int kHeadWarps = 2;
 constexpr int kHeadThreads = 32 * kHeadWarps;
 constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kHeadThreads;
-constexpr uint32_t kTmemCols = 512;
 
 struct TcGeom {
   int H, W, A, pitch, block, boards_per_group;
@@ -138,19 +132,40 @@ __device__ __forceinline__ float lrelu_tc(float x) { return fmaxf(x, kLeaky * x)
     if (trace != nullptr && blockIdx.x == 0 && (idx) < 1000) trace[(kind) * 1000 + (idx)] = clock64(); \
   } while (0)
 
-struct TcSmem {
+// Kernel configuration.
+//   TILES = UMMA M-tiles (128 padded positions each) a CTA processes per pass,
+//   SPLIT = "bf16x3" precision mode: activations and weights are kept as bf16 hi + lo pairs and every product is
+//           evaluated as hi*hi + lo*hi + hi*lo (fp32 accumulate), ~16 mantissa bits instead of 8.  Needed for
+//           trained checkpoints whose policy logits span +-100; 3x the tensor work and twice
+//           the shared memory per row, hence 2 tiles per pass and a single (hi+lo) weight buffer.
+template <int TILES, bool SPLIT>
+struct TcCfg {
+  static constexpr int kTiles = TILES;
+  static constexpr bool kSplit = SPLIT;
+  static constexpr int kGroupRows = TILES * kTileRows;
+  static constexpr int kActRows = kGroupRows + 2 * kHalo;
+  static constexpr int kChunkBytes = kActRows * 16;      // one 8-channel chunk of all positions
+  static constexpr int kActBytes = 8 * kChunkBytes;      // one bf16 activation image (hi or lo)
+  static constexpr int kActBufs = SPLIT ? 2 : 1;
+  static constexpr int kWStages = SPLIT ? 1 : 2;         // weight buffers in flight
+  static constexpr int kWParts = SPLIT ? 2 : 1;          // hi (+ lo) images per layer
+  static constexpr int kWStageBytes = kWParts * kLayerBytes;
+  static constexpr uint32_t kTmemCols = 2 * TILES * 64;  // accumulators + fp32 residual stream
   // dynamic shared memory carve-up (byte offsets from a 128-aligned base)
   static constexpr int kAct = 0;
-  static constexpr int kWgt = kAct + kActBytes;                    // 2 layer images (double buffer)
-  static constexpr int kBias = kWgt + 2 * kLayerBytes;             // float [6][64]
+  static constexpr int kWgt = kAct + kActBufs * kActBytes;
+  static constexpr int kBias = kWgt + kWStages * kWStageBytes;     // float [6][64]
   static constexpr int kHeadW = kBias + kNumLayers * 64 * 4;       // float [3][64] + [3] biases (+pad)
-  static constexpr int kHeadF = kHeadW + 4 * 64 * 4;               // float [512][3] head features
-  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[nb][20] + logits[nb][A]  (<= 1024 floats)
-  static constexpr int kCellTab = kFc + 1024 * 4;                  // uint16 [512]: (board << 9) | (cell + 1), 0 = padding
+  static constexpr int kHeadF = kHeadW + 4 * 64 * 4;               // float [rows][3] head features
+  static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[nb][20] + logits[nb][A]
+  static constexpr int kFcFloats = TILES * 256;
+  static constexpr int kCellTab = kFc + kFcFloats * 4;             // uint16 [rows]: (board << 9) | (cell + 1), 0 = padding
   static constexpr int kBars = kCellTab + kGroupRows * 2;          // mbarriers + tmem base
   static constexpr int kTotal = kBars + 128;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
-static_assert(TcSmem::kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+using TcFast = TcCfg<4, false>;
+using TcExact = TcCfg<2, true>;
 
 // ------------------------------------------------------------------------------------- kernel
 // Roles: warps 0-7 = epilogue (warp w owns TMEM lanes [32(w&3), +32) = rows of every tile, channels 32(w>>2)..+32),
@@ -162,7 +177,7 @@ static_assert(TcSmem::kTotal <= 232448, "exceeds the 227 KB shared memory of an 
 //   MMA(L,t)  needs act_ready[t-1..t+1] of the previous stage (their bf16 rows + tile t's accumulator drained)
 //   EPI(L,t)  needs acc_full[min(t+1,3)]  (tile t+1 reads the last rows of tile t as its halo)
 // so the epilogue of tile t runs underneath the MMAs of tile t+2 / the next layer's tile t-1.
-template <class R>
+template <class R, class K>
 __global__ void __launch_bounds__(kThreads, 1)
 net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
@@ -170,18 +185,18 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
               float* __restrict__ values, long long* __restrict__ trace) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* act = smem + TcSmem::kAct;
-  uint8_t* wgt = smem + TcSmem::kWgt;
-  float* bias_s = reinterpret_cast<float*>(smem + TcSmem::kBias);
-  float* headw_s = reinterpret_cast<float*>(smem + TcSmem::kHeadW);
-  float* headf_s = reinterpret_cast<float*>(smem + TcSmem::kHeadF);
-  float* fc_s = reinterpret_cast<float*>(smem + TcSmem::kFc);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + TcSmem::kBars);  // [2] weights buffer filled
+  uint8_t* act = smem + K::kAct;
+  uint8_t* wgt = smem + K::kWgt;
+  float* bias_s = reinterpret_cast<float*>(smem + K::kBias);
+  float* headw_s = reinterpret_cast<float*>(smem + K::kHeadW);
+  float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
+  float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [2] weights buffer filled
   uint64_t* bar_acc = bar_w + 2;                                        // [4] accumulator tile complete
   uint64_t* bar_act = bar_w + 6;                                        // [4] activation tile rewritten / accumulator drained
   uint64_t* bar_feat = bar_w + 10;                                      // [0] head features complete, [1] consumed + re-zeroed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 12);
-  uint16_t* cell_tab = reinterpret_cast<uint16_t*>(smem + TcSmem::kCellTab);
+  uint16_t* cell_tab = reinterpret_cast<uint16_t*>(smem + K::kCellTab);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -192,14 +207,14 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   // ---- one-time setup ---------------------------------------------------------------------
-  for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < K::kActBufs * K::kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < kNumLayers * 64; i += kThreads) bias_s[i] = bias_g[i];
-  for (int p = tid; p < kGroupRows; p += kThreads) {  // padded position -> (board, cell) once, no divisions in the hot loop
+  for (int p = tid; p < K::kGroupRows; p += kThreads) {  // padded position -> (board, cell) once, no divisions in the hot loop
     const int b = p / gm.block, within = p - b * gm.block;
     const int r = within / gm.pitch, c = within - r * gm.pitch;
     cell_tab[p] = (b < nb && r < gm.H && c < gm.W) ? (uint16_t)((b << 9) | (r * gm.W + c + 1)) : (uint16_t)0;
   }
-  for (int i = tid; i < kGroupRows * 3; i += kThreads) headf_s[i] = 0.0f;
+  for (int i = tid; i < K::kGroupRows * 3; i += kThreads) headf_s[i] = 0.0f;
   for (int i = tid; i < 64; i += kThreads) {
     headw_s[i] = blob[L.val_conv_w + i];
     headw_s[64 + i] = blob[L.pol_conv_w + i];
@@ -221,7 +236,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   }
   if (warp == kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -320,67 +335,87 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     const uint32_t act_addr = smem_u32(act);
     const uint32_t wgt_addr = smem_u32(wgt);
     const int total_layers = my_groups * kNumLayers;
-    auto load_layer = [&](int gl) {  // global layer index -> buffer gl & 1
+    auto load_layer = [&](int gl) {  // global layer index -> weight stage gl % kWStages (hi image, then lo)
       const int l = gl % kNumLayers;
-      uint8_t* dst = wgt + (gl & 1) * kLayerBytes;
-      uint64_t* bar = bar_w + (gl & 1);
-      if (l == 0) {
-        mbar_expect_tx(bar, kLayerBytesIn);
-        for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytesIn, wimg + tap * kTapBytesIn, kTapBytesIn, bar);
-      } else {
-        mbar_expect_tx(bar, kLayerBytes);
-        const uint8_t* src = wimg + kLayerBytesIn + (size_t)(l - 1) * kLayerBytes;
-        for (int tap = 0; tap < 9; ++tap) bulk_g2s(dst + tap * kTapBytes, src + tap * kTapBytes, kTapBytes, bar);
-      }
+      uint8_t* dst = wgt + (gl % K::kWStages) * K::kWStageBytes;
+      uint64_t* bar = bar_w + (gl % K::kWStages);
+      const int tap_bytes = l == 0 ? kTapBytesIn : kTapBytes;
+      const int layer_bytes = 9 * tap_bytes;
+      // global image: conv_in {hi, lo}, then per block {hi, lo}
+      const uint8_t* src = l == 0 ? wimg : wimg + 2 * kLayerBytesIn + (size_t)(l - 1) * 2 * kLayerBytes;
+      mbar_expect_tx(bar, (uint32_t)(K::kWParts * layer_bytes));
+      for (int part = 0; part < K::kWParts; ++part)
+        for (int tap = 0; tap < 9; ++tap)
+          bulk_g2s(dst + part * kLayerBytes + tap * tap_bytes, src + (size_t)part * layer_bytes + tap * tap_bytes, tap_bytes, bar);
     };
     if (mw == 1 && elected) {
       load_layer(0);
-      if (total_layers > 1) load_layer(1);
+      if (K::kWStages > 1 && total_layers > 1) load_layer(1);
     }
     // descriptor templates: only the 14-bit start-address field (units of 16 B) changes per MMA
-    const uint64_t a_desc0 = make_desc(act_addr + (uint32_t)kHalo * 16u, kChunkBytes, 128u);
+    const uint64_t a_desc0 = make_desc(act_addr + (uint32_t)kHalo * 16u, K::kChunkBytes, 128u);
     const uint64_t b_desc0 = make_desc(wgt_addr, 1024u, 128u);
+    constexpr uint64_t kALo = (uint64_t)(K::kActBytes / 16);   // lo activation image
+    constexpr uint64_t kBLo = (uint64_t)(kLayerBytes / 16);    // lo weight image
     const int pitch = gm.pitch;
     for (int gl = 0; gl < total_layers; ++gl) {
       const bool first = (gl % kNumLayers) == 0;
-      const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl & 1) * (kLayerBytes / 16));
-      mbar_wait(bar_w + (gl & 1), (uint32_t)(gl >> 1) & 1u);
+      const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl % K::kWStages) * (K::kWStageBytes / 16));
+      mbar_wait(bar_w + (gl % K::kWStages), (uint32_t)(gl / K::kWStages) & 1u);
       if (elected) TC_TRACE(6, gl * 2 + mw);  // weights present
       const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
 #pragma unroll 1
-      for (int t = mw; t < kTilesPerGroup; t += 2) {
+      for (int t = mw; t < K::kTiles; t += 2) {
         // MMA(gl,t) reads the rows of tiles t-1..t+1 as rewritten by the previous stage
         if (t > 0) mbar_wait(bar_act + t - 1, act_par);
         mbar_wait(bar_act + t, act_par);
-        if (t + 1 < kTilesPerGroup) mbar_wait(bar_act + t + 1, act_par);
+        if (t + 1 < K::kTiles) mbar_wait(bar_act + t + 1, act_par);
         tc_fence_after();
         if (elected) TC_TRACE(0, gl * 4 + t);  // MMA issue start
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * 64);
         const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(t * kTileRows);
         if (elected) {
-          if (first) {
+          if (first) {  // conv_in: the 0/1 input planes are exact in bf16, so there is no lo activation term
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int sh = (tap / 3 - 1) * pitch + (tap % 3 - 1);
-              umma_bf16(d_tmem, a_tile + (uint64_t)(int64_t)sh, b_layer + (uint64_t)(tap * (kTapBytesIn / 16)), kIdesc, tap > 0 ? 1u : 0u);
+              const uint64_t ad = a_tile + (uint64_t)(int64_t)sh;
+              const uint64_t bd = b_layer + (uint64_t)(tap * (kTapBytesIn / 16));
+              umma_bf16(d_tmem, ad, bd, kIdesc, tap > 0 ? 1u : 0u);
+              if (K::kSplit) umma_bf16(d_tmem, ad, bd + kBLo, kIdesc, 1u);
             }
           } else {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int sh = (tap / 3 - 1) * pitch + (tap % 3 - 1);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(d_tmem, a_tile + (uint64_t)(int64_t)(sh + kk * 2 * kActRows),
-                          b_layer + (uint64_t)(tap * (kTapBytes / 16) + kk * (2048 / 16)), kIdesc, (tap | kk) ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = a_tile + (uint64_t)(int64_t)(sh + kk * 2 * K::kActRows);
+                const uint64_t bd = b_layer + (uint64_t)(tap * (kTapBytes / 16) + kk * (2048 / 16));
+                umma_bf16(d_tmem, ad, bd, kIdesc, (tap | kk) ? 1u : 0u);
+                if (K::kSplit) {
+                  umma_bf16(d_tmem, ad + kALo, bd, kIdesc, 1u);   // lo(a) * hi(w)
+                  umma_bf16(d_tmem, ad, bd + kBLo, kIdesc, 1u);   // hi(a) * lo(w)
+                }
+              }
             }
           }
           umma_commit(bar_acc + t);
           TC_TRACE(1, gl * 4 + t);  // MMA issued + committed
-          // tile 1 waited on the rewritten rows of tiles 0..2, whose epilogues waited on every commit of layer
-          // gl-1: all MMAs of layer gl-1 are complete, its weight buffer is free for layer gl+1
-          if (t == 1 && gl >= 1 && gl + 1 < total_layers) load_layer(gl + 1);
         }
         __syncwarp();
+        if (t == 1 && gl + 1 < total_layers) {
+          if (K::kWStages > 1) {
+            // tile 1 waited on the rewritten rows of tiles 0..2, whose epilogues waited on every commit of layer
+            // gl-1: all MMAs of layer gl-1 are complete, its weight buffer is free for layer gl+1
+            if (gl >= 1 && elected) load_layer(gl + 1);
+          } else {
+            // single weight buffer: layer gl+1 can only stream in once every MMA of layer gl has completed
+            for (int tt = 0; tt < K::kTiles; ++tt) mbar_wait(bar_acc + tt, (uint32_t)gl & 1u);
+            if (elected) load_layer(gl + 1);
+            __syncwarp();
+          }
+        }
       }
     }
   } else {
@@ -395,7 +430,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
 
     auto write_inputs = [&](long long leaf0) {
 #pragma unroll 1
-      for (int t = 0; t < kTilesPerGroup; ++t) {
+      for (int t = 0; t < K::kTiles; ++t) {
         const int p = t * kTileRows + row;
         uint32_t lo = 0u;
         if (half == 0) {
@@ -411,7 +446,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             lo = mine | (other << 16);
           }
         }
-        *reinterpret_cast<uint4*>(act + (size_t)(half * kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + (size_t)(half * K::kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
         fence_async_smem();
         mbar_arrive(bar_act + t);
       }
@@ -429,11 +464,11 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         const bool has_res = layer > 0;
         const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64 + half * 32);
 #pragma unroll 1
-        for (int t = 0; t < kTilesPerGroup; ++t) {
+        for (int t = 0; t < K::kTiles; ++t) {
           // tile t's own accumulator AND tile t+1's (it reads the tail rows of tile t as its halo); the two
           // tiles are issued by different warps, so neither commit implies the other
           mbar_wait(bar_acc + t, acc_par);
-          if (t + 1 < kTilesPerGroup) mbar_wait(bar_acc + t + 1, acc_par);
+          if (t + 1 < K::kTiles) mbar_wait(bar_acc + t + 1, acc_par);
           __syncwarp();
           tc_fence_after();
           if (tid == 0) TC_TRACE(2, gl * 4 + t);  // epilogue start (warp 0)
@@ -441,7 +476,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
           const uint32_t tab = cell_tab[p];
           const bool real = tab != 0u;
           const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(t * 64 + half * 32);
-          const uint32_t a_res = a_acc + 256u;
+          const uint32_t a_res = a_acc + (uint32_t)(K::kTiles * 64);
           uint32_t ra[32], rr[32];
           TMEM_LD16(a_acc, ra);
           TMEM_LD16(a_acc + 16u, (ra + 16));
@@ -467,15 +502,21 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             TMEM_ST16(a_res + 16u, (rr + 16));
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-              uint32_t packed[4];
+              uint32_t packed[4], packed_lo[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h =
-                    __floats2bfloat162_rn(__uint_as_float(rr[c8 * 8 + 2 * j]), __uint_as_float(rr[c8 * 8 + 2 * j + 1]));
+                const float v0 = __uint_as_float(rr[c8 * 8 + 2 * j]), v1 = __uint_as_float(rr[c8 * 8 + 2 * j + 1]);
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
                 packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+                if (K::kSplit) {  // lo = bf16(v - hi): the second 8 mantissa bits
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
+                  packed_lo[j] = real ? *reinterpret_cast<const uint32_t*>(&l2) : 0u;
+                }
               }
-              *reinterpret_cast<uint4*>(act + (size_t)((half * 4 + c8) * kActRows + kHalo + p) * 16) =
-                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              uint8_t* dst = act + (size_t)((half * 4 + c8) * K::kActRows + kHalo + p) * 16;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              if (K::kSplit)
+                *reinterpret_cast<uint4*>(dst + K::kActBytes) = make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             fence_async_smem();
@@ -517,7 +558,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   __syncthreads();
   if (warp == kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::kTmemCols) : "memory");
   }
 }
 
@@ -537,21 +578,28 @@ using namespace caro;
 
 int caro_net_tc_pack(caro_net* net, const float* h) {
   const BlobLayout& L = net->layout;
-  const size_t img_bytes = (size_t)kLayerBytesIn + (size_t)kBlocks * kLayerBytes;
+  // global image: conv_in {hi, lo}, then per residual block {hi, lo}; each part is a stack of 9 tap images in the
+  // UMMA B-operand layout [8-channel chunk][n = 64 out channels][8 in channels] (no-swizzle K-major core matrices)
+  const size_t img_bytes = 2 * ((size_t)kLayerBytesIn + (size_t)kBlocks * kLayerBytes);
   std::vector<uint16_t> img(img_bytes / 2, 0);
-  // conv_in: [tap][chunk(2)][n=64][8] with only channels 0,1 non-zero
+  auto put = [&](size_t part_base, size_t tap_bytes, int tap, int co, int ci, float w) {
+    const uint16_t hi = f32_to_bf16(w);
+    uint32_t hb = (uint32_t)hi << 16;
+    float hf;
+    memcpy(&hf, &hb, 4);
+    const uint16_t lo = f32_to_bf16(w - hf);
+    const size_t off = ((size_t)tap * tap_bytes + (size_t)((ci / 8) * 64 + co) * 16) / 2 + (ci % 8);
+    img[part_base / 2 + off] = hi;
+    img[(part_base + 9 * tap_bytes) / 2 + off] = lo;
+  };
   for (int tap = 0; tap < 9; ++tap)
     for (int co = 0; co < 64; ++co)
-      for (int ci = 0; ci < 2; ++ci)
-        img[((size_t)tap * kTapBytesIn + (size_t)((ci / 8) * 64 + co) * 16) / 2 + (ci % 8)] =
-            f32_to_bf16(h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + tap)]);
+      for (int ci = 0; ci < 2; ++ci) put(0, kTapBytesIn, tap, co, ci, h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + tap)]);
   for (int l = 0; l < kBlocks; ++l) {
-    const size_t base = (size_t)kLayerBytesIn + (size_t)l * kLayerBytes;
+    const size_t base = 2 * (size_t)kLayerBytesIn + (size_t)l * 2 * kLayerBytes;
     for (int tap = 0; tap < 9; ++tap)
       for (int co = 0; co < 64; ++co)
-        for (int ci = 0; ci < 64; ++ci)
-          img[(base + (size_t)tap * kTapBytes + (size_t)((ci / 8) * 64 + co) * 16) / 2 + (ci % 8)] =
-              f32_to_bf16(h[L.conv_w[l] + ((size_t)(co * 64 + ci) * 9 + tap)]);
+        for (int ci = 0; ci < 64; ++ci) put(base, kTapBytes, tap, co, ci, h[L.conv_w[l] + ((size_t)(co * 64 + ci) * 9 + tap)]);
   }
   std::vector<float> bias((size_t)kNumLayers * 64);
   for (int co = 0; co < 64; ++co) bias[co] = h[L.conv_in_b + co];
@@ -584,7 +632,7 @@ void caro_net_tc_free(caro_net* net) {
   net->d_pol_fc_t = nullptr;
 }
 
-template <class R>
+template <class R, class K>
 static int launch_tc(const R& rules, caro_net* net, const void* boards, const uint8_t* who, const int32_t* d_count,
                      int64_t max_count, float* probs, float* values, cudaStream_t st) {
   TcGeom gm;
@@ -593,8 +641,9 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   gm.A = net->A;
   gm.pitch = net->W + 1;
   gm.block = (net->H + 1) * gm.pitch;
-  gm.boards_per_group = kGroupRows / gm.block;
-  if (gm.boards_per_group < 1 || gm.boards_per_group > 32 || gm.pitch + 1 > kHalo)
+  gm.boards_per_group = K::kGroupRows / gm.block;
+  if (gm.boards_per_group < 1 || gm.boards_per_group > 32 || gm.pitch + 1 > kHalo ||
+      gm.boards_per_group * (20 + gm.A) > K::kFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the tensor-core tile geometry");
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -602,20 +651,28 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = net_tc_kernel<R>;
-  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal);
-  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  auto kern = net_tc_kernel<R, K>;
+  static bool attr_set = false;  // per (R, K) instantiation
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kTotal);
+    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+    attr_set = true;
+  }
   const long long max_groups = (max_count + gm.boards_per_group - 1) / gm.boards_per_group;
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
-  kern<<<grid, kThreads, TcSmem::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
-                                               (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                               net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values,
-                                               (long long*)net->d_trace);
+  kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
+                                          (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
+                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values,
+                                          (long long*)net->d_trace);
   return caro_check_launch("net_tc_kernel");
 }
 
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st) {
-  if (game == CARO_GAME_CONNECT4) return launch_tc<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
-  return launch_tc<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int exact, cudaStream_t st) {
+  if (game == CARO_GAME_CONNECT4) {
+    if (exact) return launch_tc<C4Rules, TcExact>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+    return launch_tc<C4Rules, TcFast>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  }
+  if (exact) return launch_tc<MnkRules, TcExact>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  return launch_tc<MnkRules, TcFast>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
 }

@@ -131,8 +131,9 @@ class SelfPlayEngine:
                                                           self._stream()))
 
     # ------------------------------------------------------------------ fused paths
-    def search(self, net: DeviceNet, count: int, batch: int, impl: int = IMPL_TCGEN05):
+    def search(self, net: DeviceNet, count: int, batch: int, impl: int = None):
         """MCTS.search_batch(count, batch, ...) for all games with the built-in network."""
+        impl = net.impl if impl is None else impl
         _cabi.check(_cabi.lib().caro_engine_search(self.handle, net.handle, count, batch, impl, self._stream()))
 
     def search_with(self, evaluate, count: int, batch: int, noise_fn=None):
@@ -168,7 +169,8 @@ class SelfPlayEngine:
         return actions
 
     def play(self, net_p0: DeviceNet, net_p1: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
-             auto_restart: bool = True, first_player: int = -1, impl: int = IMPL_TCGEN05):
+             auto_restart: bool = True, first_player: int = -1, impl: int = None):
+        impl = net_p0.impl if impl is None else impl
         _cabi.check(_cabi.lib().caro_engine_play(self.handle, net_p0.handle, net_p1.handle, moves, count, batch, tau_plies,
                                                  1 if auto_restart else 0, first_player, impl, self._stream()))
 
@@ -185,7 +187,7 @@ class SelfPlayEngine:
                 "launches": int(launches.value)}
 
     def step_host(self, boards_pinned: torch.Tensor, players_pinned: torch.Tensor, net: DeviceNet, count: int, batch: int,
-                  tau_plies: int, out_pinned: Dict[str, torch.Tensor], impl: int = IMPL_TCGEN05):
+                  tau_plies: int, out_pinned: Dict[str, torch.Tensor], impl: int = None):
         """One ply for all games through HOST buffers (the end-to-end path): roots H2D from pinned memory,
         search + advance on the device, then policy / actions / new roots D2H into pinned buffers."""
         self.set_roots_pinned(boards_pinned, players_pinned)
@@ -198,9 +200,10 @@ class SelfPlayEngine:
         out_pinned["players"].copy_(self.region("root_player"), non_blocking=True)
 
     def play_pair(self, other: "SelfPlayEngine", net: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
-                  auto_restart: bool = True, first_player: int = -1, impl: int = IMPL_TCGEN05):
+                  auto_restart: bool = True, first_player: int = -1, impl: int = None):
         """Self-play of two engines (two halves of the game batch) as a software pipeline: one half's tree kernels
         run on a side stream underneath the other half's network pass (caro_engine_play_pair)."""
+        impl = net.impl if impl is None else impl
         _cabi.check(_cabi.lib().caro_engine_play_pair(self.handle, other.handle, net.handle, moves, count, batch, tau_plies,
                                                       1 if auto_restart else 0, first_player, impl, self._stream()))
 

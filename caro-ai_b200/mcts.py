@@ -36,6 +36,7 @@ class MCTS:
                  noise_fn: Optional[Callable[[int, int], np.ndarray]] = None):
         """``noise_fn(batch, actions) -> float64 [batch, actions]`` injects the Dirichlet draws (tests)."""
         self.c_puct = C_PUCT
+        self.precision = "bf16x3"  # nn.Module nets handed to this facade are folded at fp32-class accuracy
         self.game = game
         self.noise_fn = noise_fn
         self._engine: Optional[SelfPlayEngine] = None
@@ -60,7 +61,7 @@ class MCTS:
         if isinstance(net, Net):
             key = id(net)
             if key not in self._device_nets:
-                self._device_nets[key] = DeviceNet(net, self.game)
+                self._device_nets[key] = DeviceNet(net, self.game, precision=self.precision)
             return self._device_nets[key]
         return None
 

@@ -106,14 +106,20 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], rows: int, cols: int, actions: 
     return np.ascontiguousarray(blob)
 
 
-IMPL_TCGEN05, IMPL_SIMT = 0, 1
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3 = 0, 1, 2
 
 
 class DeviceNet:
     """Folded network resident on the GPU (``caro_net`` handle)."""
 
-    def __init__(self, net_or_state_dict, game):
+    def __init__(self, net_or_state_dict, game, precision: str = "bf16"):
+        """``precision``: "bf16" (one bf16 tensor-core pass, fp32 accumulate: the throughput mode, within 1e-3 of
+        fp32 for networks whose logits are O(10)) or "bf16x3" (hi/lo split, fp32-class accuracy: use it for trained
+        checkpoints with large logits, e.g. the shipped Connect4 nets)."""
         _cabi.require_cuda()
+        assert precision in ("bf16", "bf16x3", "fp32-simt")
+        self.precision = precision
+        self.impl = {"bf16": IMPL_TCGEN05, "bf16x3": IMPL_TCGEN05_X3, "fp32-simt": IMPL_SIMT}[precision]
         sd = net_or_state_dict.state_dict() if isinstance(net_or_state_dict, nn.Module) else net_or_state_dict
         _, self.rows, self.cols = game.obs_shape
         self.actions = game.action_space
@@ -130,8 +136,9 @@ class DeviceNet:
         blob = fold_state_dict(sd, self.rows, self.cols, self.actions)
         _cabi.check(_cabi.lib().caro_net_update(self.handle, blob.ctypes.data, blob.size))
 
-    def forward_boards(self, d_boards, d_who, count: int, impl: int = IMPL_TCGEN05):
+    def forward_boards(self, d_boards, d_who, count: int, impl: int = None):
         """(priors [count,A], values [count]) float32 CUDA tensors for device boards."""
+        impl = self.impl if impl is None else impl
         probs = torch.empty((count, self.actions), dtype=torch.float32, device="cuda")
         values = torch.empty((count,), dtype=torch.float32, device="cuda")
         if count:
@@ -141,7 +148,7 @@ class DeviceNet:
                                                      impl, torch.cuda.current_stream().cuda_stream))
         return probs, values
 
-    def forward_states(self, states, players, impl: int = IMPL_TCGEN05):
+    def forward_states(self, states, players, impl: int = None):
         d_boards = torch.from_numpy(self.game.boards_from_states(states).view(np.int64)).cuda()
         d_who = torch.tensor(list(players), dtype=torch.uint8, device="cuda")
         return self.forward_boards(d_boards, d_who, len(states), impl)

@@ -103,8 +103,10 @@ int caro_net_set_trace(caro_net* net, void* d_trace);
  *             max_count leaves are evaluated.
  *   d_probs : float32 [max_count][A] softmax priors (over ALL actions, like the reference).
  *   d_values: float32 [max_count]    tanh value head.
- *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path), 1 = fp32 SIMT tower (numerics
- *             reference kernel used by the tests). */
+ *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path: one bf16 pass, fp32 accumulate),
+ *             2 = tcgen05 "bf16x3" tower (hi/lo split of activations and weights, 3 MMAs per product:
+ *                 fp32-class accuracy for trained checkpoints with large logits, ~1/3.5 of the speed),
+ *             1 = fp32 SIMT tower (numerics reference kernel used by the tests). */
 int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards,
                      const uint8_t* d_who, const int32_t* d_count, int64_t max_count,
                      float* d_probs, float* d_values, int impl, void* stream);

@@ -247,6 +247,15 @@ def test_net_tcgen05_matches_pytorch(torch_cuda):
         assert dp < gp and dv < gv and agree >= ga, (tag, dp, dv, agree)
 
 
+def test_net_tcgen05_x3_matches_pytorch_on_trained_checkpoints(torch_cuda):
+    """"bf16x3" tensor-core tower (hi/lo split, 3 MMAs per product) vs PyTorch fp32: 1e-3 absolute on priors and values
+    for EVERY test network including the shipped trained checkpoints (policy logits of +-100)."""
+    rng = np.random.default_rng(3)
+    for tag, game, net in _net_cases():
+        dp, dv, agree = _net_errors(game, net, 2, rng)
+        assert dp < 1e-3 and dv < 1e-3 and agree == 1.0, (tag, dp, dv, agree)
+
+
 def test_checkpoint_format_roundtrip(torch_cuda, tmp_path, golden_net):
     """saves/*.dat contract: the product Net has the reference's key set / shapes, loads a reference
     checkpoint, and writes one the reference layout accepts (train.py:214-216, play.py:29-35)."""
