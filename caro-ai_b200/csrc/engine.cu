@@ -1,6 +1,7 @@
 // Host side of the engine: workspace carving, kernel dispatch per game family, C ABI.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -460,37 +461,119 @@ int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int 
   return CARO_OK;
 }
 
-int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch, int tau_plies,
-                          int auto_restart, int first_player, int net_impl, void* stream) {
-  if (!e0 || !e1 || !net) return caro_fail(CARO_E_ARG, "null argument");
-  static cudaStream_t s_side[2] = {nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-  if (!s_side[0]) {
-    cudaStreamCreateWithFlags(&s_side[0], cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&s_side[1], cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_join[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_join[1], cudaEventDisableTiming);
-  }
-  cudaStream_t s_net = S(stream);  // network passes stay on the caller's stream, tree kernels go to two side streams
-  cudaEventRecord(ev_fork, s_net);
-  cudaStreamWaitEvent(s_side[0], ev_fork, 0);
-  cudaStreamWaitEvent(s_side[1], ev_fork, 0);
-  caro_engine* es[2] = {e0, e1};
+// One ply of the multi-part pipeline: `count` minibatches of every part (round robin), then the advance kernels.
+static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batch, int tau_plies, int auto_restart,
+                     int first_player, int net_impl, cudaStream_t* s_side, cudaStream_t s_net) {
   int rc = CARO_OK;
-  for (int m = 0; m < moves && rc == CARO_OK; ++m) {
-    for (int i = 0; i < count && rc == CARO_OK; ++i)
-      for (int h = 0; h < 2 && rc == CARO_OK; ++h) rc = search_step(es[h], net, i, batch, net_impl, s_side[h], s_net);
-    for (int h = 0; h < 2 && rc == CARO_OK; ++h) {
-      rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
-      es[h]->launches += 1;
-    }
-  }
-  for (int h = 0; h < 2; ++h) {
-    cudaEventRecord(ev_join[h], s_side[h]);
-    cudaStreamWaitEvent(s_net, ev_join[h], 0);
+  for (int i = 0; i < count && rc == CARO_OK; ++i)
+    for (int h = 0; h < n && rc == CARO_OK; ++h) rc = search_step(es[h], net, i, batch, net_impl, s_side[h], s_net);
+  for (int h = 0; h < n && rc == CARO_OK; ++h) {
+    rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
+    es[h]->launches += 1;
   }
   return rc;
+}
+
+constexpr int kMaxParts = 8;
+
+struct MultiGraph {  // one captured ply, replayed while its parameters stay the same
+  cudaGraphExec_t exec = nullptr;
+  caro_engine* es[kMaxParts] = {nullptr};
+  caro_net* net = nullptr;
+  int n = 0, count = 0, batch = 0, tau = 0, restart = 0, first = 0, impl = 0;
+  unsigned long long launches_per_ply = 0;
+};
+
+int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int moves, int count, int batch, int tau_plies,
+                           int auto_restart, int first_player, int net_impl, void* stream) {
+  if (!engines || !net || n < 1 || n > kMaxParts) return caro_fail(CARO_E_ARG, "need 1..8 engines and a network");
+  for (int h = 0; h < n; ++h)
+    if (!engines[h]) return caro_fail(CARO_E_ARG, "null engine");
+  static cudaStream_t s_side[kMaxParts] = {nullptr};
+  static cudaStream_t s_cap = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts] = {nullptr};
+  static MultiGraph mg;
+  if (!s_cap) {
+    for (int h = 0; h < kMaxParts; ++h) {
+      cudaStreamCreateWithFlags(&s_side[h], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_join[h], cudaEventDisableTiming);
+    }
+    cudaStreamCreateWithFlags(&s_cap, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  }
+  // The network passes of all parts stay on one stream, each part's tree kernels go to its own side stream.  With
+  // profiling off the whole ply (n x count x 5 kernels + n) is captured once into a CUDA graph and replayed per
+  // ply: the host issues one graph launch instead of ~500 n kernel launches and ~400 n event operations.
+  bool profiling = false;
+  for (int h = 0; h < n; ++h) profiling = profiling || engines[h]->profiling != 0;
+  const bool use_graph = !profiling && !getenv("CARO_NO_GRAPH");
+  auto fork_join = [&](cudaStream_t s_net, auto&& body) {
+    cudaEventRecord(ev_fork, s_net);
+    for (int h = 0; h < n; ++h) cudaStreamWaitEvent(s_side[h], ev_fork, 0);
+    const int rc = body();
+    for (int h = 0; h < n; ++h) {
+      cudaEventRecord(ev_join[h], s_side[h]);
+      cudaStreamWaitEvent(s_net, ev_join[h], 0);
+    }
+    return rc;
+  };
+  if (use_graph) {
+    bool same = mg.exec && mg.n == n && mg.net == net && mg.count == count && mg.batch == batch && mg.tau == tau_plies &&
+                mg.restart == auto_restart && mg.first == first_player && mg.impl == net_impl;
+    for (int h = 0; h < n && same; ++h) same = mg.es[h] == engines[h];
+    if (!same) {
+      if (mg.exec) cudaGraphExecDestroy(mg.exec);
+      mg = MultiGraph();
+      unsigned long long before = 0, after = 0, saved[kMaxParts];
+      for (int h = 0; h < n; ++h) {
+        saved[h] = engines[h]->launches;
+        before += engines[h]->launches;
+      }
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(s_cap, cudaStreamCaptureModeThreadLocal);
+      int rc = CARO_OK;
+      if (ce == cudaSuccess) {
+        rc = fork_join(s_cap, [&] {
+          return multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, s_side, s_cap);
+        });
+        ce = cudaStreamEndCapture(s_cap, &graph);
+      }
+      if (ce == cudaSuccess && rc == CARO_OK) ce = cudaGraphInstantiate(&mg.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      for (int h = 0; h < n; ++h) {
+        after += engines[h]->launches;
+        engines[h]->launches = saved[h];  // capturing launches nothing
+      }
+      mg.launches_per_ply = after - before;
+      if (ce != cudaSuccess || rc != CARO_OK) {
+        mg = MultiGraph();
+        cudaGetLastError();
+        return caro_fail(CARO_E_CUDA, "CUDA graph capture of the self-play pipeline failed");
+      }
+      mg.n = n; mg.net = net; mg.count = count; mg.batch = batch; mg.tau = tau_plies;
+      mg.restart = auto_restart; mg.first = first_player; mg.impl = net_impl;
+      for (int h = 0; h < n; ++h) mg.es[h] = engines[h];
+    }
+    for (int m = 0; m < moves; ++m) {
+      const cudaError_t ce = cudaGraphLaunch(mg.exec, S(stream));
+      if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+      engines[0]->launches += mg.launches_per_ply;  // kernels executed by the replay (attributed to the first part)
+    }
+    return CARO_OK;
+  }
+  cudaStream_t s_net = S(stream);
+  return fork_join(s_net, [&] {
+    int rc = CARO_OK;
+    for (int m = 0; m < moves && rc == CARO_OK; ++m)
+      rc = multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, s_side, s_net);
+    return rc;
+  });
+}
+
+int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch, int tau_plies,
+                          int auto_restart, int first_player, int net_impl, void* stream) {
+  caro_engine* es[2] = {e0, e1};
+  return caro_engine_play_multi(es, 2, net, moves, count, batch, tau_plies, auto_restart, first_player, net_impl, stream);
 }
 
 int caro_engine_root_policy(caro_engine* e, int tau_mode, int tau_plies, double* d_pi, float* d_q, int32_t* d_n, void* stream) {

@@ -164,6 +164,17 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
   net->d_trace = nullptr;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    net->sm_count = 148;
+    cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const int prc = caro_net_tc_prepare();
+    if (prc != CARO_OK) {
+      delete net;
+      return prc;
+    }
+  }
   if (n_floats != net->layout.total) {
     delete net;
     return caro_fail(CARO_E_ARG, "weight blob has the wrong size");

@@ -55,10 +55,12 @@ struct caro_net {
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
+  int sm_count;         // multiprocessors of the device the handle was created on
 };
 
 // net_tc.cu
 int caro_net_tc_pack(caro_net* net, const float* h_blob);
+int caro_net_tc_prepare();
 void caro_net_tc_free(caro_net* net);
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                         const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int exact, cudaStream_t st);

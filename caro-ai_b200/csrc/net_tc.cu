@@ -645,19 +645,8 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   if (gm.boards_per_group < 1 || gm.boards_per_group > 32 || gm.pitch + 1 > kHalo ||
       gm.boards_per_group * (20 + gm.A) > K::kFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the tensor-core tile geometry");
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sm_count = net->sm_count;
   auto kern = net_tc_kernel<R, K>;
-  static bool attr_set = false;  // per (R, K) instantiation
-  if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kTotal);
-    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
-    attr_set = true;
-  }
   const long long max_groups = (max_count + gm.boards_per_group - 1) / gm.boards_per_group;
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
   kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
@@ -665,6 +654,17 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
                                           net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values,
                                           (long long*)net->d_trace);
   return caro_check_launch("net_tc_kernel");
+}
+
+// Sets the dynamic shared memory attribute of every instantiation up front (caro_net_create), so that no
+// attribute call can fall inside a CUDA-graph capture of the search loop.
+int caro_net_tc_prepare() {
+  cudaError_t ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFast::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFast::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  return CARO_OK;
 }
 
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,

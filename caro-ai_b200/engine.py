@@ -207,6 +207,16 @@ class SelfPlayEngine:
         _cabi.check(_cabi.lib().caro_engine_play_pair(self.handle, other.handle, net.handle, moves, count, batch, tau_plies,
                                                       1 if auto_restart else 0, first_player, impl, self._stream()))
 
+    @staticmethod
+    def play_multi(engines: Sequence["SelfPlayEngine"], net: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
+                   auto_restart: bool = True, first_player: int = -1, impl: int = None):
+        """Round-robin software pipeline over several engines (parts of the game batch): every part's tree kernels
+        run on its own side stream underneath the other parts' network passes (caro_engine_play_multi)."""
+        impl = net.impl if impl is None else impl
+        arr = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+        _cabi.check(_cabi.lib().caro_engine_play_multi(arr, len(engines), net.handle, moves, count, batch, tau_plies,
+                                                       1 if auto_restart else 0, first_player, impl, engines[0]._stream()))
+
     # ------------------------------------------------------------------ read-back
     COUNTER_NAMES = ("leaf_evals", "games", "plies", "wins_p0", "wins_p1", "draws", "descents", "errors")
 

@@ -202,6 +202,11 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
  * network pass.  Self-play only (one network).  `stream` is joined with the side streams before returning. */
 int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch,
                           int tau_plies, int auto_restart, int first_player, int net_impl, void* stream);
+/* General form: n = 1..8 parts in round robin.  With three parts the tree kernels of one part have two network
+ * passes to hide under (they run 3-5x slower next to the persistent network kernel than alone).  While profiling
+ * is off, one ply (n x count x 5 kernels + n) is captured into a CUDA graph once and replayed per ply. */
+int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int moves, int count, int batch,
+                           int tau_plies, int auto_restart, int first_player, int net_impl, void* stream);
 
 /* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
  * profile_read synchronises `stream` and returns the summed milliseconds of

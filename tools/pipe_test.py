@@ -40,6 +40,12 @@ def main():
     b = SelfPlayEngine(game, G // 2, max_batch=8, node_capacity=24576, seed=3)
     a.play_pair(b, dn, moves=20, count=8, batch=8, tau_plies=10, auto_restart=True)
     run("pair pipeline", lambda n: a.play_pair(b, dn, moves=n, count=100, batch=8, tau_plies=10, auto_restart=True), 20)
+    if len(sys.argv) > 2:
+        n = int(sys.argv[2])
+        es = [SelfPlayEngine(game, G, max_batch=8, node_capacity=24576, seed=10 + i) for i in range(n)]
+        SelfPlayEngine.play_multi(es, dn, moves=20, count=8, batch=8, tau_plies=10, auto_restart=True)
+        run("multi pipeline %dx4096" % n, lambda k: SelfPlayEngine.play_multi(es, dn, moves=k, count=100, batch=8, tau_plies=10, auto_restart=True), 20)
+        return
     if len(sys.argv) > 1:
         a2 = SelfPlayEngine(game, G, max_batch=8, node_capacity=24576, seed=4)
         b2 = SelfPlayEngine(game, G, max_batch=8, node_capacity=24576, seed=5)
