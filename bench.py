@@ -311,7 +311,7 @@ def engine_arm(args):
             "e2e": {"value": e2e_leaf / (e2e_max / 1000.0), "unit": "leaf_evals/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(world * G * 17), "d2h_bytes_per_step": int(world * G * 17)},
             "gpu_launches": int(prof["launches"]),
-            "roofline": {"kernel": "net_tc_kernel (tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
+            "roofline": {"kernel": "net_rt_kernel (row-tiled tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
                          "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),

@@ -147,7 +147,9 @@ int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats) {
   if (n_floats != net->layout.total) return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
   cudaError_t ce = cudaMemcpy(net->d_blob, h_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
-  return caro_net_tc_pack(net, h_blob);
+  const int rc = caro_net_tc_pack(net, h_blob);
+  if (rc != CARO_OK) return rc;
+  return caro_net_rt_supports(net) ? caro_net_rt_pack(net, h_blob) : CARO_OK;
 }
 
 int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t n_floats, caro_net** out) {
@@ -161,6 +163,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->layout = blob_layout(rows, cols, actions);
   net->d_blob = nullptr;
   net->d_tc_weights = nullptr;
+  net->d_rt_weights = nullptr;
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
   net->d_trace = nullptr;
@@ -169,7 +172,8 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
     cudaGetDevice(&dev);
     net->sm_count = 148;
     cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const int prc = caro_net_tc_prepare();
+    int prc = caro_net_tc_prepare();
+    if (prc == CARO_OK) prc = caro_net_rt_prepare();
     if (prc != CARO_OK) {
       delete net;
       return prc;
@@ -202,6 +206,7 @@ int caro_net_set_trace(caro_net* net, void* d_trace) {
 void caro_net_destroy(caro_net* net) {
   if (!net) return;
   caro_net_tc_free(net);
+  caro_net_rt_free(net);
   if (net->d_blob) cudaFree(net->d_blob);
   delete net;
 }
@@ -222,7 +227,9 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
     if (game == CARO_GAME_CONNECT4) return launch_simt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
     return launch_simt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   }
-  if (impl == 0 || impl == 2)
+  if (impl == 0 && caro_net_rt_supports(net))
+    return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if (impl == 0 || impl == 2 || impl == 3)
     return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 2 ? 1 : 0, st);
   return caro_fail(CARO_E_ARG, "unknown net impl");
 }

@@ -52,6 +52,7 @@ struct caro_net {
   caro::BlobLayout layout;
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
+  void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
@@ -64,3 +65,11 @@ int caro_net_tc_prepare();
 void caro_net_tc_free(caro_net* net);
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                         const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int exact, cudaStream_t st);
+
+// net_rt.cu (row-tiled tower for boards up to 6 x 7)
+int caro_net_rt_pack(caro_net* net, const float* h_blob);
+int caro_net_rt_prepare();
+void caro_net_rt_free(caro_net* net);
+bool caro_net_rt_supports(const caro_net* net);
+int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);

@@ -1,0 +1,680 @@
+// Row-tiled policy/value tower on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// lib/model.py:82-94 (eval-mode BatchNorm folded on the host) for boards with H <= 6, W <= 7 (Connect4, 3x3 ..
+// 6x6 m,n,k) -- the second-generation kernel; net_tc.cu keeps serving larger boards and the bf16x3 mode.
+//
+// What limited net_tc.cu: a 128x64x16 MMA reads 4 KB of A and 2 KB of B from shared memory, 48 cycles of the
+// 128 B/clk operand path against a 32-cycle tensor floor, and 26 % of its rows were padding.  Here
+//   * an M-tile is ONE BOARD ROW of 128/pitch boards (lane = board * pitch + column, pitch = 8 for Connect4),
+//     so the vertical taps of a 3x3 convolution are TILE offsets, not row offsets: no zero row between boards
+//     (87.5 % useful rows), and rows outside the board are simply not issued;
+//   * the three vertical taps are stacked along N: source tile y multiplies its activations ONCE per
+//     (horizontal tap, k-step) with B = [w(dy=+1) | w(dy=0) | w(dy=-1)] (192 columns) and the MMA accumulates
+//     into the three neighbouring output tiles, which are adjacent column ranges of TMEM (out[y] at 64y):
+//     12 MMAs of 128x192x16 per tile and layer instead of 36 of 128x64x16, 10 KB of operands per 96-cycle MMA
+//     -> tensor-bound instead of shared-memory-bound;
+//   * the fp32 accumulators of all H output tiles fill 384 of the 512 TMEM columns, so the residual stream
+//     v <- v + lrelu(conv(v)) is kept as bf16 hi (the shared-memory activations themselves) + an e5m2 lo part
+//     (4 channels per TMEM column, 96 columns): ~11 mantissa bits, indistinguishable from the fp32 stream at
+//     the 1e-3 contract;
+//   * weights stream through a ring of 6 KB blocks (one (horizontal tap, k-step) each) with full/empty
+//     mbarriers: cp.async.bulk by a producer warp, released by tcgen05.commit after the last tile used a block.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "../../include/caro_b200.h"
+#include "common_host.h"
+#include "net.h"
+#include "rules.cuh"
+
+#include "tc_common.cuh"
+
+#ifndef CARO_RT_CP
+#define CARO_RT_CP 2  // channel parts of the epilogue: 2 -> 8 epilogue warps of 32 channels, 4 -> 16 warps of 16
+#endif
+
+namespace caro {
+
+constexpr int kRtMaxH = 6;
+constexpr int kRtMaxW = 7;
+constexpr int kRtHalo = 2;                                   // zero rows before / after the tiles (>= 1)
+constexpr int kRtActRows = kRtMaxH * 128 + 2 * kRtHalo;      // 772
+constexpr int kRtChunkBytes = kRtActRows * 16;               // one 8-channel chunk of all rows
+constexpr int kRtActBytes = 8 * kRtChunkBytes;               // 98,816
+constexpr int kRtBlockBytes = 2 * 192 * 16;                  // 6,144: B operand of one (dx, k-step): [2 chunks][192][8]
+constexpr int kRtBlockUnits = kRtBlockBytes / 16;            // in descriptor units
+constexpr int kRtRegionBlocks = 6;                           // a weight region = half a layer
+constexpr int kRtRegions = 3;                                // resident regions: layer L in two, the first half of L+1 in the third
+constexpr int kRtRegionBytes = kRtRegionBlocks * kRtBlockBytes;          // 36,864
+constexpr int kRtRegionsNet = 1 + 2 * kBlocks;               // conv_in (3 blocks + 3 unused) + 2 per residual block
+constexpr int kRtBlocksNet = kRtRegionsNet * kRtRegionBlocks;             // 66 blocks in the global image
+constexpr int kRtLayers = 1 + kBlocks;
+constexpr uint32_t kRtTmemCols = 512;
+constexpr uint32_t kRtLoCol = 384;                           // e5m2 lo residual: tile y at 384 + 16 y
+constexpr int kRtHeadFloats = 2016;                          // max nb * 3 * H * W (16 Connect4 boards)
+constexpr int kRtFcFloats = 928;                             // max nb * (20 + A) (32 3x3 boards)
+
+__host__ __device__ constexpr uint32_t rt_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+struct RtGeom {
+  int H, W, A, pitch, pshift, nb;
+};
+
+// CP = channel parts of the epilogue (2 -> 8 epilogue warps x 32 channels, 4 -> 16 warps x 16 channels)
+template <int CP>
+struct RtCfg {
+  static constexpr int kCP = CP;
+  static constexpr int kCH = 64 / CP;
+  static constexpr int kEpiWarps = 4 * CP;
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kMmaWarp = kEpiWarps;
+  static constexpr int kLoadWarp = kEpiWarps + 1;
+  static constexpr int kHeadWarp = kEpiWarps + 2;
+  static constexpr int kHeadWarps = 4;
+  static constexpr int kHeadThreads = 32 * kHeadWarps;
+  static constexpr int kThreads = kEpiThreads + 64 + kHeadThreads;
+  static constexpr int kNF = CP / 2;                         // partial head-feature arrays (two commutative adds each)
+  static constexpr int kAct = 0;
+  static constexpr int kWgt = kAct + kRtActBytes;
+  static constexpr int kBias = kWgt + kRtRegions * kRtRegionBytes;
+  static constexpr int kHeadW = kBias + kRtLayers * 64 * 4;
+  static constexpr int kHeadF = kHeadW + 4 * 64 * 4;
+  static constexpr int kFc = kHeadF + kNF * kRtHeadFloats * 4;
+  static constexpr int kFcW = kFc + kRtFcFloats * 4;               // transposed FC weights (policy, value FC1) when they fit
+  static constexpr int kBars0 = kFcW;
+  static constexpr int kNumBars = kRtRegions * kRtRegionBlocks + kRtRegions + 2 * kRtMaxH + 2;
+  static constexpr int kFixed = kBars0 + kNumBars * 8 + 16;         // everything but the FC weights
+  static constexpr int kFcWFloats = (232448 - kFixed) / 4;          // what is left of the 227 KB
+  static constexpr int kBars = kFcW + kFcWFloats * 4;
+  static constexpr int kTotal = kBars + kNumBars * 8 + 16;
+  static_assert(kFixed <= 232448 && kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
+
+#define TMEM_LD8(addr, r)                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"     \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+               : "r"(addr))
+#define TMEM_LD4(addr, r) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr))
+#define TMEM_ST8(addr, r)                                                                    \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"     \
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory")
+#define TMEM_ST4(addr, r) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory")
+
+// four e5m2 values (one 32-bit TMEM column) -> two float pairs.  e5m2 is the upper byte of an fp16, so the unpack
+// is a byte permute into two half2 registers.
+__device__ __forceinline__ void e5m2x4_to_float(uint32_t w, float2& f01, float2& f23) {
+  const uint32_t p0 = __byte_perm(w, 0u, 0x1404u), p1 = __byte_perm(w, 0u, 0x3424u);
+  f01 = __half22float2(*reinterpret_cast<const __half2*>(&p0));
+  f23 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+}
+__device__ __forceinline__ uint32_t float_to_e5m2x4(float2 f01, float2 f23) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(f01, __NV_SATFINITE, __NV_E5M2);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(f23, __NV_SATFINITE, __NV_E5M2);
+  return lo | (hi << 16);
+}
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+// Fully connected heads of one group by the head warps (lib/model.py:56-72,90-93 + the softmax of lib/mcts.py:216):
+// bias + LeakyReLU of the 1x1 head convolutions in place, then every (board, output) dot product in parallel with
+// the transposed FC weights read from shared memory (or from global memory when the board is too large for them
+// to fit), then value FC2 + tanh and the softmax over ALL actions, one warp per board.
+template <int TEAM, int BAR, int NF>
+__device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s, float* fc_s,
+                                      const float* headw_s, const float* __restrict__ blob, const BlobLayout& L,
+                                      const float* polw, const float* valw, float* __restrict__ probs, float* __restrict__ values) {
+  const int HW = gm.H * gm.W, A = gm.A;
+  const int per_board = 20 + A;
+  float* hid = fc_s;  // [nb][20] value hidden units, logits behind them
+  float* logit = fc_s + gm.nb * 20;
+#pragma unroll 1
+  for (int i = ttid; i < nvalid * 3 * HW; i += TEAM) {
+    float v = headf_s[i];
+#pragma unroll
+    for (int k = 1; k < NF; ++k) {
+      v += headf_s[i + k * kRtHeadFloats];
+      headf_s[i + k * kRtHeadFloats] = 0.0f;
+    }
+    const int ch = (i / HW) % 3;
+    headf_s[i] = lrelu_tc(v + headw_s[192 + ch]);
+  }
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
+#pragma unroll 1
+  for (int o = ttid; o < nvalid * per_board; o += TEAM) {
+    const int b = o / per_board, i = o - b * per_board;
+    const float* feat = headf_s + (size_t)b * 3 * HW;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    const bool is_val = i < 20;
+    const float* wt = is_val ? valw + i : polw + (i - 20);
+    const int stride = is_val ? 20 : A;
+    const float* f = is_val ? feat : feat + HW;
+    const int n = is_val ? HW : 2 * HW;
+    int c = 0;
+#pragma unroll 2
+    for (; c + 3 < n; c += 4) {
+      a0 = fmaf(wt[(size_t)c * stride], f[c], a0);
+      a1 = fmaf(wt[(size_t)(c + 1) * stride], f[c + 1], a1);
+      a2 = fmaf(wt[(size_t)(c + 2) * stride], f[c + 2], a2);
+      a3 = fmaf(wt[(size_t)(c + 3) * stride], f[c + 3], a3);
+    }
+    for (; c < n; ++c) a0 = fmaf(wt[(size_t)c * stride], f[c], a0);
+    const float acc = (a0 + a1) + (a2 + a3);
+    if (is_val) hid[b * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + acc);
+    else logit[b * A + (i - 20)] = blob[L.pol_fc_b + (i - 20)] + acc;
+  }
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
+#pragma unroll 1
+  for (int i = ttid; i < nvalid * 3 * HW; i += TEAM) headf_s[i] = 0.0f;  // re-arm the accumulation slots
+#pragma unroll 1
+  for (int b = ttid >> 5; b < nvalid; b += TEAM / 32) {
+    const int lane = ttid & 31;
+    if (lane == 0) {
+      float acc = blob[L.val_fc2_b];
+      for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
+      values[leaf0 + b] = tanhf(acc);
+    }
+    const float* lrow = logit + b * A;
+    float* prow = probs + (size_t)(leaf0 + b) * A;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lrow[a]);
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.0f;
+#pragma unroll 1
+    for (int a = lane; a < A; a += 32) sum += expf(lrow[a] - mx);
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll 1
+    for (int a = lane; a < A; a += 32) prow[a] = expf(lrow[a] - mx) / sum;
+  }
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");  // hid / logit / slots are reused by the next group
+}
+
+// The MMAs of one source tile.  POS: 0 = first board row (no out[-1]: B slot 0 is skipped, the accumulators of
+// out[0], out[1] are overwritten by the first MMA; it is also the tile that waits for the weight blocks to land),
+// 1 = interior row (N = 192; the very first MMA is split so that out[y+1] is overwritten while out[y-1], out[y]
+// accumulate), 2 = last row (no out[H]; it releases the weight regions).  Everything but the two region bases, the
+// tile base and the TMEM addresses is a compile-time constant, so that the MMAs issue back to back.
+template <int POS, bool FIRST>
+__device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
+                                              uint32_t d_new, uint64_t* full0, uint64_t* full1, uint32_t ph0, uint32_t ph1,
+                                              uint64_t* empty0, uint64_t* empty1, uint64_t* next_bar, uint64_t* next_bar2, uint32_t next_par) {
+  constexpr int NB = FIRST ? 3 : 12;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int dx = FIRST ? i - 1 : i / 4 - 1, kk = FIRST ? 0 : i % 4;
+    if (POS == 0) mbar_wait(i < 6 ? full0 + i : full1 + (i - 6), i < 6 ? ph0 : ph1);  // first use of the block in this layer
+    // the barrier the NEXT tile needs is polled while this tile's MMAs are still queued in the tensor pipe
+    if (i == (FIRST ? 1 : 8) && next_bar != nullptr) {
+      mbar_wait(next_bar, next_par);
+      if (next_bar2 != nullptr) mbar_wait(next_bar2, next_par);
+    }
+    if (elected) {
+      const uint64_t ad = a_tile + (uint64_t)(int64_t)(dx + kk * 2 * kRtActRows);
+      const uint64_t bd = (i < 6 ? rb0 + (uint64_t)(i * kRtBlockUnits) : rb1 + (uint64_t)((i - 6) * kRtBlockUnits)) + (POS == 0 ? 64ull : 0ull);
+      if (POS == 1 && i == 0) {
+        umma_bf16(d_main, ad, bd, rt_idesc(128), 1u);
+        umma_bf16(d_new, ad, bd + 128ull, rt_idesc(64), 0u);
+      } else {
+        umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc(192) : rt_idesc(128), (POS == 0 && i == 0) ? 0u : 1u);
+      }
+      if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit(i < 6 ? empty0 : empty1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- kernel
+// Warp roles (CP = 4: 20 warps): 0 .. 4CP-1 epilogue (TMEM lane quarter = warp & 3, channel part = warp >> 2),
+// 4CP = TMEM owner + MMA issue (one elected lane: the accumulate flags make the order of the MMAs significant, so
+// there is exactly one issuing thread), 4CP+1 = weight producer, 4CP+2, 4CP+3 = FC heads of the previous group.
+// Per layer `gl` (stage), tile y:
+//   MMA(gl, y)  waits act[y+1] of stage gl (act[y-1], act[y] were waited for by the previous tiles): rows rewritten
+//               AND the accumulators out[y-1..y+1] drained by the previous layer's epilogues;
+//   EPI(gl, y)  waits the commit after source tile min(y+1, H-1): out[y] has received all of its contributions;
+//               it rewrites act[y] in place (source tile y has been consumed by then).
+template <class R, class K>
+__global__ void __launch_bounds__(K::kThreads, 1)
+net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
+              const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
+              const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
+              const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
+              float* __restrict__ values, long long* __restrict__ trace) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* act = smem + K::kAct;
+  uint8_t* wgt = smem + K::kWgt;
+  float* bias_s = reinterpret_cast<float*>(smem + K::kBias);
+  float* headw_s = reinterpret_cast<float*>(smem + K::kHeadW);
+  float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
+  float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [regions][6] weight block landed
+  uint64_t* bar_empty = bar_full + kRtRegions * kRtRegionBlocks;          // [regions] region consumed by the last tile
+  uint64_t* bar_acc = bar_empty + kRtRegions;                             // [H] MMAs of source tile y complete
+  uint64_t* bar_act = bar_acc + kRtMaxH;                                  // [H] activation tile rewritten + accumulator drained
+  uint64_t* bar_feat = bar_act + kRtMaxH;                                 // [0] head features complete, [1] consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_feat + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
+  const int nb = gm.nb;
+  const int H = gm.H;
+  const long long n_groups = (count + nb - 1) / nb;
+  if ((long long)blockIdx.x >= n_groups) return;  // uniform per CTA, before any barrier / TMEM use
+  const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  for (int i = tid; i < kRtActBytes / 16; i += K::kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kRtLayers * 64; i += K::kThreads) bias_s[i] = bias_g[i];
+  for (int i = tid; i < K::kNF * kRtHeadFloats; i += K::kThreads) headf_s[i] = 0.0f;
+  for (int i = tid; i < 64; i += K::kThreads) {
+    headw_s[i] = blob[L.val_conv_w + i];
+    headw_s[64 + i] = blob[L.pol_conv_w + i];
+    headw_s[128 + i] = blob[L.pol_conv_w + 64 + i];
+  }
+  if (tid == 0) {
+    headw_s[192] = blob[L.val_conv_b];
+    headw_s[193] = blob[L.pol_conv_b];
+    headw_s[194] = blob[L.pol_conv_b + 1];
+    for (int s = 0; s < kRtRegions * kRtRegionBlocks; ++s) mbar_init(bar_full + s, 1);
+    for (int s = 0; s < kRtRegions; ++s) mbar_init(bar_empty + s, 1);
+    for (int t = 0; t < kRtMaxH; ++t) {
+      mbar_init(bar_acc + t, 1);
+      mbar_init(bar_act + t, K::kEpiThreads);
+    }
+    mbar_init(bar_feat + 0, K::kEpiThreads);
+    mbar_init(bar_feat + 1, K::kHeadThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == K::kMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kRtTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= K::kHeadWarp) {
+    // ===================== head warps: FC heads of group g while the pipeline already runs group g+1; the last
+    // group of a CTA is left to the epilogue warps (idle by then, and many more threads) ==========================
+    const int htid = tid - K::kHeadWarp * 32;
+    const int HW = gm.H * gm.W;
+    const int fcw_floats = HW * (2 * gm.A + 20);
+    const float* polw = pol_fc_t;
+    const float* valw = val_fc1_t;
+    if (fcw_floats <= K::kFcWFloats) {  // both transposed matrices are contiguous in global memory (net_tc.cu pack)
+      float* fcw_s = reinterpret_cast<float*>(smem + K::kFcW);
+      for (int i = htid; i < fcw_floats; i += K::kHeadThreads) fcw_s[i] = pol_fc_t[i];
+      asm volatile("bar.sync 2, %0;" ::"n"(K::kHeadThreads) : "memory");
+      polw = fcw_s;
+      valw = fcw_s + 2 * HW * gm.A;
+    }
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
+      const int nvalid = (int)min((long long)nb, count - leaf0);
+      mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
+      rt_heads<K::kHeadThreads, 2, K::kNF>(gm, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, polw, valw, probs, values);
+      mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
+      if (htid == 0) TC_TRACE(5, gi);
+    }
+  } else if (warp == K::kLoadWarp) {
+    // ===================== weight producer: the 11 regions of the network, over and over, round-robin into the
+    // three resident regions; a region is refilled as soon as the last tile of its layer has released it ==========
+    if ((tid & 31) == 0) {
+      const int total = my_groups * kRtRegionsNet;
+      int reg = 0, src = 0;
+      uint32_t round = 0;
+      for (int n = 0; n < total; ++n) {
+        if (round > 0) mbar_wait(bar_empty + reg, (round - 1u) & 1u);
+        const int nblk = src == 0 ? 3 : kRtRegionBlocks;  // conv_in: three real blocks, the others keep their phases in step
+        for (int b = 0; b < kRtRegionBlocks; ++b) {
+          uint64_t* bar = bar_full + reg * kRtRegionBlocks + b;
+          if (b < nblk) {
+            mbar_expect_tx(bar, (uint32_t)kRtBlockBytes);
+            bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * kRtBlockBytes, wimg + (size_t)(src * kRtRegionBlocks + b) * kRtBlockBytes,
+                     (uint32_t)kRtBlockBytes, bar);
+          } else {
+            mbar_arrive(bar);
+          }
+        }
+        if (++reg == kRtRegions) { reg = 0; ++round; }
+        if (++src == kRtRegionsNet) src = 0;
+      }
+    }
+  } else if (warp == K::kMmaWarp) {
+    // ===================== MMA issuer: the whole warp runs the loop (warp-uniform descriptor arithmetic), one
+    // elected lane issues MMAs and commits ============================================================================
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+    const uint64_t a_desc0 = make_desc(smem_u32(act) + (uint32_t)kRtHalo * 16u, (uint32_t)kRtChunkBytes, 128u);
+    const uint64_t b_desc0 = make_desc(smem_u32(wgt), 192u * 16u, 128u);
+    const int total_layers = my_groups * kRtLayers;
+    int reg = 0;
+    uint32_t rphase = 0;
+    int layer = 0;
+    bool pre_waited = false;
+    for (int gl = 0; gl < total_layers; ++gl) {
+      const uint32_t par = (uint32_t)gl & 1u;
+      const bool first = layer == 0;
+      const uint64_t rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+      uint64_t* full0 = bar_full + reg * kRtRegionBlocks;
+      uint64_t* empty0 = bar_empty + reg;
+      const uint32_t ph0 = rphase;
+      if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
+      uint64_t rb1 = rb0;
+      uint64_t *full1 = full0, *empty1 = empty0;
+      uint32_t ph1 = ph0;
+      if (!first) {
+        rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+        full1 = bar_full + reg * kRtRegionBlocks;
+        empty1 = bar_empty + reg;
+        ph1 = rphase;
+        if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
+      }
+#pragma unroll 1
+      for (int y = 0; y < H; ++y) {
+        // tile y reads act[y] and writes out[y-1..y+1]: it needs the barriers of tiles y-1, y, y+1 at this stage.
+        // All but the first tile's were already polled while the previous tile's MMAs were being issued.
+        if (y == 0 && !pre_waited) {
+          mbar_wait(bar_act + 0, par);
+          mbar_wait(bar_act + 1, par);
+        }
+        tc_fence_after();  // orders this tile's MMAs after the barrier observations (also the early ones)
+        if (elected) TC_TRACE(0, gl * 8 + y);
+        const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(y * 128);
+        // D columns: out[y-1] | out[y] | out[y+1]; the first tile has no out[-1], the last no out[H]
+        const uint32_t d_main = tmem_base + (uint32_t)(y == 0 ? 0 : (y - 1) * 64);
+        const uint32_t d_new = tmem_base + (uint32_t)((y + 1) * 64);
+        uint64_t *nb0 = nullptr, *nb1 = nullptr;
+        uint32_t npar = par;
+        if (y + 2 < H) {
+          nb0 = bar_act + y + 2;  // for tile y+1
+        } else if (y == H - 1 && H >= 4 && gl + 1 < total_layers) {
+          // next layer's first tile: its barriers depend on commits issued two or more tiles ago (H >= 4)
+          nb0 = bar_act + 0;
+          nb1 = bar_act + 1;
+          npar = par ^ 1u;
+        }
+        if (first) {
+          if (y == 0) rt_issue_tile<0, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+        } else {
+          if (y == 0) rt_issue_tile<0, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+        }
+        if (elected) {
+          umma_commit(bar_acc + y);
+          TC_TRACE(1, gl * 8 + y);
+        }
+        __syncwarp();
+      }
+      pre_waited = H >= 4 && gl + 1 < total_layers;
+      if (++layer == kRtLayers) layer = 0;
+    }
+  } else {
+    // ========================================= epilogue warps =========================================
+    constexpr int CH = K::kCH;
+    const int quarter = warp & 3, cp = warp >> 2;
+    const int row = quarter * 32 + (tid & 31);              // lane of the tile = TMEM lane
+    const int bidx = row >> gm.pshift, col = row & (gm.pitch - 1);
+    const bool real = col < gm.W;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int HW = gm.H * gm.W;
+    float* featc = headf_s + (cp >> 1) * kRtHeadFloats;     // two commutative contributions per slot and array
+    const bool dbg_skip_epilogue = trace != nullptr && trace[7999] == 1;
+
+    auto write_inputs = [&](int y, long long leaf0) {
+      if (cp == 0) {
+        uint32_t lo = 0u;
+        const long long leaf = leaf0 + bidx;
+        if (real && leaf < count) {
+          const typename R::Board s = boards[leaf];
+          const int wm = who[leaf];
+          const uint32_t mine = rules.plane_value(s, wm, 0, y, col) ? 0x3F80u : 0u;  // bf16(1.0)
+          const uint32_t other = rules.plane_value(s, wm, 1, y, col) ? 0x3F80u : 0u;
+          lo = mine | (other << 16);
+        }
+        uint8_t* dst = act + (size_t)(kRtHalo + y * 128 + row) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(lo, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + kRtChunkBytes) = make_uint4(0u, 0u, 0u, 0u);  // K is padded to 16
+        fence_async_smem();
+      }
+      mbar_arrive(bar_act + y);
+    };
+
+    // One tile of one layer.  HAS_RES: the layer has a residual input (all but conv_in); LAST: the tower's last
+    // layer feeds the 1x1 head convolutions instead of the next layer.
+    auto epilogue_tile = [&](auto has_res_c, auto last_c, int gi, int layer, int gl, int y, bool more, long long next_leaf0) {
+      constexpr bool HAS_RES = decltype(has_res_c)::value;
+      constexpr bool LAST = decltype(last_c)::value;
+      mbar_wait(bar_acc + min(y + 1, H - 1), (uint32_t)gl & 1u);
+      __syncwarp();
+      tc_fence_after();
+      if (tid == 0) TC_TRACE(2, gl * 8 + y);
+      if (dbg_skip_epilogue) {  // debug (tools/net_trace.py): measure the MMA stream without the epilogue's traffic
+        tc_fence_before();
+        if (!LAST || more) mbar_arrive(bar_act + y);
+        return;
+      }
+      const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(y * 64 + cp * CH);
+      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * (CH / 4));
+      uint8_t* arow = act + (size_t)(cp * (CH / 8) * kRtActRows + kRtHalo + y * 128 + row) * 16;
+      const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64 + cp * CH);
+      uint32_t ra[CH], rl[CH / 4];
+      uint4 hv[CH / 8];
+      TMEM_LD16(a_acc, ra);
+      if (CH == 32) TMEM_LD16(a_acc + 16u, (ra + 16));
+      if (HAS_RES) {
+        if (CH == 32) {
+          TMEM_LD8(a_lo, rl);
+        } else {
+          TMEM_LD4(a_lo, rl);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < CH / 8; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float2 v[CH / 2];
+      const float2 slope = make_float2(kLeaky, kLeaky);
+#pragma unroll
+      for (int q = 0; q < CH / 4; ++q) {
+        const float4 bq = bl4[q];
+        const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4]), __uint_as_float(ra[q * 4 + 1])), make_float2(bq.x, bq.y));
+        const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4 + 2]), __uint_as_float(ra[q * 4 + 3])), make_float2(bq.z, bq.w));
+        const float2 t01 = __fmul2_rn(x01, slope), t23 = __fmul2_rn(x23, slope);
+        float2 m01 = make_float2(fmaxf(x01.x, t01.x), fmaxf(x01.y, t01.y));
+        float2 m23 = make_float2(fmaxf(x23.x, t23.x), fmaxf(x23.y, t23.y));
+        if (HAS_RES) {
+          float2 l01, l23;
+          e5m2x4_to_float(rl[q], l01, l23);
+          const uint4 h4 = hv[q >> 1];
+          const uint32_t w0 = (q & 1) ? h4.z : h4.x, w1 = (q & 1) ? h4.w : h4.y;
+          m01 = __fadd2_rn(m01, __fadd2_rn(bf16x2_to_float2(w0), l01));
+          m23 = __fadd2_rn(m23, __fadd2_rn(bf16x2_to_float2(w1), l23));
+        }
+        v[q * 2] = m01;
+        v[q * 2 + 1] = m23;
+      }
+      if (!LAST) {
+        const float2 minus1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+        for (int c8 = 0; c8 < CH / 8; ++c8) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 vv = v[c8 * 4 + j];
+            const __nv_bfloat162 h = __floats2bfloat162_rn(vv.x, vv.y);
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+            packed[j] = real ? hw : 0u;
+            v[c8 * 4 + j] = __ffma2_rn(bf16x2_to_float2(hw), minus1, vv);  // lo part
+          }
+          *reinterpret_cast<uint4*>(arow + (size_t)c8 * kRtChunkBytes) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
+        if (CH == 32) {
+          TMEM_ST8(a_lo, rl);
+        } else {
+          TMEM_ST4(a_lo, rl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_act + y);
+        if (tid == 0) TC_TRACE(3, gl * 8 + y);
+      } else {
+        // 1x1 head convolutions on the fp32 values: this thread holds CH of the 64 channels
+        const float4* hw4 = reinterpret_cast<const float4*>(headw_s + cp * CH);
+        float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) {
+          const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
+          const float2 a = v[q * 2], b = v[q * 2 + 1];
+          av = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(b.x, w0.z, fmaf(b.y, w0.w, av))));
+          ap0 = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(b.x, w1.z, fmaf(b.y, w1.w, ap0))));
+          ap1 = fmaf(a.x, w2.x, fmaf(a.y, w2.y, fmaf(b.x, w2.z, fmaf(b.y, w2.w, ap1))));
+        }
+        if (gi > 0 && y == 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // slots re-zeroed by the head warps
+        if (real) {
+          const int cell = y * gm.W + col;
+          atomicAdd(&featc[(bidx * 3 + 0) * HW + cell], av);
+          atomicAdd(&featc[(bidx * 3 + 1) * HW + cell], ap0);
+          atomicAdd(&featc[(bidx * 3 + 2) * HW + cell], ap1);
+        }
+        // source tile y of the last layer has been consumed (its commit precedes the one waited for above):
+        // the next group's input planes can go in right away
+        tc_fence_before();
+        if (more) write_inputs(y, next_leaf0);
+        if (tid == 0) TC_TRACE(3, gl * 8 + y);
+      }
+    };
+
+    for (int y = 0; y < H; ++y) write_inputs(y, (long long)blockIdx.x * nb);
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
+      const bool more = gi + 1 < my_groups;
+      const long long next_leaf0 = (blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb;
+      const int gl0 = gi * kRtLayers;
+#pragma unroll 1
+      for (int y = 0; y < H; ++y) epilogue_tile(std::false_type{}, std::false_type{}, gi, 0, gl0, y, more, next_leaf0);
+#pragma unroll 1
+      for (int layer = 1; layer < kRtLayers - 1; ++layer) {
+#pragma unroll 1
+        for (int y = 0; y < H; ++y) epilogue_tile(std::true_type{}, std::false_type{}, gi, layer, gl0 + layer, y, more, next_leaf0);
+      }
+#pragma unroll 1
+      for (int y = 0; y < H; ++y)
+        epilogue_tile(std::true_type{}, std::true_type{}, gi, kRtLayers - 1, gl0 + kRtLayers - 1, y, more, next_leaf0);
+      mbar_arrive(bar_feat + 0);  // this thread's head features are in place (release) -> head warps
+      if (tid == 0) TC_TRACE(4, gi);
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == K::kMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");
+  }
+}
+
+static uint16_t rt_f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace caro
+
+using namespace caro;
+
+// Weight image: 11 regions of 6 blocks of 6,144 B (conv_in: 3 blocks used).  Block (layer, dx, k-step) = B operand
+// [2 k-chunks][n = 192][8 in-channels], n = 64 j + out-channel with j = 0,1,2 <-> vertical tap ky = 2,1,0 (the
+// output tile above / at / below the source tile).
+int caro_net_rt_pack(caro_net* net, const float* h) {
+  const BlobLayout& L = net->layout;
+  const size_t img_bytes = (size_t)kRtBlocksNet * kRtBlockBytes;
+  std::vector<uint16_t> img(img_bytes / 2, 0);
+  auto put = [&](int block, int j, int co, int c, float w) {
+    const size_t off = (size_t)block * kRtBlockBytes + (size_t)(c / 8) * 3072 + (size_t)(j * 64 + co) * 16 + (size_t)(c % 8) * 2;
+    img[off / 2] = rt_f32_to_bf16(w);
+  };
+  for (int kx = 0; kx < 3; ++kx)
+    for (int j = 0; j < 3; ++j)
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 2; ++ci) put(kx, j, co, ci, h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + (2 - j) * 3 + kx)]);
+  for (int l = 0; l < kBlocks; ++l)
+    for (int kx = 0; kx < 3; ++kx)
+      for (int kk = 0; kk < 4; ++kk)
+        for (int j = 0; j < 3; ++j)
+          for (int co = 0; co < 64; ++co)
+            for (int c = 0; c < 16; ++c)
+              put(kRtRegionBlocks + l * 12 + kx * 4 + kk, j, co, c,
+                  h[L.conv_w[l] + ((size_t)(co * 64 + kk * 16 + c) * 9 + (2 - j) * 3 + kx)]);
+  cudaError_t ce = cudaSuccess;
+  if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);
+  if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  return CARO_OK;
+}
+
+void caro_net_rt_free(caro_net* net) {
+  if (net->d_rt_weights) cudaFree(net->d_rt_weights);
+  net->d_rt_weights = nullptr;
+}
+
+bool caro_net_rt_supports(const caro_net* net) { return net->H >= 2 && net->H <= kRtMaxH && net->W >= 2 && net->W <= kRtMaxW; }
+
+using RtK = RtCfg<CARO_RT_CP>;
+
+template <class R>
+static int launch_rt(const R& rules, caro_net* net, const void* boards, const uint8_t* who, const int32_t* d_count,
+                     int64_t max_count, float* probs, float* values, cudaStream_t st) {
+  RtGeom gm;
+  gm.H = net->H;
+  gm.W = net->W;
+  gm.A = net->A;
+  gm.pshift = net->W < 4 ? 2 : 3;
+  gm.pitch = 1 << gm.pshift;
+  gm.nb = 128 / gm.pitch;
+  if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats)
+    return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
+  const long long max_groups = (max_count + gm.nb - 1) / gm.nb;
+  const unsigned grid = (unsigned)(max_groups < net->sm_count ? max_groups : net->sm_count);
+  net_rt_kernel<R, RtK><<<grid, RtK::kThreads, RtK::kTotal, st>>>(
+      rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_weights,
+      net->d_tc_bias, net->d_blob, net->layout, net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs,
+      values, (long long*)net->d_trace);
+  return caro_check_launch("net_rt_kernel");
+}
+
+int caro_net_rt_prepare() {
+  cudaError_t ce = cudaFuncSetAttribute(net_rt_kernel<C4Rules, RtK>, cudaFuncAttributeMaxDynamicSharedMemorySize, RtK::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rt_kernel<MnkRules, RtK>, cudaFuncAttributeMaxDynamicSharedMemorySize, RtK::kTotal);
+  if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  return CARO_OK;
+}
+
+int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st) {
+  if (game == CARO_GAME_CONNECT4) return launch_rt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  return launch_rt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+}

@@ -103,7 +103,9 @@ int caro_net_set_trace(caro_net* net, void* d_trace);
  *             max_count leaves are evaluated.
  *   d_probs : float32 [max_count][A] softmax priors (over ALL actions, like the reference).
  *   d_values: float32 [max_count]    tanh value head.
- *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path: one bf16 pass, fp32 accumulate),
+ *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path: one bf16 pass, fp32 accumulate); boards up to
+ *                 6 x 7 run the row-tiled kernel (net_rt.cu), larger ones the tap-per-MMA kernel (net_tc.cu),
+ *             3 = tcgen05 bf16 tower, tap-per-MMA kernel for every board size (A/B comparisons),
  *             2 = tcgen05 "bf16x3" tower (hi/lo split of activations and weights, 3 MMAs per product:
  *                 fp32-class accuracy for trained checkpoints with large logits, ~1/3.5 of the speed),
  *             1 = fp32 SIMT tower (numerics reference kernel used by the tests). */

@@ -14,16 +14,20 @@ from caro_ai_b200.model import DeviceNet, Net
 
 def main():
     leaves = int(sys.argv[1]) if len(sys.argv) > 1 else 10368
+    impl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    div = 8 if impl == 0 else 4  # the row-tiled kernel stamps gl * 8 + tile, the tap-per-MMA kernel gl * 4 + tile
     game = ConnectFour()
     torch.manual_seed(0)
     dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
     boards = torch.zeros((leaves, 2), dtype=torch.int64, device="cuda")
     who = torch.zeros(leaves, dtype=torch.uint8, device="cuda")
     for _ in range(3):
-        dn.forward_boards(boards, who, leaves, 0)
+        dn.forward_boards(boards, who, leaves, impl)
     trace = torch.zeros(8000, dtype=torch.int64, device="cuda")
+    if len(sys.argv) > 4 and sys.argv[4] == "mma-only":
+        trace[7999] = 1  # row-tiled kernel: epilogue warps only pass the barriers on
     _cabi.check(_cabi.lib().caro_net_set_trace(dn.handle, trace.data_ptr()))
-    dn.forward_boards(boards, who, leaves, 0)
+    dn.forward_boards(boards, who, leaves, impl)
     torch.cuda.synchronize()
     _cabi.check(_cabi.lib().caro_net_set_trace(dn.handle, None))
     t = trace.cpu().numpy()
@@ -41,7 +45,7 @@ def main():
         if kind == 6:
             print("%8d  %-14s gl=%d mw=%d" % (clk - t0, names[kind], idx // 2, idx % 2))
         elif kind < 4:
-            print("%8d  %-14s gl=%d t=%d" % (clk - t0, names[kind], idx // 4, idx % 4))
+            print("%8d  %-14s gl=%d t=%d" % (clk - t0, names[kind], idx // div, idx % div))
         else:
             print("%8d  %-14s group=%d" % (clk - t0, names[kind], idx))
 
