@@ -184,6 +184,8 @@ def engine_arm(args):
     torch.manual_seed(0)
     net = Net(game.obs_shape, game.action_space).eval()
     dnet = DeviceNet(net, game)
+    if args.net_sms:
+        dnet.set_grid_limit(args.net_sms)
     G = args.games
     # the game batch is split in two halves that are software-pipelined against each other (one half's tree kernels
     # run on a side stream underneath the other half's network pass); --no-pipeline keeps one engine, one stream
@@ -343,6 +345,7 @@ def main():
     ap.add_argument("--cpu-plies", type=int, default=20)
     ap.add_argument("--preroll", type=int, default=30)
     ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--net-sms", type=int, default=0, help="SMs the network kernel may occupy (0 = all); the rest serve the tree kernels")
     ap.add_argument("--profile-level", type=int, default=1, help="1: CUDA events around the network kernel only, 2: all phases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

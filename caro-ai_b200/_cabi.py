@@ -34,6 +34,7 @@ _SIGNATURES = {
     "caro_net_update": (C.c_int, [_P, _P, C.c_size_t]),
     "caro_net_destroy": (None, [_P]),
     "caro_net_set_trace": (C.c_int, [_P, _P]),
+    "caro_net_set_grid_limit": (C.c_int, [_P, C.c_int]),
     "caro_net_forward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, C.c_int, _P]),
     "caro_engine_workspace_bytes": (C.c_size_t, [C.POINTER(EngineConfig)]),
     "caro_engine_create": (C.c_int, [C.POINTER(EngineConfig), _P, C.c_size_t, C.POINTER(_P), _P]),

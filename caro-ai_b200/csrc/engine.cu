@@ -180,11 +180,14 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // group width / actions per lane for the select and noise kernels
 template <class R, class Board>
 int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const SearchParams& sp, int batch, int mb,
-                  const double* noise, double* noise_out, cudaStream_t st) {
+                  const double* noise, double* noise_out, cudaStream_t st, int phase = 0) {
+  // phase 0: noise (unless injected) + select; 1: only generate the Philox noise of minibatch `mb` into v.noise;
+  // 2: only select, reading v.noise as generated by an earlier phase-1 call (the self-play pipeline issues the
+  // noise of minibatch i+1 underneath the network pass of minibatch i: it depends on (uid, ply, i) alone)
   const long long groups = (long long)dm.G * batch;
   auto grid = [&](int gw) { return (unsigned)((groups * gw + 255) / 256); };
   const int A = dm.A;
-  const double* src = noise;
+  const double* src = phase == 2 ? v.noise : noise;
   if (src == nullptr) {  // Philox path: generate this minibatch's Dirichlet vectors first
     double* dst = noise_out ? noise_out : v.noise;
 #define NOISE(GW, APL) noise_kernel<GW, APL><<<grid(GW), 256, 0, st>>>(v.uid, v.ply, v.root_player, dm, sp, batch, mb, dst)
@@ -196,7 +199,8 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
     else NOISE(32, 8);
 #undef NOISE
     src = dst;
-  } else if (noise_out != nullptr) {
+    if (phase == 1) return caro_check_launch("noise_kernel");
+  } else if (noise_out != nullptr && phase != 2) {
     cudaMemcpyAsync(noise_out, noise, sizeof(double) * (size_t)groups * A, cudaMemcpyDeviceToDevice, st);
   }
 #define SELECT(GW, APL) select_kernel<R, GW, APL><<<grid(GW), 256, 0, st>>>(v, rules, dm, sp, batch, src)
@@ -216,6 +220,23 @@ static int do_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player
 
 extern "C" {
 
+// Experiment switch (CARO_TREE_CARVEOUT=1): ask for the same maximal shared-memory carve-out as the tensor-core
+// tower for the Connect4 tree kernels, so that the SM does not have to be reconfigured for their blocks and they
+// can become resident next to a running tower CTA (which leaves ~15 K registers and one block reservation free).
+static void apply_tree_carveout() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* env = getenv("CARO_TREE_CARVEOUT");
+  if (!env || env[0] != '1') return;
+  const int v = cudaSharedmemCarveoutMaxShared;
+  cudaFuncSetAttribute(select_thread_kernel<C4Rules, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+  cudaFuncSetAttribute(noise_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+  cudaFuncSetAttribute(plan_kernel<C4Board, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+  cudaFuncSetAttribute(expand_backup_kernel<C4Rules, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+  cudaFuncSetAttribute(advance_kernel<C4Rules>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+}
+
 size_t caro_engine_workspace_bytes(const caro_engine_config* cfg) {
   Dims dm;
   int plies;
@@ -233,6 +254,7 @@ size_t caro_engine_workspace_bytes(const caro_engine_config* cfg) {
 
 int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t bytes, caro_engine** out, void* stream) {
   if (!out || !d_workspace) return caro_fail(CARO_E_ARG, "null argument");
+  apply_tree_carveout();
   if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the engine has no CPU fallback");
   Dims dm;
   int plies;
@@ -413,7 +435,16 @@ int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, c
 
 // One minibatch.  `s_tree` runs noise/select/plan and expand+backup, `s_net` the network; when they differ the
 // hand-offs are CUDA events, so that another engine's tree kernels can run underneath this engine's network pass.
-static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_impl, cudaStream_t s_tree, cudaStream_t s_net) {
+static int select_phase(caro_engine* e, int batch, int mb, int phase, cudaStream_t st) {
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    return launch_select<C4Rules>(e->v_c4, C4Rules(), e->dm, e->sp, batch, mb, nullptr, nullptr, st, phase);
+  return launch_select<MnkRules>(e->v_mnk, e->mnk, e->dm, e->sp, batch, mb, nullptr, nullptr, st, phase);
+}
+
+// `prefetch`: 0 = noise + select as one step, 1 = minibatch i's noise was issued by the previous step, and this
+// step issues minibatch i+1's (if `more`) right behind its plan kernel, i.e. underneath its own network pass.
+static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_impl, cudaStream_t s_tree, cudaStream_t s_net,
+                       int prefetch = 0, bool more = false) {
   const bool c4 = e->cfg.game == CARO_GAME_CONNECT4;
   const void* lb = c4 ? (const void*)e->v_c4.leaf_board : (const void*)e->v_mnk.leaf_board;
   const uint8_t* lp = c4 ? e->v_c4.leaf_player : e->v_mnk.leaf_player;
@@ -426,7 +457,12 @@ static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_
     cudaEventCreateWithFlags(&e->sync_b, cudaEventDisableTiming);
   }
   e->span_begin(0, s_tree);
-  int rc = caro_engine_select(e, batch, i, nullptr, nullptr, s_tree);
+  int rc = CARO_OK;
+  if (prefetch && i > 0) {
+    rc = select_phase(e, batch, i, 2, s_tree);
+  } else {
+    rc = caro_engine_select(e, batch, i, nullptr, nullptr, s_tree);
+  }
   e->span_end(0, s_tree);
   e->span_begin(1, s_tree);
   if (rc == CARO_OK) rc = caro_engine_plan(e, batch, s_tree);
@@ -435,6 +471,7 @@ static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_
     cudaEventRecord(e->sync_a, s_tree);
     cudaStreamWaitEvent(s_net, e->sync_a, 0);
   }
+  if (prefetch && more && rc == CARO_OK) rc = select_phase(e, batch, i + 1, 1, s_tree);
   e->span_begin(2, s_net);
   if (rc == CARO_OK)
     rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, lb, lp, lc, (int64_t)e->dm.G * batch, pr, va, net_impl, s_net);
@@ -465,8 +502,12 @@ int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int 
 static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batch, int tau_plies, int auto_restart,
                      int first_player, int net_impl, cudaStream_t* s_side, cudaStream_t s_net) {
   int rc = CARO_OK;
+  // CARO_SPLIT_NET=1 (experiment): every part keeps its network passes on its own side stream, so the parts are
+  // completely independent chains and the tail of one part's network kernel overlaps the head of the other's
+  static const bool split = getenv("CARO_SPLIT_NET") && getenv("CARO_SPLIT_NET")[0] == '1';
   for (int i = 0; i < count && rc == CARO_OK; ++i)
-    for (int h = 0; h < n && rc == CARO_OK; ++h) rc = search_step(es[h], net, i, batch, net_impl, s_side[h], s_net);
+    for (int h = 0; h < n && rc == CARO_OK; ++h)
+      rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);
   for (int h = 0; h < n && rc == CARO_OK; ++h) {
     rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
     es[h]->launches += 1;

@@ -167,6 +167,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
   net->d_trace = nullptr;
+  net->grid_limit = 0;
   {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -194,6 +195,12 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
     return rc;
   }
   *out = net;
+  return CARO_OK;
+}
+
+int caro_net_set_grid_limit(caro_net* net, int ctas) {
+  if (!net || ctas < 0) return caro_fail(CARO_E_ARG, "bad grid limit");
+  net->grid_limit = ctas;
   return CARO_OK;
 }
 

@@ -36,6 +36,12 @@
 
 #include "tc_common.cuh"
 
+#ifndef CARO_RT_MAXREG
+#define CARO_RT_MAXREG 112  // 448 threads x 112 = 50,176 registers: 15 K stay free for a co-resident tree-kernel block
+#endif
+#ifndef CARO_RT_SMEM_LIMIT
+#define CARO_RT_SMEM_LIMIT (232448 - 1024)  // one more 1 KB block reservation fits beside this CTA on the SM
+#endif
 #ifndef CARO_RT_CP
 #define CARO_RT_CP 2  // channel parts of the epilogue: 2 -> 8 epilogue warps of 32 channels, 4 -> 16 warps of 16
 #endif
@@ -69,6 +75,14 @@ struct RtGeom {
   int H, W, A, pitch, pshift, nb;
 };
 
+// Small per-network constants passed BY VALUE as a __grid_constant__ kernel parameter: they are read through the
+// constant cache (LDC), not through the shared-memory pipe, which the tensor cores' operand fetches saturate.
+struct RtConsts {
+  float bias[kRtLayers * 64];   // folded conv biases
+  float headw[3 * 64];          // 1x1 head convolutions: value, policy 0, policy 1
+  float headb[4];               // their (folded) biases
+};
+
 // CP = channel parts of the epilogue (2 -> 8 epilogue warps x 32 channels, 4 -> 16 warps x 16 channels)
 template <int CP>
 struct RtCfg {
@@ -82,21 +96,19 @@ struct RtCfg {
   static constexpr int kHeadWarps = 4;
   static constexpr int kHeadThreads = 32 * kHeadWarps;
   static constexpr int kThreads = kEpiThreads + 64 + kHeadThreads;
-  static constexpr int kNF = CP / 2;                         // partial head-feature arrays (two commutative adds each)
+  static_assert(CP == 2, "the last layer's even/odd tile split assumes two channel parts");
   static constexpr int kAct = 0;
   static constexpr int kWgt = kAct + kRtActBytes;
-  static constexpr int kBias = kWgt + kRtRegions * kRtRegionBytes;
-  static constexpr int kHeadW = kBias + kRtLayers * 64 * 4;
-  static constexpr int kHeadF = kHeadW + 4 * 64 * 4;
-  static constexpr int kFc = kHeadF + kNF * kRtHeadFloats * 4;
+  static constexpr int kHeadF = kWgt + kRtRegions * kRtRegionBytes;  // float [nb][3][HW] head features
+  static constexpr int kFc = kHeadF + kRtHeadFloats * 4;
   static constexpr int kFcW = kFc + kRtFcFloats * 4;               // transposed FC weights (policy, value FC1) when they fit
   static constexpr int kBars0 = kFcW;
   static constexpr int kNumBars = kRtRegions * kRtRegionBlocks + kRtRegions + 2 * kRtMaxH + 2;
-  static constexpr int kFixed = kBars0 + kNumBars * 8 + 16;         // everything but the FC weights
-  static constexpr int kFcWFloats = (232448 - kFixed) / 4;          // what is left of the 227 KB
+  static constexpr int kFixed = kBars0 + kNumBars * 8 + 32;         // everything but the FC weights
+  static constexpr int kFcWFloats = (CARO_RT_SMEM_LIMIT - kFixed) / 4;  // what is left of the budget
   static constexpr int kBars = kFcW + kFcWFloats * 4;
-  static constexpr int kTotal = kBars + kNumBars * 8 + 16;
-  static_assert(kFixed <= 232448 && kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+  static constexpr int kTotal = kBars + kNumBars * 8 + 32;
+  static_assert(kFixed <= CARO_RT_SMEM_LIMIT && kTotal <= CARO_RT_SMEM_LIMIT, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
 #define TMEM_LD8(addr, r)                                                                    \
@@ -129,24 +141,19 @@ __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t w) { return make_flo
 // bias + LeakyReLU of the 1x1 head convolutions in place, then every (board, output) dot product in parallel with
 // the transposed FC weights read from shared memory (or from global memory when the board is too large for them
 // to fit), then value FC2 + tanh and the softmax over ALL actions, one warp per board.
-template <int TEAM, int BAR, int NF>
+template <int TEAM, int BAR>
 __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s, float* fc_s,
-                                      const float* headw_s, const float* __restrict__ blob, const BlobLayout& L,
-                                      const float* polw, const float* valw, float* __restrict__ probs, float* __restrict__ values) {
+                                      float hb0, float hb1, float hb2, const float* fcv, const float* polw, const float* valw,
+                                      float* __restrict__ probs, float* __restrict__ values) {
+  // fcv (shared memory): value FC1 bias [20], value FC2 weights [20], value FC2 bias [1], policy FC bias [A]
   const int HW = gm.H * gm.W, A = gm.A;
   const int per_board = 20 + A;
   float* hid = fc_s;  // [nb][20] value hidden units, logits behind them
   float* logit = fc_s + gm.nb * 20;
 #pragma unroll 1
-  for (int i = ttid; i < nvalid * 3 * HW; i += TEAM) {
-    float v = headf_s[i];
-#pragma unroll
-    for (int k = 1; k < NF; ++k) {
-      v += headf_s[i + k * kRtHeadFloats];
-      headf_s[i + k * kRtHeadFloats] = 0.0f;
-    }
-    const int ch = (i / HW) % 3;
-    headf_s[i] = lrelu_tc(v + headw_s[192 + ch]);
+  for (int b = 0; b < nvalid; ++b) {  // bias + LeakyReLU of the 1x1 head convolutions, in place
+    float* fb = headf_s + (size_t)b * 3 * HW;
+    for (int i = ttid; i < 3 * HW; i += TEAM) fb[i] = lrelu_tc(fb[i] + (i < HW ? hb0 : (i < 2 * HW ? hb1 : hb2)));
   }
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
 #pragma unroll 1
@@ -169,20 +176,16 @@ __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long le
     }
     for (; c < n; ++c) a0 = fmaf(wt[(size_t)c * stride], f[c], a0);
     const float acc = (a0 + a1) + (a2 + a3);
-    if (is_val) hid[b * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + acc);
-    else logit[b * A + (i - 20)] = blob[L.pol_fc_b + (i - 20)] + acc;
+    if (is_val) hid[b * 20 + i] = lrelu_tc(fcv[i] + acc);
+    else logit[b * A + (i - 20)] = fcv[41 + (i - 20)] + acc;
   }
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
 #pragma unroll 1
-  for (int i = ttid; i < nvalid * 3 * HW; i += TEAM) headf_s[i] = 0.0f;  // re-arm the accumulation slots
-#pragma unroll 1
   for (int b = ttid >> 5; b < nvalid; b += TEAM / 32) {
     const int lane = ttid & 31;
-    if (lane == 0) {
-      float acc = blob[L.val_fc2_b];
-      for (int i = 0; i < 20; ++i) acc = fmaf(blob[L.val_fc2_w + i], hid[b * 20 + i], acc);
-      values[leaf0 + b] = tanhf(acc);
-    }
+    float part = lane < 20 ? fcv[20 + lane] * hid[b * 20 + lane] : 0.0f;  // value FC2: fixed-order butterfly sum
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) values[leaf0 + b] = tanhf(fcv[40] + part);
     const float* lrow = logit + b * A;
     float* prow = probs + (size_t)(leaf0 + b) * A;
     float mx = -INFINITY;
@@ -196,7 +199,7 @@ __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long le
 #pragma unroll 1
     for (int a = lane; a < A; a += 32) prow[a] = expf(lrow[a] - mx) / sum;
   }
-  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");  // hid / logit / slots are reused by the next group
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");  // hid / logit / features are reused by the next group
 }
 
 // The MMAs of one source tile.  POS: 0 = first board row (no out[-1]: B slot 0 is skipped, the accumulators of
@@ -242,17 +245,15 @@ __device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile,
 //   EPI(gl, y)  waits the commit after source tile min(y+1, H-1): out[y] has received all of its contributions;
 //               it rewrites act[y] in place (source tile y has been consumed by then).
 template <class R, class K>
-__global__ void __launch_bounds__(K::kThreads, 1)
+__global__ void __maxnreg__(CARO_RT_MAXREG)
 net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
-              const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
+              const __grid_constant__ RtConsts consts, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
               float* __restrict__ values, long long* __restrict__ trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + K::kAct;
   uint8_t* wgt = smem + K::kWgt;
-  float* bias_s = reinterpret_cast<float*>(smem + K::kBias);
-  float* headw_s = reinterpret_cast<float*>(smem + K::kHeadW);
   float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
   float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [regions][6] weight block landed
@@ -273,17 +274,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < kRtActBytes / 16; i += K::kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < kRtLayers * 64; i += K::kThreads) bias_s[i] = bias_g[i];
-  for (int i = tid; i < K::kNF * kRtHeadFloats; i += K::kThreads) headf_s[i] = 0.0f;
-  for (int i = tid; i < 64; i += K::kThreads) {
-    headw_s[i] = blob[L.val_conv_w + i];
-    headw_s[64 + i] = blob[L.pol_conv_w + i];
-    headw_s[128 + i] = blob[L.pol_conv_w + 64 + i];
-  }
   if (tid == 0) {
-    headw_s[192] = blob[L.val_conv_b];
-    headw_s[193] = blob[L.pol_conv_b];
-    headw_s[194] = blob[L.pol_conv_b + 1];
     for (int s = 0; s < kRtRegions * kRtRegionBlocks; ++s) mbar_init(bar_full + s, 1);
     for (int s = 0; s < kRtRegions; ++s) mbar_init(bar_empty + s, 1);
     for (int t = 0; t < kRtMaxH; ++t) {
@@ -311,22 +302,36 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     // group of a CTA is left to the epilogue warps (idle by then, and many more threads) ==========================
     const int htid = tid - K::kHeadWarp * 32;
     const int HW = gm.H * gm.W;
+    float* fcv = reinterpret_cast<float*>(smem + K::kFcW);  // small head vectors: FC1 bias, FC2 weights + bias, policy bias
+    for (int i = htid; i < 41 + gm.A; i += K::kHeadThreads)
+      fcv[i] = i < 20 ? blob[L.val_fc1_b + i] : i < 40 ? blob[L.val_fc2_w + i - 20] : i == 40 ? blob[L.val_fc2_b] : blob[L.pol_fc_b + i - 41];
+    const int fcv_floats = (41 + gm.A + 3) & ~3;
     const int fcw_floats = HW * (2 * gm.A + 20);
     const float* polw = pol_fc_t;
     const float* valw = val_fc1_t;
-    if (fcw_floats <= K::kFcWFloats) {  // both transposed matrices are contiguous in global memory (net_tc.cu pack)
-      float* fcw_s = reinterpret_cast<float*>(smem + K::kFcW);
+    if (fcv_floats + fcw_floats <= K::kFcWFloats) {  // both transposed matrices are contiguous in global memory (net_tc.cu pack)
+      float* fcw_s = fcv + fcv_floats;
       for (int i = htid; i < fcw_floats; i += K::kHeadThreads) fcw_s[i] = pol_fc_t[i];
-      asm volatile("bar.sync 2, %0;" ::"n"(K::kHeadThreads) : "memory");
       polw = fcw_s;
       valw = fcw_s + 2 * HW * gm.A;
     }
-    for (int gi = 0; gi < my_groups; ++gi) {
+    asm volatile("bar.sync 2, %0;" ::"n"(K::kHeadThreads) : "memory");
+    for (int gi = 0; gi + 1 < my_groups; ++gi) {
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const int nvalid = (int)min((long long)nb, count - leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
-      rt_heads<K::kHeadThreads, 2, K::kNF>(gm, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, polw, valw, probs, values);
+      rt_heads<K::kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, fc_s, consts.headb[0], consts.headb[1], consts.headb[2], fcv, polw,
+                                   valw, probs, values);
       mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
+      if (htid == 0) TC_TRACE(5, gi);
+    }
+    {  // the last group of this CTA: nothing is left to overlap with, the (idle) epilogue warps join in
+      const int gi = my_groups - 1;
+      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
+      const int nvalid = (int)min((long long)nb, count - leaf0);
+      mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
+      rt_heads<K::kEpiThreads + K::kHeadThreads, 3>(gm, nvalid, leaf0, K::kEpiThreads + htid, headf_s, fc_s, consts.headb[0],
+                                                    consts.headb[1], consts.headb[2], fcv, polw, valw, probs, values);
       if (htid == 0) TC_TRACE(5, gi);
     }
   } else if (warp == K::kLoadWarp) {
@@ -427,18 +432,17 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     }
   } else {
     // ========================================= epilogue warps =========================================
-    constexpr int CH = K::kCH;
     const int quarter = warp & 3, cp = warp >> 2;
     const int row = quarter * 32 + (tid & 31);              // lane of the tile = TMEM lane
     const int bidx = row >> gm.pshift, col = row & (gm.pitch - 1);
     const bool real = col < gm.W;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int HW = gm.H * gm.W;
-    float* featc = headf_s + (cp >> 1) * kRtHeadFloats;     // two commutative contributions per slot and array
     const bool dbg_skip_epilogue = trace != nullptr && trace[7999] == 1;
 
-    auto write_inputs = [&](int y, long long leaf0) {
-      if (cp == 0) {
+    // `writer`: the warp set that stores the planes (the one that last read this tile's activations)
+    auto write_inputs = [&](int y, long long leaf0, int writer) {
+      if (cp == writer) {
         uint32_t lo = 0u;
         const long long leaf = leaf0 + bidx;
         if (real && leaf < count) {
@@ -456,42 +460,26 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       mbar_arrive(bar_act + y);
     };
 
-    // One tile of one layer.  HAS_RES: the layer has a residual input (all but conv_in); LAST: the tower's last
-    // layer feeds the 1x1 head convolutions instead of the next layer.
-    auto epilogue_tile = [&](auto has_res_c, auto last_c, int gi, int layer, int gl, int y, bool more, long long next_leaf0) {
+    // Loads the accumulator, bias, LeakyReLU and (HAS_RES) the residual hi (bf16, shared memory) + lo (e5m2, TMEM)
+    // of 32 channels [c0, c0+32) of tile y into v[16] (pairs).
+    auto load_values = [&](auto has_res_c, int layer, int y, int c0, float2* v, uint8_t* arow) {
       constexpr bool HAS_RES = decltype(has_res_c)::value;
-      constexpr bool LAST = decltype(last_c)::value;
-      mbar_wait(bar_acc + min(y + 1, H - 1), (uint32_t)gl & 1u);
-      __syncwarp();
-      tc_fence_after();
-      if (tid == 0) TC_TRACE(2, gl * 8 + y);
-      if (dbg_skip_epilogue) {  // debug (tools/net_trace.py): measure the MMA stream without the epilogue's traffic
-        tc_fence_before();
-        if (!LAST || more) mbar_arrive(bar_act + y);
-        return;
-      }
-      const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(y * 64 + cp * CH);
-      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * (CH / 4));
-      uint8_t* arow = act + (size_t)(cp * (CH / 8) * kRtActRows + kRtHalo + y * 128 + row) * 16;
-      const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64 + cp * CH);
-      uint32_t ra[CH], rl[CH / 4];
-      uint4 hv[CH / 8];
+      const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(y * 64 + c0);
+      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + c0 / 4);
+      const float4* bl4 = reinterpret_cast<const float4*>(consts.bias + layer * 64 + c0);
+      uint32_t ra[32], rl[8];
+      uint4 hv[4];
       TMEM_LD16(a_acc, ra);
-      if (CH == 32) TMEM_LD16(a_acc + 16u, (ra + 16));
+      TMEM_LD16(a_acc + 16u, (ra + 16));
       if (HAS_RES) {
-        if (CH == 32) {
-          TMEM_LD8(a_lo, rl);
-        } else {
-          TMEM_LD4(a_lo, rl);
-        }
+        TMEM_LD8(a_lo, rl);
 #pragma unroll
-        for (int c8 = 0; c8 < CH / 8; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
+        for (int c8 = 0; c8 < 4; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float2 v[CH / 2];
       const float2 slope = make_float2(kLeaky, kLeaky);
 #pragma unroll
-      for (int q = 0; q < CH / 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const float4 bq = bl4[q];
         const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4]), __uint_as_float(ra[q * 4 + 1])), make_float2(bq.x, bq.y));
         const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4 + 2]), __uint_as_float(ra[q * 4 + 3])), make_float2(bq.z, bq.w));
@@ -509,78 +497,116 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         v[q * 2] = m01;
         v[q * 2 + 1] = m23;
       }
-      if (!LAST) {
-        const float2 minus1 = make_float2(-1.0f, -1.0f);
-#pragma unroll
-        for (int c8 = 0; c8 < CH / 8; ++c8) {
-          uint32_t packed[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 vv = v[c8 * 4 + j];
-            const __nv_bfloat162 h = __floats2bfloat162_rn(vv.x, vv.y);
-            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
-            packed[j] = real ? hw : 0u;
-            v[c8 * 4 + j] = __ffma2_rn(bf16x2_to_float2(hw), minus1, vv);  // lo part
-          }
-          *reinterpret_cast<uint4*>(arow + (size_t)c8 * kRtChunkBytes) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
-#pragma unroll
-        for (int q = 0; q < CH / 4; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
-        if (CH == 32) {
-          TMEM_ST8(a_lo, rl);
-        } else {
-          TMEM_ST4(a_lo, rl);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_act + y);
-        if (tid == 0) TC_TRACE(3, gl * 8 + y);
-      } else {
-        // 1x1 head convolutions on the fp32 values: this thread holds CH of the 64 channels
-        const float4* hw4 = reinterpret_cast<const float4*>(headw_s + cp * CH);
-        float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
-#pragma unroll
-        for (int q = 0; q < CH / 4; ++q) {
-          const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
-          const float2 a = v[q * 2], b = v[q * 2 + 1];
-          av = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(b.x, w0.z, fmaf(b.y, w0.w, av))));
-          ap0 = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(b.x, w1.z, fmaf(b.y, w1.w, ap0))));
-          ap1 = fmaf(a.x, w2.x, fmaf(a.y, w2.y, fmaf(b.x, w2.z, fmaf(b.y, w2.w, ap1))));
-        }
-        if (gi > 0 && y == 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // slots re-zeroed by the head warps
-        if (real) {
-          const int cell = y * gm.W + col;
-          atomicAdd(&featc[(bidx * 3 + 0) * HW + cell], av);
-          atomicAdd(&featc[(bidx * 3 + 1) * HW + cell], ap0);
-          atomicAdd(&featc[(bidx * 3 + 2) * HW + cell], ap1);
-        }
-        // source tile y of the last layer has been consumed (its commit precedes the one waited for above):
-        // the next group's input planes can go in right away
-        tc_fence_before();
-        if (more) write_inputs(y, next_leaf0);
-        if (tid == 0) TC_TRACE(3, gl * 8 + y);
-      }
     };
 
-    for (int y = 0; y < H; ++y) write_inputs(y, (long long)blockIdx.x * nb);
+    // One tile of one layer but the last: every warp handles its 32 channels of the tile's 128 rows and rewrites
+    // the activations in place (bf16 hi -> shared memory, e5m2 lo -> TMEM).
+    auto epilogue_tile = [&](auto has_res_c, int layer, int gl, int y) {
+      mbar_wait(bar_acc + min(y + 1, H - 1), (uint32_t)gl & 1u);
+      __syncwarp();
+      tc_fence_after();
+      if (tid == 0) TC_TRACE(2, gl * 8 + y);
+      if (dbg_skip_epilogue) {  // debug (tools/net_trace.py): measure the MMA stream without the epilogue's traffic
+        tc_fence_before();
+        mbar_arrive(bar_act + y);
+        return;
+      }
+      uint8_t* arow = act + (size_t)(cp * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
+      float2 v[16];
+      load_values(has_res_c, layer, y, cp * 32, v, arow);
+      const float2 minus1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 vv = v[c8 * 4 + j];
+          const __nv_bfloat162 h = __floats2bfloat162_rn(vv.x, vv.y);
+          const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+          packed[j] = real ? hw : 0u;
+          v[c8 * 4 + j] = __ffma2_rn(bf16x2_to_float2(hw), minus1, vv);  // lo part
+        }
+        *reinterpret_cast<uint4*>(arow + (size_t)c8 * kRtChunkBytes) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      uint32_t rl[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
+      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * 8);
+      TMEM_ST8(a_lo, rl);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_act + y);
+      if (tid == 0) TC_TRACE(3, gl * 8 + y);
+    };
+
+    // One tile of the last layer: its output only feeds the 1x1 head convolutions (64 channels -> 3 features per
+    // cell).  Warp set cp takes the tiles with y % 2 == cp and all 64 channels of its rows, so that every feature
+    // slot receives ONE plain store (no atomics, no zeroing, a fixed summation order); the other set only passes
+    // the barrier on.  The same set then writes the next group's input planes into the tile it has just read.
+    auto last_tile = [&](int gi, int gl, int y, bool more, long long next_leaf0) {
+      mbar_wait(bar_acc + min(y + 1, H - 1), (uint32_t)gl & 1u);
+      __syncwarp();
+      tc_fence_after();
+      if (tid == 0) TC_TRACE(2, gl * 8 + y);
+      if (!dbg_skip_epilogue && (y & 1) == cp) {
+        float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint8_t* arow = act + (size_t)(hh * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
+          float2 v[16];
+          load_values(std::true_type{}, kRtLayers - 1, y, hh * 32, v, arow);
+          const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
+            const float2 a = v[q * 2], b = v[q * 2 + 1];
+            av = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(b.x, w0.z, fmaf(b.y, w0.w, av))));
+            ap0 = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(b.x, w1.z, fmaf(b.y, w1.w, ap0))));
+            ap1 = fmaf(a.x, w2.x, fmaf(a.y, w2.y, fmaf(b.x, w2.z, fmaf(b.y, w2.w, ap1))));
+          }
+        }
+        if (real) {
+          const int cell = y * gm.W + col;
+          headf_s[(bidx * 3 + 0) * HW + cell] = av;
+          headf_s[(bidx * 3 + 1) * HW + cell] = ap0;
+          headf_s[(bidx * 3 + 2) * HW + cell] = ap1;
+        }
+      }
+      tc_fence_before();
+      if (more) write_inputs(y, next_leaf0, y & 1);  // by the set that just read this tile's residual
+      if (tid == 0) TC_TRACE(3, gl * 8 + y);
+    };
+
+    for (int y = 0; y < H; ++y) write_inputs(y, (long long)blockIdx.x * nb, 0);
     for (int gi = 0; gi < my_groups; ++gi) {
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const bool more = gi + 1 < my_groups;
       const long long next_leaf0 = (blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb;
       const int gl0 = gi * kRtLayers;
 #pragma unroll 1
-      for (int y = 0; y < H; ++y) epilogue_tile(std::false_type{}, std::false_type{}, gi, 0, gl0, y, more, next_leaf0);
+      for (int y = 0; y < H; ++y) epilogue_tile(std::false_type{}, 0, gl0, y);
 #pragma unroll 1
       for (int layer = 1; layer < kRtLayers - 1; ++layer) {
 #pragma unroll 1
-        for (int y = 0; y < H; ++y) epilogue_tile(std::true_type{}, std::false_type{}, gi, layer, gl0 + layer, y, more, next_leaf0);
+        for (int y = 0; y < H; ++y) epilogue_tile(std::true_type{}, layer, gl0 + layer, y);
       }
+      if (gi > 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // the previous group's features have been consumed
 #pragma unroll 1
-      for (int y = 0; y < H; ++y)
-        epilogue_tile(std::true_type{}, std::true_type{}, gi, kRtLayers - 1, gl0 + kRtLayers - 1, y, more, next_leaf0);
+      for (int y = 0; y < H; ++y) last_tile(gi, gl0 + kRtLayers - 1, y, more, next_leaf0);
       mbar_arrive(bar_feat + 0);  // this thread's head features are in place (release) -> head warps
       if (tid == 0) TC_TRACE(4, gi);
+      if (!more) {  // join the head warps for the heads of the last group
+        mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
+        const int nvalid = (int)min((long long)nb, count - leaf0);
+        const float* fcv = reinterpret_cast<const float*>(smem + K::kFcW);  // staged by the head warps (same rule as there)
+        const int fcv_floats = (41 + gm.A + 3) & ~3;
+        const bool staged = fcv_floats + HW * (2 * gm.A + 20) <= K::kFcWFloats;
+        const float* polw = staged ? fcv + fcv_floats : pol_fc_t;
+        const float* valw = staged ? fcv + fcv_floats + 2 * HW * gm.A : val_fc1_t;
+        rt_heads<K::kEpiThreads + K::kHeadThreads, 3>(gm, nvalid, leaf0, tid, headf_s, fc_s, consts.headb[0], consts.headb[1],
+                                                      consts.headb[2], fcv, polw, valw, probs, values);
+      }
     }
   }
 
@@ -629,6 +655,20 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
             for (int c = 0; c < 16; ++c)
               put(kRtRegionBlocks + l * 12 + kx * 4 + kk, j, co, c,
                   h[L.conv_w[l] + ((size_t)(co * 64 + kk * 16 + c) * 9 + (2 - j) * 3 + kx)]);
+  static_assert(sizeof(RtConsts) <= sizeof(net->h_rt_consts), "caro_net::h_rt_consts is too small");
+  RtConsts* hc = reinterpret_cast<RtConsts*>(net->h_rt_consts);
+  for (int co = 0; co < 64; ++co) hc->bias[co] = h[L.conv_in_b + co];
+  for (int l = 0; l < kBlocks; ++l)
+    for (int co = 0; co < 64; ++co) hc->bias[(l + 1) * 64 + co] = h[L.conv_b[l] + co];
+  for (int c = 0; c < 64; ++c) {
+    hc->headw[c] = h[L.val_conv_w + c];
+    hc->headw[64 + c] = h[L.pol_conv_w + c];
+    hc->headw[128 + c] = h[L.pol_conv_w + 64 + c];
+  }
+  hc->headb[0] = h[L.val_conv_b];
+  hc->headb[1] = h[L.pol_conv_b];
+  hc->headb[2] = h[L.pol_conv_b + 1];
+  hc->headb[3] = 0.0f;
   cudaError_t ce = cudaSuccess;
   if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
@@ -658,10 +698,11 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;
-  const unsigned grid = (unsigned)(max_groups < net->sm_count ? max_groups : net->sm_count);
+  const int ctas = net->grid_limit > 0 && net->grid_limit < net->sm_count ? net->grid_limit : net->sm_count;
+  const unsigned grid = (unsigned)(max_groups < ctas ? max_groups : ctas);
   net_rt_kernel<R, RtK><<<grid, RtK::kThreads, RtK::kTotal, st>>>(
       rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_weights,
-      net->d_tc_bias, net->d_blob, net->layout, net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs,
+      *reinterpret_cast<const RtConsts*>(net->h_rt_consts), net->d_blob, net->layout, net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs,
       values, (long long*)net->d_trace);
   return caro_check_launch("net_rt_kernel");
 }

@@ -148,6 +148,10 @@ class DeviceNet:
                                                      impl, torch.cuda.current_stream().cuda_stream))
         return probs, values
 
+    def set_grid_limit(self, ctas: int) -> None:
+        """Limit the persistent tower to ``ctas`` SMs (0 = all), leaving the rest to concurrent tree kernels."""
+        _cabi.check(_cabi.lib().caro_net_set_grid_limit(self.handle, int(ctas)))
+
     def forward_states(self, states, players, impl: int = None):
         d_boards = torch.from_numpy(self.game.boards_from_states(states).view(np.int64)).cuda()
         d_who = torch.tensor(list(players), dtype=torch.uint8, device="cuda")

@@ -97,6 +97,11 @@ void caro_net_destroy(caro_net* net);
  * (tag, clock64) pairs -- the pipeline timeline used to tune the kernel; NULL switches tracing off. */
 int caro_net_set_trace(caro_net* net, void* d_trace);
 
+/* The tensor-core tower is a persistent kernel with one CTA per SM that owns the SM's whole shared memory.
+ * Limiting it to `ctas` SMs (0 = all) leaves the remaining SMs to the tree kernels of the other half-batch, which
+ * the self-play pipeline runs on side streams underneath the network pass (caro_engine_play_multi). */
+int caro_net_set_grid_limit(caro_net* net, int ctas);
+
 /* Forward pass over a compact batch of leaf positions given as boards + side to move.
  *   d_count : device int32 holding the number of valid leaves (<= max_count); read on device, so
  *             no host synchronisation is needed between search steps.  May be NULL, then
