@@ -189,7 +189,8 @@ def engine_arm(args):
     G = args.games
     # the game batch is split in two halves that are software-pipelined against each other (one half's tree kernels
     # run on a side stream underneath the other half's network pass); --no-pipeline keeps one engine, one stream
-    halves = 1 if args.no_pipeline else 2
+    halves = 1 if args.no_pipeline else args.parts
+    assert G % halves == 0, "--games must be divisible by --parts"
     engs = [SelfPlayEngine(game, G // halves, trees_per_game=1, max_batch=SIMS_BATCH, node_capacity=args.node_capacity,
                            replay_capacity=1 << 19, seed=1234 + 16 * rank + h) for h in range(halves)]
     stream = torch.cuda.current_stream()
@@ -201,8 +202,8 @@ def engine_arm(args):
         torch.cuda.synchronize()
 
     def play(n, count=SIMS_COUNT):
-        if halves == 2:
-            engs[0].play_pair(engs[1], dnet, moves=n, count=count, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
+        if halves >= 2:
+            SelfPlayEngine.play_multi(engs, dnet, moves=n, count=count, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
         else:
             engs[0].play(dnet, dnet, moves=n, count=count, batch=SIMS_BATCH, tau_plies=TAU_PLIES, auto_restart=True)
 
@@ -290,7 +291,7 @@ def engine_arm(args):
     if rank == 0:
         peaks = measured_peaks()
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "net_tc_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "net_traffic.json")
         if os.path.exists(tpath):  # dram__bytes_read + dram__bytes_write of one `ncu --set full` capture of this kernel
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
@@ -306,7 +307,7 @@ def engine_arm(args):
             "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, %d concurrent games per GPU, "
                                    "random-init 5x64 residual net (bf16 tcgen05, fp32 accumulate), tau=1 for 10 plies" % G,
                        "games_per_gpu": G, "sims_per_move": SIMS_COUNT * SIMS_BATCH, "node_capacity": args.node_capacity,
-                       "pipeline": "2 half-batches, tree kernels on side streams under the other half's network pass" if halves == 2 else "single stream",
+                       "pipeline": ("%d part-batches of %d games, each part's tree kernels on its own side stream under the other parts' network passes" % (halves, G // halves)) if halves >= 2 else "single stream",
                        "cache": "tree arenas %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
                                 % workspace_gb},
             "games_per_sec": games / sec, "plies_per_sec": plies / sec, "descents_per_sec": desc / sec,
@@ -345,6 +346,7 @@ def main():
     ap.add_argument("--cpu-plies", type=int, default=20)
     ap.add_argument("--preroll", type=int, default=30)
     ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--parts", type=int, default=2, help="software-pipelined parts the game batch is split into")
     ap.add_argument("--net-sms", type=int, default=0, help="SMs the network kernel may occupy (0 = all); the rest serve the tree kernels")
     ap.add_argument("--profile-level", type=int, default=1, help="1: CUDA events around the network kernel only, 2: all phases")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -71,7 +71,8 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise CaroError("%s is missing: run `python __graft_entry__.py` (build()) first; "
                             "there is no CPU fallback" % LIB_PATH)
-        handle = C.CDLL(LIB_PATH)
+        # CARO_B200_LIB: developer switch for A/B runs of two builds on the same GPU box (tools/ only)
+        handle = C.CDLL(os.environ.get("CARO_B200_LIB") or LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = res

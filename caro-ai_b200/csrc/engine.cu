@@ -502,9 +502,10 @@ int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int 
 static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batch, int tau_plies, int auto_restart,
                      int first_player, int net_impl, cudaStream_t* s_side, cudaStream_t s_net) {
   int rc = CARO_OK;
-  // CARO_SPLIT_NET=1 (experiment): every part keeps its network passes on its own side stream, so the parts are
-  // completely independent chains and the tail of one part's network kernel overlaps the head of the other's
-  static const bool split = getenv("CARO_SPLIT_NET") && getenv("CARO_SPLIT_NET")[0] == '1';
+  // Every part keeps its network passes on its own side stream: the parts are independent chains, and the tail of
+  // one part's network kernel (CTAs that ran out of groups) overlaps the head of the next part's.  CARO_SPLIT_NET=0
+  // restores the older scheme (all network passes on one stream, event hand-offs to the tree streams).
+  static const bool split = !(getenv("CARO_SPLIT_NET") && getenv("CARO_SPLIT_NET")[0] == '0');
   for (int i = 0; i < count && rc == CARO_OK; ++i)
     for (int h = 0; h < n && rc == CARO_OK; ++h)
       rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);

@@ -372,6 +372,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     bool pre_waited = false;
     for (int gl = 0; gl < total_layers; ++gl) {
       const uint32_t par = (uint32_t)gl & 1u;
+      if (elected) TC_TRACE(6, gl * 2);      // layer iteration entered
       const bool first = layer == 0;
       const uint64_t rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
       uint64_t* full0 = bar_full + reg * kRtRegionBlocks;
@@ -396,6 +397,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           mbar_wait(bar_act + 0, par);
           mbar_wait(bar_act + 1, par);
         }
+        if (elected && y == 0) TC_TRACE(6, gl * 2 + 1);  // first tile: barriers passed
         tc_fence_after();  // orders this tile's MMAs after the barrier observations (also the early ones)
         if (elected) TC_TRACE(0, gl * 8 + y);
         const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(y * 128);

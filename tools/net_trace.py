@@ -43,7 +43,7 @@ def main():
     limit = int(sys.argv[2]) if len(sys.argv) > 2 else 140
     for clk, kind, idx in ev[:limit]:
         if kind == 6:
-            print("%8d  %-14s gl=%d mw=%d" % (clk - t0, names[kind], idx // 2, idx % 2))
+            print("%8d  %-14s gl=%d %s" % (clk - t0, "layer_enter" if idx % 2 == 0 else "bars_passed", idx // 2, ""))
         elif kind < 4:
             print("%8d  %-14s gl=%d t=%d" % (clk - t0, names[kind], idx // div, idx % div))
         else:
