@@ -277,3 +277,83 @@ def test_checkpoint_format_roundtrip(torch_cuda, tmp_path, golden_net):
     save_checkpoint(net, path)
     sd = torch.load(path, map_location="cpu")
     assert list(sd.keys()) == list(case["keys"].keys())
+
+
+def _random_net(game, seed=0):
+    import torch
+    from caro_ai_b200.model import Net
+    torch.manual_seed(seed)
+    net = Net(game.obs_shape, game.action_space)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    return net.eval()
+
+
+def test_net_row_tiled_kernel_geometries_and_ragged_counts(torch_cuda):
+    """The row-tiled tower (net_rt.cu, impl 0 for boards <= 6x7) on every geometry class it serves -- pitch 4 (3x3),
+    pitch 8 (4x4, 5x5, 6x6: the last one reads its FC weights from global memory), Connect4 -- and on leaf counts that
+    leave the last 16/32-board group ragged or spill into a second pass of the persistent CTAs: 1e-3 vs PyTorch fp32,
+    agreement with the tap-per-MMA kernel (impl 3), and bit-identical results from run to run (no atomics)."""
+    import torch
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(11)
+    for game, counts in [(ConnectFour(), (1, 15, 16, 17, 2400)), (TicTacToe(3, 3), (1, 31, 33, 4800)),
+                         (TicTacToe(4, 3), (5, 40)), (TicTacToe(5, 4), (7, 50)), (TicTacToe(6, 4), (3, 37))]:
+        net = _random_net(game)
+        og = oracle_for(game)
+        cells = game.obs_shape[1] * game.obs_shape[2]
+        dn = DeviceNet(net, game)
+        for count in counts:
+            base = [random_position(og, rng, int(rng.integers(0, max(1, cells - 3)))) for _ in range(min(count, 64))]
+            pos = [base[i % len(base)] for i in range(count)]
+            states, players = [p[0] for p in pos], [p[1] for p in pos]
+            ref_p, ref_v = _reference_outputs(game, net, states[:len(base)], players[:len(base)])
+            p0, v0 = dn.forward_states(states, players, impl=0)
+            p0b, v0b = dn.forward_states(states, players, impl=0)
+            p3, v3 = dn.forward_states(states, players, impl=3)
+            torch.cuda.synchronize()
+            assert torch.equal(p0, p0b) and torch.equal(v0, v0b), (type(game).__name__, count)
+            p0, v0, p3, v3 = p0.cpu().numpy(), v0.cpu().numpy(), p3.cpu().numpy(), v3.cpu().numpy()
+            assert np.isfinite(p0).all() and np.isfinite(v0).all()
+            n = len(base)
+            for i in range(0, count, n):  # every copy of the base positions, wherever it landed in the groups
+                m = min(n, count - i)
+                assert np.abs(p0[i:i + m] - ref_p[:m]).max() < 1e-3, (type(game).__name__, game.obs_shape, count, i)
+                assert np.abs(v0[i:i + m] - ref_v[:m]).max() < 1e-3, (type(game).__name__, game.obs_shape, count, i)
+            assert np.abs(p0 - p3).max() < 2e-3 and np.abs(v0 - v3).max() < 2e-3
+        dn.close()
+
+
+def test_net_row_tiled_kernel_device_count(torch_cuda):
+    """caro_net_forward reads the leaf count on the device (d_count <= max_count): rows beyond it stay untouched."""
+    import ctypes as C
+    import torch
+    from caro_ai_b200 import _cabi
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import DeviceNet
+    game = ConnectFour()
+    net = _random_net(game, 1)
+    dn = DeviceNet(net, game)
+    og = oracle_for(game)
+    rng = np.random.default_rng(5)
+    pos = [random_position(og, rng, int(rng.integers(0, 30))) for _ in range(100)]
+    states, players = [p[0] for p in pos], [p[1] for p in pos]
+    d_boards = torch.from_numpy(game.boards_from_states(states).view(np.int64)).cuda()
+    d_who = torch.tensor(players, dtype=torch.uint8, device="cuda")
+    full_p, full_v = dn.forward_boards(d_boards, d_who, 100, 0)
+    probs = torch.full((100, 7), -7.0, dtype=torch.float32, device="cuda")
+    values = torch.full((100,), -7.0, dtype=torch.float32, device="cuda")
+    d_count = torch.tensor([37], dtype=torch.int32, device="cuda")
+    _cabi.check(_cabi.lib().caro_net_forward(dn.handle, game.game_kind, game.n, game.k, d_boards.data_ptr(), d_who.data_ptr(),
+                                             d_count.data_ptr(), 100, probs.data_ptr(), values.data_ptr(), 0,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(probs[:37], full_p[:37]) and torch.equal(values[:37], full_v[:37])
+    assert bool((probs[37:] == -7.0).all()) and bool((values[37:] == -7.0).all())
+    dn.close()
