@@ -505,10 +505,45 @@ static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batc
   // Every part keeps its network passes on its own side stream: the parts are independent chains, and the tail of
   // one part's network kernel (CTAs that ran out of groups) overlaps the head of the next part's.  CARO_SPLIT_NET=0
   // restores the older scheme (all network passes on one stream, event hand-offs to the tree streams).
-  static const bool split = !(getenv("CARO_SPLIT_NET") && getenv("CARO_SPLIT_NET")[0] == '0');
+  // CARO_SPLIT_NET=2: per-part network streams of LOW priority next to the part's HIGH-priority tree stream (event
+  // hand-offs), so that pending tree blocks are dispatched ahead of pending tower CTAs.
+  static const int split = getenv("CARO_SPLIT_NET") ? atoi(getenv("CARO_SPLIT_NET")) : 1;
+  static cudaStream_t s_tree_hi[8] = {nullptr}, s_net_lo[8] = {nullptr};
+  if (split == 2 && !s_tree_hi[0]) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority (numerically greatest)
+    for (int h = 0; h < 8; ++h) {
+      cudaStreamCreateWithPriority(&s_tree_hi[h], cudaStreamNonBlocking, hi);
+      cudaStreamCreateWithPriority(&s_net_lo[h], cudaStreamNonBlocking, lo);
+    }
+  }
+  if (split == 2) {  // fork the priority streams off the part streams (also inside a graph capture)
+    static cudaEvent_t ev_f[8] = {nullptr};
+    for (int h = 0; h < n; ++h) {
+      if (!ev_f[h]) cudaEventCreateWithFlags(&ev_f[h], cudaEventDisableTiming);
+      cudaEventRecord(ev_f[h], s_side[h]);
+      cudaStreamWaitEvent(s_tree_hi[h], ev_f[h], 0);
+      cudaStreamWaitEvent(s_net_lo[h], ev_f[h], 0);
+    }
+  }
   for (int i = 0; i < count && rc == CARO_OK; ++i)
-    for (int h = 0; h < n && rc == CARO_OK; ++h)
-      rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);
+    for (int h = 0; h < n && rc == CARO_OK; ++h) {
+      if (split == 2) rc = search_step(es[h], net, i, batch, net_impl, s_tree_hi[h], s_net_lo[h], 1, i + 1 < count);
+      else rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);
+    }
+  if (split == 2) {  // join back
+    static cudaEvent_t ev_j[16] = {nullptr};
+    for (int h = 0; h < n; ++h) {
+      if (!ev_j[2 * h]) {
+        cudaEventCreateWithFlags(&ev_j[2 * h], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_j[2 * h + 1], cudaEventDisableTiming);
+      }
+      cudaEventRecord(ev_j[2 * h], s_tree_hi[h]);
+      cudaEventRecord(ev_j[2 * h + 1], s_net_lo[h]);
+      cudaStreamWaitEvent(s_side[h], ev_j[2 * h], 0);
+      cudaStreamWaitEvent(s_side[h], ev_j[2 * h + 1], 0);
+    }
+  }
   for (int h = 0; h < n && rc == CARO_OK; ++h) {
     rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
     es[h]->launches += 1;

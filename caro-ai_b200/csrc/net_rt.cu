@@ -37,7 +37,9 @@
 #include "tc_common.cuh"
 
 #ifndef CARO_RT_MAXREG
-#define CARO_RT_MAXREG 112  // 448 threads x 112 = 50,176 registers: 15 K stay free for a co-resident tree-kernel block
+#define CARO_RT_MAXREG 96  // registers are allocated per SM sub-partition (16 K each): 14 warps x 96 registers leave
+                           // >= 4 K per partition, enough for the warps of a tree-kernel block to become resident
+                           // NEXT TO a tower CTA (tools/coresidency_test.py; at 112 they have to wait for it to end)
 #endif
 #ifndef CARO_RT_SMEM_LIMIT
 #define CARO_RT_SMEM_LIMIT (232448 - 1024)  // one more 1 KB block reservation fits beside this CTA on the SM
@@ -319,7 +321,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     for (int gi = 0; gi + 1 < my_groups; ++gi) {
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const int nvalid = (int)min((long long)nb, count - leaf0);
-      mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
+      mbar_wait_relaxed(bar_feat + 0, (uint32_t)gi & 1u);
       rt_heads<K::kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, fc_s, consts.headb[0], consts.headb[1], consts.headb[2], fcv, polw,
                                    valw, probs, values);
       mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
@@ -342,7 +344,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       int reg = 0, src = 0;
       uint32_t round = 0;
       for (int n = 0; n < total; ++n) {
-        if (round > 0) mbar_wait(bar_empty + reg, (round - 1u) & 1u);
+        if (round > 0) mbar_wait_relaxed(bar_empty + reg, (round - 1u) & 1u);
         const int nblk = src == 0 ? 3 : kRtRegionBlocks;  // conv_in: three real blocks, the others keep their phases in step
         for (int b = 0; b < kRtRegionBlocks; ++b) {
           uint64_t* bar = bar_full + reg * kRtRegionBlocks + b;

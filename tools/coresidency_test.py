@@ -24,7 +24,12 @@ def main():
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     torch.cuda.synchronize()
 
+    x = torch.zeros(1024, device="cuda")
+
     def tree(mb):
+        if len(sys.argv) > 1 and sys.argv[1] == "tiny":
+            x.add_(1.0)  # a 1-block elementwise kernel: can ANYTHING become resident next to the tower?
+            return
         eng.select(8, mb)
         eng.plan(8)
 
