@@ -37,6 +37,7 @@ constexpr int kTapBytes = 8 * 64 * 16;                   // 8,192: one tap of a 
 constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of conv_in (K padded to 16)
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
+constexpr int kHeadsInTowerMaxHW = 64;                    // larger boards run their FC heads in heads_kernel
 constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
 constexpr int kEpiWarps = 8;                             // warps 0-7: epilogue; TMEM lane quarter = warp & 3, column half = warp >> 2
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -84,6 +85,97 @@ using TcFast = TcCfg<4, false>;
 using TcExact = TcCfg<2, true>;
 
 
+// Large boards (Caro 15x15: 225 actions, 450 x 225 policy FC) do not run their FC heads inside the tower: two head warps
+// re-reading 405 KB of FC weights for every 2-board group made the heads, not the convolutions, the bottleneck (1.9 ms
+// per 4,096 leaves, of which ~0.3 ms tower).  The tower only exports the raw 1x1 head-convolution sums of the group
+// ([leaf][3][HW] floats) and heads_kernel below does the FC layers for 32 leaves per CTA, reading every weight once
+// per CTA from L2 and the features from shared memory.
+template <int TEAM, int BAR>
+__device__ __noinline__ void export_heads(const TcGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s,
+                                          float* __restrict__ out) {
+  const int n = nvalid * 3 * gm.H * gm.W;
+  float* dst = out + (size_t)leaf0 * 3 * gm.H * gm.W;
+#pragma unroll 1
+  for (int i = ttid; i < n; i += TEAM) {
+    dst[i] = headf_s[i];
+    headf_s[i] = 0.0f;  // re-arm the accumulation slots
+  }
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
+}
+
+constexpr int kHeadsLeaves = 32;   // leaves per CTA of heads_kernel
+constexpr int kHeadsThreads = 256;
+
+// FC heads for a batch of leaves (lib/model.py:56-72,90-93 + softmax of lib/mcts.py:216) from the exported head features.
+// Shared memory: fs[3 HW][32] activated features (leaf index fastest: the inner loops read 32 leaves of one feature as
+// eight broadcast float4), lg[32][A] logits, hid[32][20].
+__global__ void __launch_bounds__(kHeadsThreads)
+heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count, long long max_count, int HW, int A,
+             const float* __restrict__ blob, BlobLayout L, const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t,
+             float* __restrict__ probs, float* __restrict__ values) {
+  extern __shared__ __align__(16) float hs[];
+  float* fs = hs;                                 // [3 HW][32]
+  float* lg = fs + (size_t)3 * HW * kHeadsLeaves;  // [32][A]
+  float* hid = lg + (size_t)kHeadsLeaves * A;      // [32][20]
+  const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
+  const int tid = threadIdx.x;
+  const float hb[3] = {blob[L.val_conv_b], blob[L.pol_conv_b], blob[L.pol_conv_b + 1]};
+  for (long long leaf0 = (long long)blockIdx.x * kHeadsLeaves; leaf0 < count; leaf0 += (long long)gridDim.x * kHeadsLeaves) {
+    const int nvalid = (int)min((long long)kHeadsLeaves, count - leaf0);
+    const int l = tid & 31;
+    for (int k = tid >> 5; k < 3 * HW; k += kHeadsThreads / 32) {
+      float v = 0.0f;
+      if (l < nvalid) v = lrelu_tc(feat[(size_t)(leaf0 + l) * 3 * HW + k] + hb[k / HW]);
+      fs[k * kHeadsLeaves + l] = v;
+    }
+    __syncthreads();
+    for (int a = tid; a < A; a += kHeadsThreads) {  // policy FC: this thread owns action a of all 32 leaves
+      float acc[kHeadsLeaves];
+#pragma unroll
+      for (int i = 0; i < kHeadsLeaves; ++i) acc[i] = 0.0f;
+      const float4* f4 = reinterpret_cast<const float4*>(fs + (size_t)HW * kHeadsLeaves);
+#pragma unroll 2
+      for (int k = 0; k < 2 * HW; ++k) {
+        const float w = __ldg(pol_fc_t + (size_t)k * A + a);
+#pragma unroll
+        for (int q = 0; q < kHeadsLeaves / 4; ++q) {
+          const float4 f = f4[k * (kHeadsLeaves / 4) + q];
+          acc[4 * q] = fmaf(w, f.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(w, f.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(w, f.w, acc[4 * q + 3]);
+        }
+      }
+      const float b = blob[L.pol_fc_b + a];
+#pragma unroll
+      for (int i = 0; i < kHeadsLeaves; ++i) lg[i * A + a] = acc[i] + b;
+    }
+    for (int o = tid; o < kHeadsLeaves * 20; o += kHeadsThreads) {  // value FC1
+      const int ll = o & 31, i = o >> 5;
+      float a0 = 0.0f;
+      for (int c = 0; c < HW; ++c) a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsLeaves + ll], a0);
+      hid[ll * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + a0);
+    }
+    __syncthreads();
+    for (int b = tid >> 5; b < nvalid; b += kHeadsThreads / 32) {
+      const int lane = tid & 31;
+      float part = lane < 20 ? blob[L.val_fc2_w + lane] * hid[b * 20 + lane] : 0.0f;
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (lane == 0) values[leaf0 + b] = tanhf(blob[L.val_fc2_b] + part);
+      const float* lrow = lg + b * A;
+      float* prow = probs + (size_t)(leaf0 + b) * A;
+      float mx = -INFINITY;
+      for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lrow[a]);
+      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      float sum = 0.0f;
+      for (int a = lane; a < A; a += 32) sum += expf(lrow[a] - mx);
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      for (int a = lane; a < A; a += 32) prow[a] = expf(lrow[a] - mx) / sum;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------- kernel
 // Roles: warps 0-7 = epilogue (warp w owns TMEM lanes [32(w&3), +32) = rows of every tile, channels 32(w>>2)..+32),
 //        warp 8    = TMEM allocation, elected-lane MMA issue for tiles 0 and 2,
@@ -100,7 +192,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
-              float* __restrict__ values, long long* __restrict__ trace) {
+              float* __restrict__ values, float* __restrict__ headfeat_out, long long* __restrict__ trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + K::kAct;
   uint8_t* wgt = smem + K::kWgt;
@@ -171,7 +263,8 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const int nvalid = (int)min((long long)nb, count - leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
-      run_heads<kHeadThreads, 2>(gm, nb, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
+      if (headfeat_out != nullptr) export_heads<kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, headfeat_out);
+      else run_heads<kHeadThreads, 2>(gm, nb, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
       mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
       if (htid == 0) TC_TRACE(5, gi);  // heads done
     }
@@ -404,7 +497,8 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         // last group of this CTA: nothing left to overlap with, so all eight epilogue warps do the heads
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int nvalid = (int)min((long long)nb, count - leaf0);
-        run_heads<kEpiThreads, 1>(gm, nb, nvalid, leaf0, tid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
+        if (headfeat_out != nullptr) export_heads<kEpiThreads, 1>(gm, nvalid, leaf0, tid, headf_s, headfeat_out);
+        else run_heads<kEpiThreads, 1>(gm, nb, nvalid, leaf0, tid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
         if (tid == 0) TC_TRACE(5, gi);
       }
     }
@@ -470,6 +564,11 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
   for (int i = 0; i < 20; ++i)
     for (int c = 0; c < HW; ++c) polt[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
   cudaError_t ce = cudaSuccess;
+  if (HW > kHeadsInTowerMaxHW && !net->d_headfeat) {  // large boards: FC heads run in heads_kernel from exported features
+    net->headfeat_leaves = 65536;
+    ce = cudaMalloc(&net->d_headfeat, (size_t)net->headfeat_leaves * 3 * HW * sizeof(float));
+    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  }
   if (!net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
   if (ce == cudaSuccess && !net->d_tc_bias) ce = cudaMalloc(&net->d_tc_bias, bias.size() * sizeof(float));
   if (ce == cudaSuccess && !net->d_pol_fc_t) ce = cudaMalloc(&net->d_pol_fc_t, polt.size() * sizeof(float));
@@ -484,6 +583,8 @@ void caro_net_tc_free(caro_net* net) {
   if (net->d_tc_weights) cudaFree(net->d_tc_weights);
   if (net->d_tc_bias) cudaFree(net->d_tc_bias);
   if (net->d_pol_fc_t) cudaFree(net->d_pol_fc_t);
+  if (net->d_headfeat) cudaFree(net->d_headfeat);
+  net->d_headfeat = nullptr;
   net->d_tc_weights = nullptr;
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
@@ -506,11 +607,22 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   auto kern = net_tc_kernel<R, K>;
   const long long max_groups = (max_count + gm.boards_per_group - 1) / gm.boards_per_group;
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
+  const int HW = net->H * net->W;
+  float* headfeat = (net->d_headfeat != nullptr && max_count <= net->headfeat_leaves) ? net->d_headfeat : nullptr;
   kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
                                           (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values,
+                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat,
                                           (long long*)net->d_trace);
-  return caro_check_launch("net_tc_kernel");
+  int rc = caro_check_launch("net_tc_kernel");
+  if (rc == CARO_OK && headfeat != nullptr) {
+    const size_t smem = ((size_t)3 * HW * kHeadsLeaves + (size_t)kHeadsLeaves * net->A + kHeadsLeaves * 20) * sizeof(float);
+    const long long tiles = (max_count + kHeadsLeaves - 1) / kHeadsLeaves;
+    const unsigned hgrid = (unsigned)(tiles < 2 * sm_count ? tiles : 2 * sm_count);
+    heads_kernel<<<hgrid, kHeadsThreads, smem, st>>>(headfeat, d_count, (long long)max_count, HW, net->A, net->d_blob, net->layout,
+                                                     net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values);
+    rc = caro_check_launch("heads_kernel");
+  }
+  return rc;
 }
 
 // Sets the dynamic shared memory attribute of every instantiation up front (caro_net_create), so that no
@@ -520,6 +632,7 @@ int caro_net_tc_prepare() {
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFast::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }

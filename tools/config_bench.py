@@ -1,0 +1,185 @@
+"""GPU measurements of the BASELINE.json configurations other than the headline one (which is bench.py):
+
+  1  TicTacToe 3,3,3 self-play, ~30 sims/move (train.py -g 1), beside the CPU oracle port on the host
+  3  Connect4 self-play + the SGD step of the training loop (train.py:82-111) on this GPU
+  4  Caro 15,15,5 self-play, 1600 sims/move
+  5  tournament: random-init Connect4 checkpoints through the .dat format, every ordered pair, tau = 0
+
+One JSON line per configuration on stdout.  Usage: python tools/config_bench.py [1,3,4,5]"""
+import collections
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+
+from caro_ai_b200 import config as cfg
+from caro_ai_b200.engine import SelfPlayEngine
+from caro_ai_b200.game import ConnectFour, TicTacToe
+from caro_ai_b200.model import DeviceNet, Net, load_checkpoint, save_checkpoint
+from caro_ai_b200.utils import play_games_batched
+
+
+def timed_plies(eng, dn, plies, count, batch, tau):
+    """Lock-step self-play with re-seating: returns (seconds, counter deltas) over `plies` plies, CUDA-event timed."""
+    eng.play(dn, dn, moves=2, count=count, batch=batch, tau_plies=tau, auto_restart=True)
+    torch.cuda.synchronize()
+    c0 = eng.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.play(dn, dn, moves=plies, count=count, batch=batch, tau_plies=tau, auto_restart=True)
+    e1.record()
+    torch.cuda.synchronize()
+    c1 = eng.counters()
+    assert c1["errors"] == 0
+    return e0.elapsed_time(e1) / 1e3, {k: c1[k] - c0[k] for k in c1}
+
+
+def config1():
+    game = TicTacToe(3, 3)
+    torch.manual_seed(0)
+    net = Net(game.obs_shape, game.action_space).eval()
+    dn = DeviceNet(net, game)
+    out = {"config": 1, "workload": "TicTacToe 3,3,3 self-play, random-init 5x64 net, tau=1 for 10 plies, 4096 concurrent games"}
+    for count, batch in ((4, 8), (30, 1)):
+        eng = SelfPlayEngine(game, 4096, max_batch=batch, node_capacity=2048, seed=1)
+        sec, d = timed_plies(eng, dn, 60, count, batch, cfg.STEPS_BEFORE_TAU_0)
+        out["search_batch(%d,%d)" % (count, batch)] = {"games_per_sec": d["games"] / sec, "leaf_evals_per_sec": d["leaf_evals"] / sec,
+                                                       "plies_per_sec": d["plies"] / sec}
+        eng.close()
+    # CPU oracle port of the reference on one host core: 20 games with search_batch(4, 8)
+    from oracle.games import MNKOracle
+    from oracle.mcts import OracleMCTS
+    from oracle.net import OracleNet
+    og = MNKOracle(3, 3)
+    torch.set_num_threads(1)
+    onet = OracleNet(og.obs_shape, og.action_space)
+    rows = {"n": 0}
+    fwd = onet.forward
+
+    def counting(x):
+        rows["n"] += int(x.shape[0])
+        return fwd(x)
+
+    onet.forward = counting
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    games = 0
+    while games < 20:
+        state, cur, tree, ply = og.initial_state, int(np.random.choice(2)), OracleMCTS(og), 0
+        while True:
+            tree.search_batch(4, 8, state, cur, onet)
+            pi, _ = tree.get_policy_value(state, tau=1 if ply < cfg.STEPS_BEFORE_TAU_0 else 0)
+            a = int(np.random.choice(og.action_space, p=pi))
+            state, won = og.move(state, a, cur)
+            cur, ply = 1 - cur, ply + 1
+            if won or not og.possible_moves(state):
+                break
+        games += 1
+    dt = time.perf_counter() - t0
+    out["cpu_port_search_batch(4,8)"] = {"games_per_sec": games / dt, "leaf_evals_per_sec": rows["n"] / dt, "cores": 1,
+                                         "sample": "20 games of the oracle port, 1 torch thread"}
+    dn.close()
+    return out
+
+
+def config3():
+    """One outer step of the training loop at train.py's own search setting (10 x 8) plus the 10 SGD rounds."""
+    import torch.optim as optim
+    from caro_ai_b200 import train as T
+    game = ConnectFour()
+    torch.manual_seed(0)
+    device = torch.device("cuda", torch.cuda.current_device())
+    net = Net(game.obs_shape, game.action_space).to(device)
+    best = DeviceNet(net, game)
+    replay = collections.deque(maxlen=1 << 20)
+
+    class _TB:
+        def track(self, *a, **k):
+            pass
+
+    games = 4096
+    t0 = time.perf_counter()
+    stats, dt = T.self_play(game, replay, best, games, _TB(), 0, seed=1)
+    torch.cuda.synchronize()
+    sp = time.perf_counter() - t0
+    opt = optim.SGD(net.parameters(), lr=cfg.LEARNING_RATE, momentum=0.9)
+    T.train_neural_net(game, net, replay, opt, _TB(), 1, device)  # warm-up (cuDNN autotune)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    losses = T.train_neural_net(game, net, replay, opt, _TB(), 2, device)
+    torch.cuda.synchronize()
+    sgd = time.perf_counter() - t1
+    n_param = sum(p.numel() for p in net.parameters())
+    best.close()
+    return {"config": 3, "workload": "Connect4 training step on one GPU: %d self-play games at search_batch(%d,%d) + %d SGD rounds of %d "
+                                     "(plain PyTorch autograd); with N ranks: one flattened NCCL all-reduce of %d fp32 gradients per round"
+                                     % (games, cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.TRAIN_ROUNDS, cfg.BATCH_SIZE, n_param),
+            "self_play_games_per_sec": games / sp, "self_play_leaf_evals_per_sec": stats["leaf_evals"] / sp,
+            "replay_positions": len(replay), "sgd_ms_per_round": 1e3 * sgd / cfg.TRAIN_ROUNDS, "loss_total": losses[0],
+            "gradient_bytes": 4 * n_param}
+
+
+def config4(games=128):
+    game = TicTacToe(15, 5)
+    torch.manual_seed(0)
+    dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
+    eng = SelfPlayEngine(game, games, max_batch=8, node_capacity=16384, seed=1)
+    sec, d = timed_plies(eng, dn, 4, 200, 8, cfg.STEPS_BEFORE_TAU_0)
+    eng.close()
+    dn.close()
+    return {"config": 4, "workload": "Caro 15,15,5 self-play, search_batch(200,8) = 1600 sims/move, %d concurrent games, reference-shape 5x64 "
+                                     "net (tap-per-MMA tcgen05 kernel: boards larger than 6x7), 4 plies after 2 warm-up plies" % games,
+            "leaf_evals_per_sec": d["leaf_evals"] / sec, "plies_per_sec": d["plies"] / sec, "descents_per_sec": d["descents"] / sec,
+            "tflops_useful": d["leaf_evals"] * 83760340 / sec / 1e12}
+
+
+def config5():
+    game = ConnectFour()
+    tmp = tempfile.mkdtemp()
+    paths = []
+    for i in range(4):
+        torch.manual_seed(100 + i)
+        p = os.path.join(tmp, "net_%d.dat" % i)
+        save_checkpoint(Net(game.obs_shape, game.action_space), p)
+        paths.append(p)
+    nets = [DeviceNet(load_checkpoint(p, game).eval(), game) for p in paths]
+    rounds = 512
+    table = {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    total = 0
+    for i, a in enumerate(nets):
+        for j, b in enumerate(nets):
+            if i == j:
+                continue
+            s = play_games_batched(game, rounds, a, b, steps_before_tau_0=0, mcts_searches=cfg.PLAY_MCTS_SEARCHES,
+                                   mcts_batch_size=cfg.PLAY_MCTS_BATCH_SIZE, trees_per_game=2, seed=i * 1000 + j)
+            table["%d-%d" % (i, j)] = [s["wins"], s["losses"], s["draws"]]
+            total += s["games"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    for n in nets:
+        n.close()
+    return {"config": 5, "workload": "tournament: 4 random-init Connect4 checkpoints saved/loaded as .dat, 12 ordered pairs x %d games, "
+                                     "search_batch(40,8), tau=0, two trees per game (play.py semantics), wall clock incl. engine set-up" % rounds,
+            "games_per_sec": total / dt, "games": total, "w_l_d": table}
+
+
+def main():
+    which = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 3, 4, 5]
+    fns = {1: config1, 3: config3, 4: config4, 5: config5}
+    for k in which:
+        if k == 4 and len(sys.argv) > 2:
+            print(json.dumps(config4(int(sys.argv[2]))), flush=True)
+        else:
+            print(json.dumps(fns[k]()), flush=True)
+
+
+if __name__ == "__main__":
+    main()
