@@ -60,8 +60,9 @@ def self_play(game, replay_buffer, best: DeviceNet, games: int, tb, step_idx: in
     return stats, dt
 
 
-def train_neural_net(game, net: Net, replay_buffer, optimizer, tb, step_idx: int, device):
-    """train.py:62-117."""
+def train_neural_net(game, net: Net, replay_buffer, optimizer, tb, step_idx: int, device, bucket=None):
+    """train.py:62-117.  ``bucket``: a ``distributed.FlatGradients`` over the net's parameters (one all-reduce per
+    round, no flatten / scatter); without it the gradients are flattened per round (``allreduce_gradients``)."""
     sums = [0.0, 0.0, 0.0]
     net.train()
     for _ in range(cfg.TRAIN_ROUNDS):
@@ -70,7 +71,10 @@ def train_neural_net(game, net: Net, replay_buffer, optimizer, tb, step_idx: int
         d_boards = torch.from_numpy(game.boards_from_states(states).view("int64")).to(device)
         d_who = torch.tensor(list(who), dtype=torch.uint8, device=device)
         states_t = game.planes_device(d_boards, d_who, len(states))
-        optimizer.zero_grad()
+        if bucket is not None:
+            bucket.zero()
+        else:
+            optimizer.zero_grad()
         probs_v = torch.tensor(probs, dtype=torch.float32, device=device)
         values_v = torch.tensor(values, dtype=torch.float32, device=device)
         out_logits, out_values = net(states_t)
@@ -78,7 +82,10 @@ def train_neural_net(game, net: Net, replay_buffer, optimizer, tb, step_idx: int
         loss_policy = (-F.log_softmax(out_logits, dim=1) * probs_v).sum(dim=1).mean()
         loss = loss_policy + loss_value
         loss.backward()
-        D.allreduce_gradients(net.parameters())
+        if bucket is not None:
+            bucket.allreduce()
+        else:
+            D.allreduce_gradients(net.parameters())
         optimizer.step()
         sums[0] += loss.item()
         sums[1] += loss_value.item()
@@ -132,6 +139,7 @@ def main(argv=None):
     if rank == 0:
         print(net)
     optimizer = optim.SGD(net.parameters(), lr=cfg.LEARNING_RATE, momentum=0.9)
+    bucket = D.FlatGradients(net.parameters())
     replay_buffer = collections.deque(maxlen=cfg.REPLAY_BUFFER)
     step_idx = best_idx = 0
     with TBMeanTracker(writer, batch_size=10) as tb:
@@ -145,7 +153,7 @@ def main(argv=None):
                 sys.stdout.flush()
             if len(replay_buffer) < cfg.MIN_REPLAY_TO_TRAIN:
                 continue
-            train_neural_net(game, net, replay_buffer, optimizer, tb, step_idx, device)
+            train_neural_net(game, net, replay_buffer, optimizer, tb, step_idx, device, bucket)
             if step_idx % cfg.EVALUATE_EVERY_STEP == 0:
                 win_ratio = evaluate(game, net, best_dev, cfg.EVALUATION_ROUNDS, seed=step_idx, device=device)
                 if rank == 0:

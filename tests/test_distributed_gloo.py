@@ -36,6 +36,23 @@ def _worker(rank, world_size, port, results):
         p.grad = torch.full_like(p, float(rank + 1))
     n = D.allreduce_gradients(net.parameters())
     ok_grad = all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in net.parameters())
+    # persistent bucket: .grad tensors are views, a real backward accumulates into them, one all-reduce averages
+    torch.manual_seed(7)
+    net2 = Net(g.obs_shape, g.action_space)
+    bucket = D.FlatGradients(net2.parameters())
+    bucket.zero()
+    x = torch.full((4, 2, 6, 7), float(rank + 1))
+    logits, val = net2(x)
+    (logits.sum() + val.sum()).backward()
+    views_kept = all(p.grad.data_ptr() >= bucket.flat.data_ptr() and
+                     p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4 for p in net2.parameters())
+    local = bucket.flat.clone()
+    n2 = bucket.allreduce()
+    gathered = [torch.zeros_like(local) for _ in range(world_size)]
+    dist.all_gather(gathered, local)
+    ok_bucket = views_kept and n2 == n and torch.allclose(bucket.flat, sum(gathered) / world_size, rtol=1e-6, atol=1e-6) \
+        and bool(local.abs().sum() > 0)
+    ok_grad = ok_grad and ok_bucket
     tall = D.reduce_tallies(rank + 1, 10 * (rank + 1), 0)
     first, count = D.shard_games(4097, rank, world_size)
     results[rank] = (same, ok_grad, n, tall, first, count)
