@@ -51,6 +51,33 @@ __global__ void planes_kernel(R rules, const typename R::Board* __restrict__ in,
   planes[t] = (float)rules.plane_value(in[i], who[i], plane, row, col);
 }
 
+// Vectorised variant: every thread produces V (2 or 4) consecutive floats of one position's planes with one 8- or
+// 16-byte store (2 H W is always even; the scalar kernel above reached 21 % of the HBM roofline on 4 M Connect4
+// positions, this one is store-bandwidth-bound).
+template <class R, int V>
+__global__ void planes_vec_kernel(R rules, const typename R::Board* __restrict__ in, const uint8_t* __restrict__ who,
+                                  long long count, float* __restrict__ planes) {
+  const int H = rules.rows(), W = rules.cols();
+  const int per = 2 * H * W, vec_per = per / V;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * vec_per) return;
+  const long long i = t / vec_per;
+  const int r0 = (int)(t - i * vec_per) * V;
+  const typename R::Board s = in[i];
+  const int wm = who[i];
+  float v[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int r = r0 + e;
+    const int plane = r / (H * W), cell = r - plane * H * W;
+    const int row = cell / W, col = cell - row * W;
+    v[e] = (float)rules.plane_value(s, wm, plane, row, col);
+  }
+  float* dst = planes + i * per + r0;
+  if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[V - 1]);
+  else *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+}
+
 // MCTS._backup (lib/mcts.py:225-246) on caller-provided flat N/W/Q arrays: the dict-view facade of
 // caro_ai_b200.mcts.MCTS uses it when statistics were assigned from the host (lib/test_mcts.py:15-38).
 __global__ void backup_path_kernel(int32_t* __restrict__ N, float* __restrict__ W, float* __restrict__ Q,
@@ -126,11 +153,23 @@ int caro_boards_encode_planes(int game, int n, int k, const void* d_boards, cons
   if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the board kernels have no CPU fallback");
   if (count == 0) return CARO_OK;
   const long long per = game == CARO_GAME_CONNECT4 ? 84 : 2LL * n * n;
-  const unsigned grid = (unsigned)((count * per + 255) / 256);
-  if (game == CARO_GAME_CONNECT4)
-    planes_kernel<C4Rules><<<grid, 256, 0, S(stream)>>>(C4Rules(), (const C4Board*)d_boards, d_who, count, d_planes);
-  else
-    planes_kernel<MnkRules><<<grid, 256, 0, S(stream)>>>(MnkRules{n, k}, (const MnkBoard*)d_boards, d_who, count, d_planes);
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_planes) & 15u) == 0;
+  if (game == CARO_GAME_CONNECT4 && aligned) {
+    const unsigned grid = (unsigned)((count * (per / 4) + 255) / 256);
+    planes_vec_kernel<C4Rules, 4><<<grid, 256, 0, S(stream)>>>(C4Rules(), (const C4Board*)d_boards, d_who, count, d_planes);
+  } else if (game != CARO_GAME_CONNECT4 && aligned && per % 4 == 0) {
+    const unsigned grid = (unsigned)((count * (per / 4) + 255) / 256);
+    planes_vec_kernel<MnkRules, 4><<<grid, 256, 0, S(stream)>>>(MnkRules{n, k}, (const MnkBoard*)d_boards, d_who, count, d_planes);
+  } else if (game != CARO_GAME_CONNECT4 && aligned) {
+    const unsigned grid = (unsigned)((count * (per / 2) + 255) / 256);
+    planes_vec_kernel<MnkRules, 2><<<grid, 256, 0, S(stream)>>>(MnkRules{n, k}, (const MnkBoard*)d_boards, d_who, count, d_planes);
+  } else {
+    const unsigned grid = (unsigned)((count * per + 255) / 256);
+    if (game == CARO_GAME_CONNECT4)
+      planes_kernel<C4Rules><<<grid, 256, 0, S(stream)>>>(C4Rules(), (const C4Board*)d_boards, d_who, count, d_planes);
+    else
+      planes_kernel<MnkRules><<<grid, 256, 0, S(stream)>>>(MnkRules{n, k}, (const MnkBoard*)d_boards, d_who, count, d_planes);
+  }
   return caro_check_launch("planes_kernel");
 }
 

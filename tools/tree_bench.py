@@ -19,7 +19,57 @@ from caro_ai_b200.model import DeviceNet, Net
 HBM_GBS = 6539.2  # MEASURED_PEAKS.json
 
 
+def board_kernels(game):
+    """Streaming board kernels (caro_boards_apply / legal_mask / encode_planes) on 16 M random Connect4 positions:
+    algorithmic bytes = 16 B board in (+ 16 B out + 5 B action/player + 2 B flags for apply; + 4 B mask; + 336 B planes)."""
+    import ctypes as C
+    import numpy as np
+    from caro_ai_b200 import _cabi
+    n = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(1)
+    heights = torch.randint(0, 6, (n, 7), device="cuda", generator=g)           # never full: every column stays legal
+    colbits = torch.randint(0, 64, (n, 7), device="cuda", generator=g)
+    shifts = (7 * torch.arange(7, device="cuda")).view(1, 7)
+    col_mask = (torch.ones_like(heights) << heights) - 1
+    mask = (col_mask << shifts).sum(1)
+    black = ((colbits & col_mask) << shifts).sum(1)
+    boards = torch.stack([mask, black], 1).contiguous()
+    acts = torch.randint(0, 7, (n,), device="cuda", dtype=torch.int32, generator=g)
+    pl = torch.randint(0, 2, (n,), device="cuda", generator=g).to(torch.uint8)
+    out = torch.empty_like(boards)
+    won = torch.empty(n, dtype=torch.uint8, device="cuda")
+    draw = torch.empty(n, dtype=torch.uint8, device="cuda")
+    lm = torch.empty(n, dtype=torch.int32, device="cuda")
+    np_ = 1 << 22
+    planes = torch.empty((np_, 2, 6, 7), dtype=torch.float32, device="cuda")
+    lib, st = _cabi.lib(), torch.cuda.current_stream().cuda_stream
+    jobs = {
+        "boards_apply": (lambda: lib.caro_boards_apply(game.game_kind, 0, 0, boards.data_ptr(), acts.data_ptr(), pl.data_ptr(), n,
+                                                      out.data_ptr(), won.data_ptr(), draw.data_ptr(), st), n * (16 + 16 + 5 + 2)),
+        "boards_legal_mask": (lambda: lib.caro_boards_legal_mask(game.game_kind, 0, 0, boards.data_ptr(), n, lm.data_ptr(), st), n * 20),
+        "boards_encode_planes": (lambda: lib.caro_boards_encode_planes(game.game_kind, 0, 0, boards.data_ptr(), pl.data_ptr(), np_,
+                                                                      planes.data_ptr(), st), np_ * (17 + 336)),
+    }
+    res = {"positions": n}
+    for name, (fn, nbytes) in jobs.items():
+        for _ in range(3):
+            _cabi.check(fn())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            _cabi.check(fn())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res[name] = {"ms": ms, "GB_per_s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / HBM_GBS}
+    print(json.dumps({"board_kernels": res}), flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "boards":
+        board_kernels(ConnectFour())
+        return
     sizes = [int(x) for x in sys.argv[1:]] or [4096, 16384]
     game = ConnectFour()
     A = game.action_space
