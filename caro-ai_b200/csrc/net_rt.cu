@@ -267,6 +267,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  if (tid == 0) TC_TRACE(7, 0);  // kernel entered
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int nb = gm.nb;
   const int H = gm.H;
@@ -298,6 +299,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TC_TRACE(7, 1);  // setup done
 
   if (warp >= K::kHeadWarp) {
     // ===================== head warps: FC heads of group g while the pipeline already runs group g+1; the last
@@ -615,8 +617,10 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   }
 
   // ---- teardown ---------------------------------------------------------------------------------
+  if (tid == 0) TC_TRACE(7, 2);  // epilogue warp 0 finished (incl. the last group's heads)
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TC_TRACE(7, 3);  // all roles finished
   if (warp == K::kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");

@@ -33,7 +33,7 @@ def main():
     t = trace.cpu().numpy()
     names = ["mma_start", "mma_issued", "epi_start", "epi_done", "lastepi+inputs", "heads_done", "weights_ok"]
     ev = []
-    for kind in range(7):
+    for kind in range(8):
         for idx in range(1000):
             v = int(t[kind * 1000 + idx])
             if v:
@@ -44,6 +44,8 @@ def main():
     for clk, kind, idx in ev[:limit]:
         if kind == 6:
             print("%8d  %-14s gl=%d %s" % (clk - t0, "layer_enter" if idx % 2 == 0 else "bars_passed", idx // 2, ""))
+        elif kind == 7:
+            print("%8d  %s" % (clk - t0, ["kernel_entered", "setup_done", "warp0_finished", "all_finished"][idx]))
         elif kind < 4:
             print("%8d  %-14s gl=%d t=%d" % (clk - t0, names[kind], idx // div, idx % div))
         else:
