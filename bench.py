@@ -317,6 +317,9 @@ def engine_arm(args):
             "roofline": {"kernel": "net_rt_kernel (row-tiled tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
                          "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "note": "CUDA-event time per launch on the launching stream; the parts' towers run on their own streams "
+                                 "and overlap tail-to-head, so the summed event time can exceed the step time and `achieved` is a "
+                                 "lower bound (stand-alone: tools/net_bench.py, DESIGN.md section 4)" if halves >= 2 else "",
                          "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),
                          "avg_launch_ms": prof["net_ms"] / max(1, n_net_launches)},
             "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
