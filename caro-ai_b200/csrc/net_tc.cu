@@ -105,41 +105,61 @@ __device__ __noinline__ void export_heads(const TcGeom& gm, int nvalid, long lon
 
 constexpr int kHeadsLeaves = 32;   // leaves per CTA of heads_kernel
 constexpr int kHeadsThreads = 256;
+constexpr int kHeadsPitch = 36;    // floats per feature row in shared memory: 32 leaves + 4 (16-byte aligned rows, and the
+                                   // transposing writes of the load phase spread over 8 banks instead of hitting one)
 
 // FC heads for a batch of leaves (lib/model.py:56-72,90-93 + softmax of lib/mcts.py:216) from the exported head features.
-// Shared memory: fs[3 HW][32] activated features (leaf index fastest: the inner loops read 32 leaves of one feature as
-// eight broadcast float4), lg[32][A] logits, hid[32][20].
+// Shared memory: fs[3 HW][36] activated features (leaf index fastest: the inner loops read 32 leaves of one feature as
+// eight broadcast float4), lg[32][A] logits, hid[32][20].  The FC weights are read once per CTA, 8 rows ahead.
 __global__ void __launch_bounds__(kHeadsThreads)
 heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count, long long max_count, int HW, int A,
              const float* __restrict__ blob, BlobLayout L, const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t,
              float* __restrict__ probs, float* __restrict__ values) {
   extern __shared__ __align__(16) float hs[];
-  float* fs = hs;                                 // [3 HW][32]
-  float* lg = fs + (size_t)3 * HW * kHeadsLeaves;  // [32][A]
+  float* fs = hs;                                 // [3 HW][36]
+  float* lg = fs + (size_t)3 * HW * kHeadsPitch;   // [32][A]
   float* hid = lg + (size_t)kHeadsLeaves * A;      // [32][20]
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int tid = threadIdx.x;
   const float hb[3] = {blob[L.val_conv_b], blob[L.pol_conv_b], blob[L.pol_conv_b + 1]};
   for (long long leaf0 = (long long)blockIdx.x * kHeadsLeaves; leaf0 < count; leaf0 += (long long)gridDim.x * kHeadsLeaves) {
     const int nvalid = (int)min((long long)kHeadsLeaves, count - leaf0);
-    const int l = tid & 31;
-    for (int k = tid >> 5; k < 3 * HW; k += kHeadsThreads / 32) {
-      float v = 0.0f;
-      if (l < nvalid) v = lrelu_tc(feat[(size_t)(leaf0 + l) * 3 * HW + k] + hb[k / HW]);
-      fs[k * kHeadsLeaves + l] = v;
+    for (int l = 0; l < kHeadsLeaves; ++l) {  // coalesced reads along the features of one leaf, transposed into fs
+      const float* src = feat + (size_t)(leaf0 + l) * 3 * HW;
+      for (int k = tid; k < 3 * HW; k += kHeadsThreads)
+        fs[k * kHeadsPitch + l] = l < nvalid ? lrelu_tc(src[k] + hb[k / HW]) : 0.0f;
     }
     __syncthreads();
     for (int a = tid; a < A; a += kHeadsThreads) {  // policy FC: this thread owns action a of all 32 leaves
       float acc[kHeadsLeaves];
 #pragma unroll
       for (int i = 0; i < kHeadsLeaves; ++i) acc[i] = 0.0f;
-      const float4* f4 = reinterpret_cast<const float4*>(fs + (size_t)HW * kHeadsLeaves);
-#pragma unroll 2
-      for (int k = 0; k < 2 * HW; ++k) {
+      const float* fbase = fs + (size_t)HW * kHeadsPitch;
+      const int K2 = 2 * HW;
+      int k = 0;
+      for (; k + 8 <= K2; k += 8) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(pol_fc_t + (size_t)(k + u) * A + a);  // 8 independent L2 reads in flight
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)(k + u) * kHeadsPitch);
+#pragma unroll
+          for (int q = 0; q < kHeadsLeaves / 4; ++q) {
+            const float4 f = f4[q];
+            acc[4 * q] = fmaf(w[u], f.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(w[u], f.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w[u], f.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(w[u], f.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      for (; k < K2; ++k) {
         const float w = __ldg(pol_fc_t + (size_t)k * A + a);
+        const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)k * kHeadsPitch);
 #pragma unroll
         for (int q = 0; q < kHeadsLeaves / 4; ++q) {
-          const float4 f = f4[k * (kHeadsLeaves / 4) + q];
+          const float4 f = f4[q];
           acc[4 * q] = fmaf(w, f.x, acc[4 * q]);
           acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
           acc[4 * q + 2] = fmaf(w, f.z, acc[4 * q + 2]);
@@ -152,9 +172,14 @@ heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count
     }
     for (int o = tid; o < kHeadsLeaves * 20; o += kHeadsThreads) {  // value FC1
       const int ll = o & 31, i = o >> 5;
-      float a0 = 0.0f;
-      for (int c = 0; c < HW; ++c) a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsLeaves + ll], a0);
-      hid[ll * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + a0);
+      float a0 = 0.0f, a1 = 0.0f;
+      int c = 0;
+      for (; c + 1 < HW; c += 2) {
+        a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsPitch + ll], a0);
+        a1 = fmaf(__ldg(val_fc1_t + (size_t)(c + 1) * 20 + i), fs[(c + 1) * kHeadsPitch + ll], a1);
+      }
+      for (; c < HW; ++c) a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsPitch + ll], a0);
+      hid[ll * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + (a0 + a1));
     }
     __syncthreads();
     for (int b = tid >> 5; b < nvalid; b += kHeadsThreads / 32) {
@@ -615,7 +640,7 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
                                           (long long*)net->d_trace);
   int rc = caro_check_launch("net_tc_kernel");
   if (rc == CARO_OK && headfeat != nullptr) {
-    const size_t smem = ((size_t)3 * HW * kHeadsLeaves + (size_t)kHeadsLeaves * net->A + kHeadsLeaves * 20) * sizeof(float);
+    const size_t smem = ((size_t)3 * HW * kHeadsPitch + (size_t)kHeadsLeaves * net->A + kHeadsLeaves * 20) * sizeof(float);
     const long long tiles = (max_count + kHeadsLeaves - 1) / kHeadsLeaves;
     const unsigned hgrid = (unsigned)(tiles < 2 * sm_count ? tiles : 2 * sm_count);
     heads_kernel<<<hgrid, kHeadsThreads, smem, st>>>(headfeat, d_count, (long long)max_count, HW, net->A, net->d_blob, net->layout,

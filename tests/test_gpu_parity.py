@@ -357,3 +357,23 @@ def test_net_row_tiled_kernel_device_count(torch_cuda):
     assert torch.equal(probs[:37], full_p[:37]) and torch.equal(values[:37], full_v[:37])
     assert bool((probs[37:] == -7.0).all()) and bool((values[37:] == -7.0).all())
     dn.close()
+
+
+def test_net_grid_limit_does_not_change_results(torch_cuda):
+    """caro_net_set_grid_limit only changes how many SMs the persistent tower occupies, never a result bit."""
+    import torch
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import DeviceNet
+    game = ConnectFour()
+    dn = DeviceNet(_random_net(game, 2), game)
+    og = oracle_for(game)
+    rng = np.random.default_rng(9)
+    pos = [random_position(og, rng, int(rng.integers(0, 30))) for _ in range(64)]
+    states, players = [p[0] for p in pos] * 80, [p[1] for p in pos] * 80  # 5120 leaves: several passes per CTA
+    p0, v0 = dn.forward_states(states, players, impl=0)
+    dn.set_grid_limit(37)
+    p1, v1 = dn.forward_states(states, players, impl=0)
+    dn.set_grid_limit(0)
+    torch.cuda.synchronize()
+    assert torch.equal(p0, p1) and torch.equal(v0, v1)
+    dn.close()
