@@ -135,3 +135,29 @@ def test_config_matches_reference_values():
     assert (cfg.C_PUCT, cfg.ALPHA, cfg.EXPLORE) == (1.0, 0.30, 0.25)                         # config.py:26-28
     assert (cfg.REPLAY_BUFFER, cfg.BATCH_SIZE, cfg.TRAIN_ROUNDS, cfg.MIN_REPLAY_TO_TRAIN) == (5000, 256, 10, 2000)
     assert (cfg.PLAY_MCTS_SEARCHES, cfg.PLAY_MCTS_BATCH_SIZE, cfg.BEST_NET_WIN_RATIO) == (40, 8, 0.60)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the keys of the
+    bench contract, `impl: reference`, a cpu_baseline describing the run and an e2e object without copies."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "connect4_mcts_leaf_evals_per_sec" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    # ranks other than 0 stay silent under torchrun
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
