@@ -57,7 +57,8 @@ struct caro_net {
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
   float* d_headfeat;    // large boards: exported 1x1 head-convolution sums [leaf][3][HW] for heads_kernel (net_tc.cu)
-  long long headfeat_leaves;  // capacity of d_headfeat in leaves
+  long long headfeat_leaves;  // capacity of ONE slot of d_headfeat in leaves
+  unsigned headfeat_seq;      // next slot (round robin per launch)
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
   int sm_count;         // multiprocessors of the device the handle was created on
   int grid_limit;       // > 0: CTAs (= SMs) the persistent tower may occupy (caro_net_set_grid_limit), 0 = all

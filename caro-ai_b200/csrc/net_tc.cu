@@ -37,6 +37,7 @@ constexpr int kTapBytes = 8 * 64 * 16;                   // 8,192: one tap of a 
 constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of conv_in (K padded to 16)
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
+constexpr int kHeadfeatSlots = 8;                         // scratch slots for exported head features (launches in flight)
 constexpr int kHeadsInTowerMaxHW = 64;                    // larger boards run their FC heads in heads_kernel
 constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
 constexpr int kEpiWarps = 8;                             // warps 0-7: epilogue; TMEM lane quarter = warp & 3, column half = warp >> 2
@@ -590,8 +591,8 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
     for (int c = 0; c < HW; ++c) polt[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
   cudaError_t ce = cudaSuccess;
   if (HW > kHeadsInTowerMaxHW && !net->d_headfeat) {  // large boards: FC heads run in heads_kernel from exported features
-    net->headfeat_leaves = 65536;
-    ce = cudaMalloc(&net->d_headfeat, (size_t)net->headfeat_leaves * 3 * HW * sizeof(float));
+    net->headfeat_leaves = 8192;  // per slot: larger launches fall back to the FC heads inside the tower
+    ce = cudaMalloc(&net->d_headfeat, (size_t)kHeadfeatSlots * net->headfeat_leaves * 3 * HW * sizeof(float));
     if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   }
   if (!net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
@@ -633,7 +634,12 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   const long long max_groups = (max_count + gm.boards_per_group - 1) / gm.boards_per_group;
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);
   const int HW = net->H * net->W;
-  float* headfeat = (net->d_headfeat != nullptr && max_count <= net->headfeat_leaves) ? net->d_headfeat : nullptr;
+  // the exported head features go to one of kHeadfeatSlots scratch slots, round robin per launch: launches of different
+  // parts of the self-play pipeline can be in flight at the same time on different streams (and the slot is baked
+  // into a captured graph node), so they must not share a buffer
+  float* headfeat = nullptr;
+  if (net->d_headfeat != nullptr && max_count <= net->headfeat_leaves)
+    headfeat = net->d_headfeat + (size_t)(net->headfeat_seq++ % kHeadfeatSlots) * net->headfeat_leaves * 3 * HW;
   kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
                                           (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
                                           net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat,

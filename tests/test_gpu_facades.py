@@ -294,3 +294,33 @@ def test_finished_games_replay_and_restart():
     assert (eng.region("status") == 1).all()
     eng.reset()
     assert eng.roots()[0] == [game.initial_state] * 256 and int(eng.region("node_count").sum().item()) == 0
+
+
+def test_caro_pipeline_parts_do_not_share_head_scratch():
+    """Caro 15x15 runs its FC heads in a separate kernel from exported features; two pipeline parts have tower launches
+    in flight at the same time, so the scratch is slotted per launch: a 2-part run must reproduce the two single-engine
+    runs bit for bit (same seeds, Philox streams are addressed by game id)."""
+    import torch
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import TicTacToe
+    from caro_ai_b200.model import DeviceNet, Net
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    game = TicTacToe(15, 5)
+    torch.manual_seed(0)
+    dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
+
+    def engines():
+        return [SelfPlayEngine(game, 48, max_batch=8, node_capacity=2048, seed=31 + h) for h in range(2)]
+
+    solo = engines()
+    for e in solo:
+        e.play(dn, dn, moves=2, count=12, batch=8, tau_plies=10, auto_restart=True)
+    pair = engines()
+    SelfPlayEngine.play_multi(pair, dn, moves=2, count=12, batch=8, tau_plies=10, auto_restart=True)
+    torch.cuda.synchronize()
+    for a, b in zip(solo, pair):
+        assert a.counters() == b.counters() and a.counters()["errors"] == 0
+        assert a.roots() == b.roots()
+        assert torch.equal(a.region("N"), b.region("N")) and torch.equal(a.region("P"), b.region("P"))
+    dn.close()
