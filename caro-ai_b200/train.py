@@ -167,6 +167,8 @@ def main(argv=None):
                     best_idx += 1
                     if rank == 0:
                         save_checkpoint(net, os.path.join(saves_path, "best_%03d_%05d.dat" % (best_idx, step_idx)))
+    if ws > 1 and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
     return 0
 
 
