@@ -105,7 +105,7 @@ __device__ __noinline__ void export_heads(const TcGeom& gm, int nvalid, long lon
 }
 
 constexpr int kHeadsLeaves = 32;   // leaves per CTA of heads_kernel
-constexpr int kHeadsThreads = 256;
+constexpr int kHeadsThreads = 512;
 constexpr int kHeadsPitch = 36;    // floats per feature row in shared memory: 32 leaves + 4 (16-byte aligned rows, and the
                                    // transposing writes of the load phase spread over 8 banks instead of hitting one)
 
@@ -131,11 +131,13 @@ heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count
         fs[k * kHeadsPitch + l] = l < nvalid ? lrelu_tc(src[k] + hb[k / HW]) : 0.0f;
     }
     __syncthreads();
-    for (int a = tid; a < A; a += kHeadsThreads) {  // policy FC: this thread owns action a of all 32 leaves
-      float acc[kHeadsLeaves];
+    for (int t = tid; t < 2 * A; t += kHeadsThreads) {  // policy FC: this thread owns action a of 16 of the 32 leaves
+      constexpr int LH = kHeadsLeaves / 2;
+      const int h = t >= A ? 1 : 0, a = t - h * A;
+      float acc[LH];
 #pragma unroll
-      for (int i = 0; i < kHeadsLeaves; ++i) acc[i] = 0.0f;
-      const float* fbase = fs + (size_t)HW * kHeadsPitch;
+      for (int i = 0; i < LH; ++i) acc[i] = 0.0f;
+      const float* fbase = fs + (size_t)HW * kHeadsPitch + h * LH;
       const int K2 = 2 * HW;
       int k = 0;
       for (; k + 8 <= K2; k += 8) {
@@ -146,7 +148,7 @@ heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count
         for (int u = 0; u < 8; ++u) {
           const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)(k + u) * kHeadsPitch);
 #pragma unroll
-          for (int q = 0; q < kHeadsLeaves / 4; ++q) {
+          for (int q = 0; q < LH / 4; ++q) {
             const float4 f = f4[q];
             acc[4 * q] = fmaf(w[u], f.x, acc[4 * q]);
             acc[4 * q + 1] = fmaf(w[u], f.y, acc[4 * q + 1]);
@@ -159,7 +161,7 @@ heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count
         const float w = __ldg(pol_fc_t + (size_t)k * A + a);
         const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)k * kHeadsPitch);
 #pragma unroll
-        for (int q = 0; q < kHeadsLeaves / 4; ++q) {
+        for (int q = 0; q < LH / 4; ++q) {
           const float4 f = f4[q];
           acc[4 * q] = fmaf(w, f.x, acc[4 * q]);
           acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
@@ -169,7 +171,7 @@ heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count
       }
       const float b = blob[L.pol_fc_b + a];
 #pragma unroll
-      for (int i = 0; i < kHeadsLeaves; ++i) lg[i * A + a] = acc[i] + b;
+      for (int i = 0; i < LH; ++i) lg[(h * LH + i) * A + a] = acc[i] + b;
     }
     for (int o = tid; o < kHeadsLeaves * 20; o += kHeadsThreads) {  // value FC1
       const int ll = o & 31, i = o >> 5;
