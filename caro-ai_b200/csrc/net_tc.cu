@@ -593,7 +593,7 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
     for (int c = 0; c < HW; ++c) polt[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
   cudaError_t ce = cudaSuccess;
   if (HW > kHeadsInTowerMaxHW && !net->d_headfeat) {  // large boards: FC heads run in heads_kernel from exported features
-    net->headfeat_leaves = 8192;  // per slot: larger launches fall back to the FC heads inside the tower
+    net->headfeat_leaves = 32768;  // per slot (708 MB in all for 15x15): larger launches fall back to the FC heads inside the tower
     ce = cudaMalloc(&net->d_headfeat, (size_t)kHeadfeatSlots * net->headfeat_leaves * 3 * HW * sizeof(float));
     if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   }

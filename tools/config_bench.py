@@ -125,16 +125,43 @@ def config3():
             "gradient_bytes": 4 * n_param}
 
 
-def config4(games=128):
+def config4(games=128, parts=1):
     game = TicTacToe(15, 5)
     torch.manual_seed(0)
     dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
-    eng = SelfPlayEngine(game, games, max_batch=8, node_capacity=16384, seed=1)
-    sec, d = timed_plies(eng, dn, 4, 200, 8, cfg.STEPS_BEFORE_TAU_0)
-    eng.close()
+    if parts == 1:
+        eng = SelfPlayEngine(game, games, max_batch=8, node_capacity=16384, seed=1)
+        sec, d = timed_plies(eng, dn, 4, 200, 8, cfg.STEPS_BEFORE_TAU_0)
+        eng.close()
+    else:  # the parts pipeline (caro_engine_play_multi): tree kernels of one part under the other parts' towers
+        engs = [SelfPlayEngine(game, games // parts, max_batch=8, node_capacity=16384, seed=1 + h) for h in range(parts)]
+
+        def run(n):
+            SelfPlayEngine.play_multi(engs, dn, moves=n, count=200, batch=8, tau_plies=cfg.STEPS_BEFORE_TAU_0, auto_restart=True)
+
+        def tot():
+            t = {}
+            for e in engs:
+                for k, v in e.counters().items():
+                    t[k] = t.get(k, 0) + v
+            return t
+
+        run(2)
+        torch.cuda.synchronize()
+        c0 = tot()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(4)
+        e1.record()
+        torch.cuda.synchronize()
+        c1 = tot()
+        assert c1["errors"] == 0
+        sec, d = e0.elapsed_time(e1) / 1e3, {k: c1[k] - c0[k] for k in c1}
+        for e in engs:
+            e.close()
     dn.close()
     return {"config": 4, "workload": "Caro 15,15,5 self-play, search_batch(200,8) = 1600 sims/move, %d concurrent games, reference-shape 5x64 "
-                                     "net (tap-per-MMA tcgen05 kernel: boards larger than 6x7), 4 plies after 2 warm-up plies" % games,
+                                     "net (tap-per-MMA tcgen05 kernel: boards larger than 6x7), 4 plies after 2 warm-up plies, %d pipeline part(s)" % (games, parts),
             "leaf_evals_per_sec": d["leaf_evals"] / sec, "plies_per_sec": d["plies"] / sec, "descents_per_sec": d["descents"] / sec,
             "tflops_useful": d["leaf_evals"] * 83760340 / sec / 1e12}
 
@@ -176,7 +203,7 @@ def main():
     fns = {1: config1, 3: config3, 4: config4, 5: config5}
     for k in which:
         if k == 4 and len(sys.argv) > 2:
-            print(json.dumps(config4(int(sys.argv[2]))), flush=True)
+            print(json.dumps(config4(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 1)), flush=True)
         else:
             print(json.dumps(fns[k]()), flush=True)
 
