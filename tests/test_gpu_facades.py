@@ -324,3 +324,31 @@ def test_caro_pipeline_parts_do_not_share_head_scratch():
         assert a.roots() == b.roots()
         assert torch.equal(a.region("N"), b.region("N")) and torch.equal(a.region("P"), b.region("P"))
     dn.close()
+
+
+def test_bench_engine_arm_prints_the_contract_line():
+    """`python bench.py` on a small batch: ONE JSON line with the contract's keys, a roofline and an e2e object whose
+    byte counts match the host buffers that are copied per step, launches counted, no engine errors."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--games", "512", "--steps", "4", "--warmup", "3",
+                          "--preroll", "4", "--no-cpu-baseline", "--node-capacity", "8192"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "connect4_mcts_leaf_evals_per_sec" and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 4
+    assert d["engine_errors"] == 0 and d["gpu_launches"] >= 4 * 100 * 2 * 5
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 512 * 17 == d["e2e"]["d2h_bytes_per_step"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and 0 < r["frac"] < 1.5 and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "workload" in d["config"] and d["dtype"] == "bf16" and d["scaling"] == "weak"
