@@ -327,11 +327,12 @@ def engine_arm(args):
             "clocks": sampler.summary(), "engine_errors": int(errors),
         }
         if not args.no_cpu_baseline and world >= 1:
-            r = run_cpu_reference(args.cpu_plies, 1, 1, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+            cores = os.cpu_count() or 1
+            r = run_cpu_reference(args.cpu_plies, 1, cores, 1)  # one process per host core, like the reference arm
+            line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": cores, "kind": "port",
                                     "games_per_sec": r["games_per_s"],
-                                    "sample": "1 process, torch default threads, %d plies of oracle self-play "
-                                              "(search_batch(100,8) per ply) after 1 warm-up ply" % args.cpu_plies}
+                                    "sample": "%d processes x 1 torch thread, %d plies of oracle self-play each "
+                                              "(search_batch(100,8) per ply) after 1 warm-up ply" % (cores, args.cpu_plies)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -346,7 +347,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--node-capacity", type=int, default=NODE_CAPACITY)
-    ap.add_argument("--cpu-plies", type=int, default=20)
+    ap.add_argument("--cpu-plies", type=int, default=10)
     ap.add_argument("--preroll", type=int, default=30)
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--parts", type=int, default=2, help="software-pipelined parts the game batch is split into")
