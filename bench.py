@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--node-capacity", type=int, default=NODE_CAPACITY)
-    ap.add_argument("--cpu-plies", type=int, default=10)
+    ap.add_argument("--cpu-plies", type=int, default=40)
     ap.add_argument("--preroll", type=int, default=30)
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--parts", type=int, default=2, help="software-pipelined parts the game batch is split into")
