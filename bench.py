@@ -220,13 +220,22 @@ def engine_arm(args):
     play(args.warmup)
     barrier()
     c0 = counters()
+    # The K timed plies: the first K - P replay one CUDA graph per ply (the production path), the last P are issued
+    # launch by launch with CUDA events around every network kernel (events cannot be replayed from a graph); both
+    # kinds are inside the timed region, the roofline's per-launch duration comes from the P evented plies.
+    evented = args.steps if (args.profile_level >= 2 or halves < 2) else max(1, min(8, args.steps // 4))
+    graphed = args.steps - evented
     for e in engs:
-        e.profile(args.profile_level)
+        e.profile(0)
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    play(args.steps)
+    if graphed:
+        play(graphed)
+    for e in engs:
+        e.profile(args.profile_level)  # host-side switch, no synchronisation
+    play(evented)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -299,7 +308,10 @@ def engine_arm(args):
         my_leaf = c1["leaf_evals"] - c0["leaf_evals"]
         net_s = prof["net_ms"] / 1000.0
         n_net_launches = args.steps * SIMS_COUNT * halves
-        achieved_tflops = my_leaf * FLOP_PER_LEAF_C4 / net_s / 1e12 if net_s > 0 else 0.0
+        n_evented = evented * SIMS_COUNT * halves
+        avg_launch_s = net_s / max(1, n_evented)
+        achieved_tflops = (my_leaf / max(1, n_net_launches)) * FLOP_PER_LEAF_C4 / avg_launch_s / 1e12 if net_s > 0 else 0.0
+        graph_launches = graphed * halves * (SIMS_COUNT * 5 + 1)  # per ply and part: 100 x (noise, select, plan, tower, expand+backup) + advance
         line = {
             "metric": "connect4_mcts_leaf_evals_per_sec", "value": leaf / sec, "unit": "leaf_evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -313,16 +325,17 @@ def engine_arm(args):
             "games_per_sec": games / sec, "plies_per_sec": plies / sec, "descents_per_sec": desc / sec,
             "e2e": {"value": e2e_leaf / (e2e_max / 1000.0), "unit": "leaf_evals/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(world * G * 17), "d2h_bytes_per_step": int(world * G * 17)},
-            "gpu_launches": int(prof["launches"]),
+            "gpu_launches": int(prof["launches"]) + int(graph_launches),
             "roofline": {"kernel": "net_rt_kernel (row-tiled tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
                          "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
-                         "note": "CUDA-event time per launch on the launching stream; the parts' towers run on their own streams "
-                                 "and overlap tail-to-head, so the summed event time can exceed the step time and `achieved` is a "
-                                 "lower bound (stand-alone: tools/net_bench.py, DESIGN.md section 4)" if halves >= 2 else "",
+                         "note": "average CUDA-event time per tower launch over the evented plies of the timed region (the other timed "
+                                 "plies replay a CUDA graph, where events cannot be recorded); the parts' towers run on their own streams "
+                                 "and overlap tail-to-head, so `achieved` is a lower bound (stand-alone: tools/net_bench.py, DESIGN.md "
+                                 "section 4)" if halves >= 2 else "",
                          "flop_per_leaf": FLOP_PER_LEAF_C4, "leaves_per_launch": my_leaf / max(1, n_net_launches),
-                         "avg_launch_ms": prof["net_ms"] / max(1, n_net_launches)},
-            "phase_ms_per_step": {k: prof[k] / args.steps for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
+                         "avg_launch_ms": 1e3 * avg_launch_s, "evented_steps": evented, "graph_replayed_steps": graphed},
+            "phase_ms_per_step": {k: prof[k] / max(1, evented) for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
                                   if args.profile_level >= 2 or k == "net_ms"},
             "clocks": sampler.summary(), "engine_errors": int(errors),
         }
