@@ -405,6 +405,11 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         tc_fence_after();  // orders this tile's MMAs after the barrier observations (also the early ones)
         if (elected) TC_TRACE(0, gl * 8 + y);
         const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(y * 128);
+        // keep the 24 weight descriptors of the layer from being hoisted in front of the tile loop (110 uniform-datapath
+        // instructions during which the tensor pipe ran dry at every layer start): recomputed per tile, they interleave
+        // with the MMA issue, which has slack
+        uint64_t rb0t = rb0, rb1t = rb1;
+        asm volatile("" : "+l"(rb0t), "+l"(rb1t));
         // D columns: out[y-1] | out[y] | out[y+1]; the first tile has no out[-1], the last no out[H]
         const uint32_t d_main = tmem_base + (uint32_t)(y == 0 ? 0 : (y - 1) * 64);
         const uint32_t d_new = tmem_base + (uint32_t)((y + 1) * 64);
@@ -419,13 +424,13 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           npar = par ^ 1u;
         }
         if (first) {
-          if (y == 0) rt_issue_tile<0, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, true>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
         } else {
-          if (y == 0) rt_issue_tile<0, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, false>(elected, a_tile, rb0, rb1, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
         }
         if (elected) {
           umma_commit(bar_acc + y);
