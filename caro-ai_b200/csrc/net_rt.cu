@@ -12,13 +12,19 @@
 //     (horizontal tap, k-step) with B = [w(dy=+1) | w(dy=0) | w(dy=-1)] (192 columns) and the MMA accumulates
 //     into the three neighbouring output tiles, which are adjacent column ranges of TMEM (out[y] at 64y):
 //     12 MMAs of 128x192x16 per tile and layer instead of 36 of 128x64x16, 10 KB of operands per 96-cycle MMA
-//     -> tensor-bound instead of shared-memory-bound;
+//     (measured: ~107 cycles per MMA with the epilogue idle, ~120 with it running -- the shared-memory pipe is
+//     still the co-limit);
 //   * the fp32 accumulators of all H output tiles fill 384 of the 512 TMEM columns, so the residual stream
 //     v <- v + lrelu(conv(v)) is kept as bf16 hi (the shared-memory activations themselves) + an e5m2 lo part
 //     (4 channels per TMEM column, 96 columns): ~11 mantissa bits, indistinguishable from the fp32 stream at
 //     the 1e-3 contract;
-//   * weights stream through a ring of 6 KB blocks (one (horizontal tap, k-step) each) with full/empty
-//     mbarriers: cp.async.bulk by a producer warp, released by tcgen05.commit after the last tile used a block.
+//   * weights stream through three 36 KB regions (half a layer = six 6 KB blocks of one (horizontal tap, k-step)
+//     each): layer L occupies two, the first half of L+1 is prefetched into the third; cp.async.bulk + one "full"
+//     mbarrier per block by a producer warp, one "empty" mbarrier per region arrived by tcgen05.commit when the
+//     layer's last tile has used it;
+//   * biases and 1x1 head weights come through the constant cache (__grid_constant__ struct), the last layer
+//     stores every head feature exactly once (tiles split by parity between the two channel halves): no
+//     shared-memory atomics, bit-identical results from run to run.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
