@@ -594,6 +594,16 @@ int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int move
     }
     return rc;
   };
+  // with two or more parts the tower leaves a ninth of the SMs to the other parts' tree kernels (unless the caller
+  // set its own limit); the value is baked into a captured ply graph, so it only has to hold while launches are issued
+  struct PipelineGrid {
+    caro_net* net;
+    PipelineGrid(caro_net* n_, int parts) : net(n_) {
+      if (parts >= 2 && !(getenv("CARO_PIPELINE_SMS") && atoi(getenv("CARO_PIPELINE_SMS")) == 0))
+        net->pipeline_limit = getenv("CARO_PIPELINE_SMS") ? atoi(getenv("CARO_PIPELINE_SMS")) : net->sm_count - net->sm_count / 9;
+    }
+    ~PipelineGrid() { net->pipeline_limit = 0; }
+  } pipeline_grid(net, n);
   if (use_graph) {
     bool same = mg.exec && mg.n == n && mg.net == net && mg.count == count && mg.batch == batch && mg.tau == tau_plies &&
                 mg.restart == auto_restart && mg.first == first_player && mg.impl == net_impl;

@@ -171,6 +171,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->headfeat_leaves = 0;
   net->headfeat_seq = 0;
   net->grid_limit = 0;
+  net->pipeline_limit = 0;
   {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -62,6 +62,7 @@ struct caro_net {
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
   int sm_count;         // multiprocessors of the device the handle was created on
   int grid_limit;       // > 0: CTAs (= SMs) the persistent tower may occupy (caro_net_set_grid_limit), 0 = all
+  int pipeline_limit;   // > 0 while the parts pipeline issues / captures a ply and the user has set no limit: sm_count - sm_count / 9
 };
 
 // net_tc.cu

@@ -274,6 +274,20 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   if (tid == 0) TC_TRACE(7, 0);  // kernel entered
+  // debug (tools/pipeline_trace.py, trace[7998] == 2): global-timer entry / exit stamps of the first and the last CTA of
+  // every launch, to see how consecutive launches of the self-play pipeline overlap on the GPU
+  long long* gt_slot = nullptr;
+  if (trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && trace[7998] == 2) {
+    long long* base = trace + 8000 + (blockIdx.x == 0 ? 0 : 4096);
+    const long long k = base[0];
+    base[0] = k + 1;
+    if (k < 2040) {
+      gt_slot = base + 1 + 2 * k;
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      gt_slot[0] = t;
+    }
+  }
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int nb = gm.nb;
   const int H = gm.H;
@@ -632,6 +646,11 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   tc_fence_before();
   __syncthreads();
   if (tid == 0) TC_TRACE(7, 3);  // all roles finished
+  if (gt_slot != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    gt_slot[1] = t;
+  }
   if (warp == K::kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");
@@ -717,7 +736,11 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;
-  const int ctas = net->grid_limit > 0 && net->grid_limit < net->sm_count ? net->grid_limit : net->sm_count;
+  // SMs for the persistent tower: the user's limit, else (inside the parts pipeline) all but a ninth of the SMs, which stay
+  // with the other parts' tree kernels -- their dependent chain expand -> select -> plan, not the tower, sets the
+  // pipeline's period once they only get the leftover warp slots next to tower CTAs (tools/pipeline_trace.py)
+  const int lim = net->grid_limit > 0 ? net->grid_limit : net->pipeline_limit;
+  const int ctas = lim > 0 && lim < net->sm_count ? lim : net->sm_count;
   const unsigned grid = (unsigned)(max_groups < ctas ? max_groups : ctas);
   net_rt_kernel<R, RtK><<<grid, RtK::kThreads, RtK::kTotal, st>>>(
       rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_weights,
