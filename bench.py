@@ -311,7 +311,7 @@ def engine_arm(args):
         n_evented = evented * SIMS_COUNT * halves
         avg_launch_s = net_s / max(1, n_evented)
         achieved_tflops = (my_leaf / max(1, n_net_launches)) * FLOP_PER_LEAF_C4 / avg_launch_s / 1e12 if net_s > 0 else 0.0
-        graph_launches = graphed * halves * (SIMS_COUNT * 5 + 1)  # per ply and part: 100 x (noise, select, plan, tower, expand+backup) + advance
+        graph_launches = graphed * (prof["launches"] / max(1, evented))  # the graph replays exactly the kernels of an evented ply
         line = {
             "metric": "connect4_mcts_leaf_evals_per_sec", "value": leaf / sec, "unit": "leaf_evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

@@ -130,7 +130,7 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   CARVE(q_order, "queue_order", uint8_t, dm.G, dm.B);
   CARVE(leaf_board, "leaf_board", Board, GB);
   CARVE(leaf_player, "leaf_player", uint8_t, GB);
-  CARVE(leaf_count, "leaf_count", int32_t, 1);
+  CARVE(leaf_count, "leaf_count", int32_t, 2);  // [0]: the stepwise API; the fused tree step alternates [0] / [1] by minibatch
   CARVE(noise, "noise", double, dm.G, dm.B, dm.A);
   CARVE(probs, "probs", float, GB, dm.A);
   CARVE(values, "values", float, GB);
@@ -487,6 +487,64 @@ static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_
   return rc;
 }
 
+// Fused variant of a search step for the self-play pipeline (Connect4, batch 8): ONE tree kernel per minibatch --
+// expand+backup of minibatch i-1, select and plan of minibatch i (tree_step_kernel) -- then the tower.  The expansion
+// of the LAST minibatch of a ply is issued by fused_flush.  Both streams may be the same.
+// Measured (bench.py, A/B on one box): select+plan fused 56.0 M leaf evals/s, all three fused 54.4 M (a warp expands its
+// four games one after the other), five separate kernels 56.0 M -- the kernel boundaries are not what makes the chain
+// slow next to a tower CTA, so the fused step stays an opt-in experiment: CARO_FUSED_TREE=1 (+ CARO_FUSE_EXPAND=1).
+static bool fused_ok(const caro_engine* e, int batch) {
+  static const bool on = getenv("CARO_FUSED_TREE") && atoi(getenv("CARO_FUSED_TREE")) != 0;
+  return on && e->cfg.game == CARO_GAME_CONNECT4 && batch == 8 && e->dm.A <= 8;
+}
+
+static int fused_step(caro_engine* e, caro_net* net, int i, int net_impl, cudaStream_t st, bool more) {
+  const int batch = 8;
+  View<C4Board> v = e->v_c4;
+  int32_t* counts = e->v_c4.leaf_count;
+  v.leaf_count = counts + (i & 1);
+  int rc = CARO_OK;
+  if (i == 0) {
+    cudaMemsetAsync(counts, 0, sizeof(int32_t), st);       // counts[0] may hold the previous ply's last value
+    rc = select_phase(e, batch, 0, 1, st);                 // this minibatch's noise (later ones are prefetched below)
+    e->launches += 1;
+  }
+  static const int fuse_expand = getenv("CARO_FUSE_EXPAND") ? atoi(getenv("CARO_FUSE_EXPAND")) : 0;
+  if (!fuse_expand && i > 0 && rc == CARO_OK) {  // expand+backup of the previous minibatch as its own kernel (one warp per game)
+    e->span_begin(3, st);
+    rc = caro_engine_expand_backup(e, batch, e->v_c4.probs, e->v_c4.values, st);
+    e->span_end(3, st);
+    e->launches += 1;
+  }
+  e->span_begin(0, st);
+  if (rc == CARO_OK) {
+    const unsigned grid = (unsigned)((e->dm.G + 15) / 16);
+    tree_step_kernel<C4Rules><<<grid, 128, 0, st>>>(v, C4Rules(), e->dm, e->sp, e->v_c4.noise, e->v_c4.probs, e->v_c4.values,
+                                                    (fuse_expand && i > 0) ? 1 : 0, counts + ((i + 1) & 1));
+    rc = caro_check_launch("tree_step_kernel");
+  }
+  e->span_end(0, st);
+  if (more && rc == CARO_OK) {
+    rc = select_phase(e, batch, i + 1, 1, st);             // next minibatch's noise, underneath this tower
+    e->launches += 1;
+  }
+  e->span_begin(2, st);
+  if (rc == CARO_OK)
+    rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, e->v_c4.leaf_board, e->v_c4.leaf_player, v.leaf_count,
+                          (int64_t)e->dm.G * batch, e->v_c4.probs, e->v_c4.values, net_impl, st);
+  e->span_end(2, st);
+  e->launches += 2;
+  return rc;
+}
+
+static int fused_flush(caro_engine* e, cudaStream_t st) {  // expand+backup of the ply's last minibatch
+  e->span_begin(3, st);
+  const int rc = caro_engine_expand_backup(e, 8, e->v_c4.probs, e->v_c4.values, st);
+  e->span_end(3, st);
+  e->launches += 1;
+  return rc;
+}
+
 extern "C" {
 
 int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl, void* stream) {
@@ -526,11 +584,16 @@ static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batc
       cudaStreamWaitEvent(s_net_lo[h], ev_f[h], 0);
     }
   }
+  bool fused = split == 1 && count > 0;
+  for (int h = 0; h < n; ++h) fused = fused && fused_ok(es[h], batch);
   for (int i = 0; i < count && rc == CARO_OK; ++i)
     for (int h = 0; h < n && rc == CARO_OK; ++h) {
-      if (split == 2) rc = search_step(es[h], net, i, batch, net_impl, s_tree_hi[h], s_net_lo[h], 1, i + 1 < count);
+      if (fused) rc = fused_step(es[h], net, i, net_impl, s_side[h], i + 1 < count);
+      else if (split == 2) rc = search_step(es[h], net, i, batch, net_impl, s_tree_hi[h], s_net_lo[h], 1, i + 1 < count);
       else rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);
     }
+  if (fused)
+    for (int h = 0; h < n && rc == CARO_OK; ++h) rc = fused_flush(es[h], s_side[h]);
   if (split == 2) {  // join back
     static cudaEvent_t ev_j[16] = {nullptr};
     for (int h = 0; h < n; ++h) {

@@ -305,12 +305,10 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
 // lane and the kernel becomes issue-bound (ncu: 12.7 M warp instructions per launch).  Here each lane owns a whole
 // descent and loops over the <= 16 actions; the arithmetic and its order are identical to select_kernel.
 template <class R, int ROWV>  // ROWV = Apad / 4 = number of 16-byte vectors per row
-__global__ void __launch_bounds__(128)
-select_thread_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
-                     const double* __restrict__ noise_in) {
+__device__ __forceinline__ void select_thread_body(const View<typename R::Board>& e, const R& rules, const Dims& dm,
+                                                   const SearchParams& sp, int batch, const double* __restrict__ noise_in,
+                                                   long long grp) {
   using Board = typename R::Board;
-  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (grp == 0) *e.leaf_count = 0;
   if (grp >= (long long)dm.G * batch) return;
   const int g = (int)(grp / batch), j = (int)(grp % batch);
   const size_t di = (size_t)g * dm.B + j;
@@ -424,6 +422,15 @@ select_thread_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams s
   e.d_slot[di] = -1;
 }
 
+template <class R, int ROWV>
+__global__ void __launch_bounds__(128)
+select_thread_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
+                     const double* __restrict__ noise_in) {
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp == 0) *e.leaf_count = 0;  // plan_kernel (next launch on the stream) accumulates into it
+  select_thread_body<R, ROWV>(e, rules, dm, sp, batch, noise_in, grp);
+}
+
 // ------------------------------------------------------------------------------------ plan
 // Serial variant (batch > 32), one thread per game: back-up queue = terminal descents in descent order, then the first
 // occurrence of every distinct new leaf (lib/mcts.py:265-278); unique leaves are appended to the
@@ -484,9 +491,7 @@ plan_serial_kernel(View<Board> e, Dims dm, int batch) {
 // Lane-parallel variant (batch <= 32): GP lanes per game, lane j owns descent j, so every load of the
 // per-descent records is issued at once instead of as a dependent chain.
 template <class Board, int GP>
-__global__ void __launch_bounds__(256)
-plan_kernel(View<Board> e, Dims dm, int batch) {
-  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void plan_body(const View<Board>& e, const Dims& dm, int batch, int gthread) {
   const int g = gthread / GP;
   const int j = threadIdx.x & (GP - 1);
   const int lane = threadIdx.x & 31;
@@ -548,6 +553,12 @@ plan_kernel(View<Board> e, Dims dm, int batch) {
     if (n_new) atomicAdd(e.ctr + CTR_LEAVES, (unsigned long long)n_new);
     atomicAdd(e.ctr + CTR_DESCENTS, (unsigned long long)batch);
   }
+}
+
+template <class Board, int GP>
+__global__ void __launch_bounds__(256)
+plan_kernel(View<Board> e, Dims dm, int batch) {
+  plan_body<Board, GP>(e, dm, batch, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // --------------------------------------------------------------------------- expand + backup
@@ -645,11 +656,9 @@ __device__ __forceinline__ void ht_insert_cas(HashSlot* __restrict__ ht, int cap
 //            (float32 W sums are order dependent), forwarding values between entries that hit the same edge,
 //            and stores each distinct edge once.
 template <class R, int BK>
-__global__ void __launch_bounds__(128)
-expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
-                     const float* __restrict__ values) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void expand_backup_body(const View<typename R::Board>& e, const Dims& dm, int batch,
+                                                   const float* __restrict__ probs, const float* __restrict__ values, int g,
+                                                   int lane) {
   if (g >= dm.G || e.status[g] != ST_ACTIVE) return;
   const int who0 = e.root_player[g];
   const int tree = g * dm.tpg + (dm.tpg == 2 ? who0 : 0);
@@ -757,6 +766,39 @@ expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float*
       }
     }
   }
+}
+
+template <class R, int BK>
+__global__ void __launch_bounds__(128)
+expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
+                     const float* __restrict__ values) {
+  expand_backup_body<R, BK>(e, dm, batch, probs, values, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------ fused tree step
+// expand+backup of minibatch i-1, then select and plan of minibatch i, for 16 games per block of 128 threads (batch = 8,
+// A <= 8).  The three phases only depend on each other PER GAME (a game's descents need its own tree updated, its plan
+// needs its own descents), so one kernel with two block-level barriers replaces three kernels with grid-wide
+// boundaries: inside the self-play pipeline the tree kernels run in the few warp slots a tower CTA leaves, in several
+// waves each, and every kernel boundary drained all of them -- the chain tower -> expand -> select -> plan -> tower, not
+// the tower, set the pipeline's period (tools/pipeline_trace.py).  The compact-leaf counter is double-buffered by
+// minibatch parity (e.leaf_count = this minibatch's, `other_count` = the next one's, zeroed here) because blocks
+// reach the plan phase at different times.
+template <class R>
+__global__ void __launch_bounds__(128)
+tree_step_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, const double* __restrict__ noise_in,
+                 const float* __restrict__ probs, const float* __restrict__ values, int do_expand, int32_t* other_count) {
+  constexpr int kBatch = 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (do_expand) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) expand_backup_body<R, 8>(e, dm, kBatch, probs, values, blockIdx.x * 16 + warp * 4 + k, lane);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *other_count = 0;
+  __syncthreads();
+  select_thread_body<R, 2>(e, rules, dm, sp, kBatch, noise_in, (long long)blockIdx.x * 128 + threadIdx.x);
+  __syncthreads();
+  plan_body<typename R::Board, 8>(e, dm, kBatch, blockIdx.x * 128 + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------ root policy

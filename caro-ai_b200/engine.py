@@ -118,7 +118,7 @@ class SelfPlayEngine:
         _cabi.check(_cabi.lib().caro_engine_plan(self.handle, batch, self._stream()))
 
     def leaf_count(self) -> int:
-        return int(self.region("leaf_count").item())
+        return int(self.region("leaf_count").reshape(-1)[0].item())
 
     def leaf_planes(self, count: Optional[int] = None) -> torch.Tensor:
         """float32 [L,2,H,W] planes of the compact leaf batch (== states_to_training_batch)."""

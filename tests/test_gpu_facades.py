@@ -347,8 +347,56 @@ def test_bench_engine_arm_prints_the_contract_line():
                 "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
         assert key in d, key
     assert d["metric"] == "connect4_mcts_leaf_evals_per_sec" and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 4
-    assert d["engine_errors"] == 0 and d["gpu_launches"] >= 4 * 100 * 2 * 5
+    assert d["engine_errors"] == 0 and d["gpu_launches"] >= 4 * 100 * 2 * 5  # noise, select, plan, tower, expand+backup per minibatch and part
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 512 * 17 == d["e2e"]["d2h_bytes_per_step"]
     r = d["roofline"]
     assert r["bound"] == "tensor" and 0 < r["frac"] < 1.5 and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert "workload" in d["config"] and d["dtype"] == "bf16" and d["scaling"] == "weak"
+
+
+def test_connect4_pipeline_fused_tree_step_matches_separate_kernels():
+    """Inside the parts pipeline Connect4 runs ONE tree kernel per minibatch (expand+backup of minibatch i-1, select and
+    plan of minibatch i: tree_step_kernel) with a double-buffered leaf counter; a single engine's play() runs the five
+    separate kernels.  Same seeds => the same games and bit-identical trees (N, W, Q, P), also with a number of games
+    that is not a multiple of the 16 games a block handles, and over a ply boundary with re-seated games."""
+    import torch
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import DeviceNet, Net
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    # the fused step is opt-in (environment, read once per process on first use): run the comparison in a child process
+    if os.environ.get("CARO_FUSED_TREE") != "1":
+        import subprocess
+        import sys
+        for fuse_expand in ("0", "1"):
+            env = dict(os.environ, CARO_FUSED_TREE="1", CARO_FUSE_EXPAND=fuse_expand)
+            out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k",
+                                  "test_connect4_pipeline_fused_tree_step_matches_separate_kernels"],
+                                 capture_output=True, text=True, timeout=900, env=env,
+                                 cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            assert out.returncode == 0 and "1 passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+        return
+    game = ConnectFour()
+    torch.manual_seed(0)
+    dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
+
+    def engines():
+        return [SelfPlayEngine(game, g, max_batch=8, node_capacity=4096, seed=77 + h) for h, g in enumerate((200, 131))]
+
+    for count in (12, 7):  # even and odd numbers of minibatches per ply (the leaf counter alternates by parity)
+        solo = engines()
+        for e in solo:
+            e.play(dn, dn, moves=9, count=count, batch=8, tau_plies=3, auto_restart=True)
+        pair = engines()
+        SelfPlayEngine.play_multi(pair, dn, moves=9, count=count, batch=8, tau_plies=3, auto_restart=True)
+        torch.cuda.synchronize()
+        for a, b in zip(solo, pair):
+            ca, cb = a.counters(), b.counters()
+            assert ca == cb and ca["errors"] == 0 and ca["leaf_evals"] > 0, (count, ca, cb)
+            assert a.roots() == b.roots()
+            for name in ("N", "W", "Q", "P", "node_count"):
+                assert torch.equal(a.region(name), b.region(name)), (count, name)
+        for e in solo + pair:
+            e.close()
+    dn.close()
