@@ -655,10 +655,14 @@ __device__ __forceinline__ void ht_insert_cas(HashSlot* __restrict__ ht, int cap
 //            N/W of its edge in EVERY queued path up front, then replays the queue IN ORDER in registers
 //            (float32 W sums are order dependent), forwarding values between entries that hit the same edge,
 //            and stores each distinct edge once.
-template <class R, int BK>
+template <class R, int BK, int GW = 32>  // GW lanes per game (BK <= GW): 32 = one warp per game, 8 = four games per warp
 __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>& e, const Dims& dm, int batch,
                                                    const float* __restrict__ probs, const float* __restrict__ values, int g,
-                                                   int lane) {
+                                                   int lane32) {
+  static_assert(BK <= GW, "one lane per queue entry");
+  const int lane = lane32 & (GW - 1);           // lane within the game's group
+  const int gbase = lane32 & ~(GW - 1);         // first warp lane of the group
+  const unsigned gmask = group_mask<GW>();
   if (g >= dm.G || e.status[g] != ST_ACTIVE) return;
   const int who0 = e.root_player[g];
   const int tree = g * dm.tpg + (dm.tpg == 2 ? who0 : 0);
@@ -682,7 +686,7 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
       my_val = e.d_value[d0 + my_di];
     }
   }
-  const unsigned exp_m = __ballot_sync(0xffffffffu, my_kind == KIND_EXPAND);
+  const unsigned exp_m = (__ballot_sync(gmask, my_kind == KIND_EXPAND) >> gbase) & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
   const int n_new = __popc(exp_m);
   int my_node = count0 + __popc(exp_m & ((1u << lane) - 1u));
   const bool creates = my_kind == KIND_EXPAND && my_node < dm.node_cap;
@@ -696,36 +700,36 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
   }
   // rows of the new nodes, all lanes cooperating
   for (int q = 0; q < qn; ++q) {
-    const bool cr = __shfl_sync(0xffffffffu, (int)creates, q) != 0;
+    const bool cr = __shfl_sync(gmask, (int)creates, gbase + q) != 0;
     if (!cr) continue;
-    const int node = __shfl_sync(0xffffffffu, my_node, q);
-    const int slot = __shfl_sync(0xffffffffu, my_slot, q);
+    const int node = __shfl_sync(gmask, my_node, gbase + q);
+    const int slot = __shfl_sync(gmask, my_slot, gbase + q);
     const size_t row = (nb + (size_t)node) * dm.Apad;
-    for (int a = lane; a < dm.Apad; a += 32) {
+    for (int a = lane; a < dm.Apad; a += GW) {
       e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
       e.N[row + a] = 0;
       e.W[row + a] = 0.0f;
       e.Q[row + a] = 0.0f;
       e.C[row + a] = -1;
     }
-    for (int w = lane; w < dm.FW; w += 32) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
+    for (int w = lane; w < dm.FW; w += GW) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
   }
   if (lane == 0) e.node_count[tree] = min(count0 + n_new, dm.node_cap);
   // ---- phase 2: _backup, lib/mcts.py:225-246 ---------------------------------------------------------
   int max_len = my_len;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, off));
-  for (int i0 = 0; i0 < max_len; i0 += 32) {
+  for (int off = GW / 2; off > 0; off >>= 1) max_len = max(max_len, __shfl_xor_sync(gmask, max_len, off));
+  for (int i0 = 0; i0 < max_len; i0 += GW) {
     const int i = i0 + lane;
     long long idx[BK];
     int n_v[BK];
     float w_v[BK], cur[BK];
 #pragma unroll
     for (int q = 0; q < BK; ++q) {
-      const int di = __shfl_sync(0xffffffffu, my_di, q);
-      const int len = __shfl_sync(0xffffffffu, my_len, q);
-      const float v = __shfl_sync(0xffffffffu, my_val, q);
-      const int kind = __shfl_sync(0xffffffffu, my_kind, q);
+      const int di = __shfl_sync(gmask, my_di, gbase + q);
+      const int len = __shfl_sync(gmask, my_len, gbase + q);
+      const float v = __shfl_sync(gmask, my_val, gbase + q);
+      const int kind = __shfl_sync(gmask, my_kind, gbase + q);
       idx[q] = -1;
       n_v[q] = 0;
       w_v[q] = 0.0f;
@@ -773,6 +777,17 @@ __global__ void __launch_bounds__(128)
 expand_backup_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
                      const float* __restrict__ values) {
   expand_backup_body<R, BK>(e, dm, batch, probs, values, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
+}
+
+// Eight lanes per game (action rows of <= 8 entries, batch <= 8: Connect4): four games per warp, a quarter of the warps of
+// the warp-per-game kernel for the same work.  The tree kernels of the self-play pipeline run in the few warp slots
+// a tower CTA leaves free (+ 16 SMs of their own), where the number of warps, not the work, sets their time.
+template <class R>
+__global__ void __launch_bounds__(128)
+expand_backup_group8_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
+                            const float* __restrict__ values) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  expand_backup_body<R, 8, 8>(e, dm, batch, probs, values, t >> 3, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------ fused tree step

@@ -355,10 +355,12 @@ def test_bench_engine_arm_prints_the_contract_line():
 
 
 def test_connect4_pipeline_fused_tree_step_matches_separate_kernels():
-    """Inside the parts pipeline Connect4 runs ONE tree kernel per minibatch (expand+backup of minibatch i-1, select and
-    plan of minibatch i: tree_step_kernel) with a double-buffered leaf counter; a single engine's play() runs the five
-    separate kernels.  Same seeds => the same games and bit-identical trees (N, W, Q, P), also with a number of games
-    that is not a multiple of the 16 games a block handles, and over a ply boundary with re-seated games."""
+    """The parts pipeline vs a single engine's play() (five separate kernels, expand+backup with one warp per game): same
+    seeds => the same games and bit-identical trees (N, W, Q, P), also with a number of games that is not a multiple of
+    the 16 games a block handles, and over ply boundaries with re-seated games.  Checked for the default pipeline
+    (expand+backup with eight lanes per game) and, in child processes, for the opt-in fused tree step (expand+backup of
+    minibatch i-1, select and plan of minibatch i in ONE kernel, double-buffered leaf counter), with and without the
+    expansion inside the fused kernel."""
     import torch
     from caro_ai_b200.engine import SelfPlayEngine
     from caro_ai_b200.game import ConnectFour
@@ -376,7 +378,7 @@ def test_connect4_pipeline_fused_tree_step_matches_separate_kernels():
                                  capture_output=True, text=True, timeout=900, env=env,
                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
             assert out.returncode == 0 and "1 passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
-        return
+    # in this process: the default pipeline (separate tree kernels, expand+backup with eight lanes per game) vs play()
     game = ConnectFour()
     torch.manual_seed(0)
     dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
