@@ -95,12 +95,10 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   const int64_t GB = (int64_t)dm.G * dm.B;
   auto P = [&](size_t off) { return base ? base + off : (char*)nullptr; };
 #define CARVE(field, name, type, ...) v->field = reinterpret_cast<type*>(P(c.add(name, sizeof(type), __VA_ARGS__)))
-  CARVE(N, "N", int32_t, nodes, dm.Apad);
-  CARVE(W, "W", float, nodes, dm.Apad);
-  CARVE(Q, "Q", float, nodes, dm.Apad);
-  CARVE(P, "P", float, nodes, dm.Apad);
-  CARVE(C, "C", int32_t, nodes, dm.Apad);
-  CARVE(flags, "flags", uint32_t, nodes, dm.FW);
+  CARVE(N, "nodes", int32_t, nodes, 4, dm.Apad);  // node records: rows [N | W | P | C] (engine.cuh)
+  v->W = reinterpret_cast<float*>(v->N) + dm.Apad;
+  v->P = reinterpret_cast<float*>(v->N) + 2 * dm.Apad;
+  v->C = v->N + 3 * dm.Apad;
   CARVE(key_hi, "key_hi", uint64_t, nodes);
   CARVE(node_board, "node_board", Board, nodes);
   CARVE(node_player, "node_player", uint8_t, nodes);
@@ -166,7 +164,7 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
   dm->B = cfg->max_batch;
   dm->A = A;
   dm->Apad = (A + 7) & ~7;
-  dm->FW = (A + 31) / 32;
+  dm->RS = 4 * dm->Apad;
   dm->node_cap = cfg->node_capacity;
   dm->hash_cap = round_pow2(2 * cfg->node_capacity);
   dm->max_depth = plies;

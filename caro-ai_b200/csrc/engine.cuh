@@ -1,5 +1,6 @@
-// Device-side data layout of the self-play engine: SoA node pools with per-game arenas, a
-// per-arena open-addressing transposition table, per-descent records and the compact leaf batch.
+// Device-side data layout of the self-play engine: node records with per-game arenas (structure of arrays inside
+// a node: [N | W | P | child link] rows, one 128-byte line per Connect4 node), a per-arena open-addressing
+// transposition table, per-descent records and the compact leaf batch.
 //
 // Replaces the four `state_int -> list[A]` dicts of lib/mcts.py:29-36 and the Python queues of
 // lib/mcts.py:259-287.  See DESIGN.md section 4 for the byte budget.
@@ -12,6 +13,8 @@ namespace caro {
 enum : uint8_t { KIND_SKIP = 0, KIND_TERMINAL = 1, KIND_EXPAND = 2 };
 enum : uint8_t { ST_ACTIVE = 0, ST_FINISHED = 1 };
 enum { CTR_LEAVES = 0, CTR_GAMES, CTR_PLIES, CTR_WIN0, CTR_WIN1, CTR_DRAW, CTR_DESCENTS, CTR_ERRORS, CTR_COUNT };
+constexpr int kNetBit = (int)0x80000000u;   // flag bit inside an N word
+constexpr int kCountMask = 0x7fffffff;
 enum : unsigned long long { ERR_ARENA_FULL = 1ull, ERR_REPLAY_OVERRUN = 2ull, ERR_ILLEGAL_ACTION = 4ull };
 
 struct alignas(16) HashSlot {
@@ -25,8 +28,8 @@ struct Dims {
   int tpg;        // trees per game
   int B;          // max descents per minibatch (stride of per-descent arrays)
   int A;          // actions
-  int Apad;       // row stride of N/W/Q/P (A rounded up to 8)
-  int FW;         // flag words per node = ceil(A/32)
+  int Apad;       // entries per row of a node record (A rounded up to 8)
+  int RS;         // 32-bit words per node record = 4 * Apad: [N | W | P | C] rows of Apad entries each
   int node_cap;   // nodes per arena
   int hash_cap;   // slots per arena (power of two, 2x node_cap)
   int max_depth;  // path stride = max plies of the game
@@ -42,13 +45,16 @@ struct SearchParams {
 template <class Board>
 struct View {
   // ---- tree arenas (index = tree * node_cap + node) --------------------------------------
-  int32_t* N;          // [trees*node_cap][Apad]  visit counts            (lib/mcts.py:30)
-  float* W;            // [..][Apad]              total value             (lib/mcts.py:32)
-  float* Q;            // [..][Apad]              mean value, f32(W/N)    (lib/mcts.py:34)
-  float* P;            // [..][Apad]              priors                  (lib/mcts.py:36)
-  int32_t* C;          // [..][Apad]  cached child node per edge (-1 = not linked yet): a pure cache of the
-                       //             transposition lookup, so an interior step of a descent is ONE dependent access
-  uint32_t* flags;     // [..][FW] bit a: W(s,a) has absorbed a float32 net value (numpy promotion state)
+  // One record of RS = 4 * Apad words per node, rows [N | W | P | C]; the four pointers below address row 0 / 1 / 2 / 3
+  // of record 0, so X[(nb + node) * RS + a] is entry a of row X.  A Connect4 record is one aligned 128-byte line: a
+  // descent step reads exactly that line, a back-up touches its first 64 bytes, an expansion writes it whole.
+  int32_t* N;          // visit counts (lib/mcts.py:30) in bits 0..30; bit 31 (kNetBit): W(s,a) has absorbed a float32
+                       // network value (numpy promotion state of the reference's python-float / np.float32 sums)
+  float* W;            // total value (lib/mcts.py:32).  The mean value Q (lib/mcts.py:34) is not stored: it always
+                       // equals f32(W / N) (0 while N == 0) and is recomputed where it is read
+  float* P;            // priors (lib/mcts.py:36)
+  int32_t* C;          // cached child node per edge (-1 = not linked yet): a pure cache of the
+                       // transposition lookup, so an interior step of a descent is ONE dependent access
   uint64_t* key_hi;    // [..]  upper 64 fingerprint bits (m,n,k only)
   Board* node_board;   // [..]  position of the node (export / dict views)
   uint8_t* node_player;  // [..] side to move when the node was created

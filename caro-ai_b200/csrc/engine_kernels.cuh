@@ -177,24 +177,29 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   uint8_t* path_action = e.d_path_action + di * dm.max_depth;
 
   while (node >= 0) {
-    const size_t row = (nb + (size_t)node) * dm.Apad;
+    const size_t row = (nb + (size_t)node) * dm.RS;
     int n_loc[APL], c_loc[APL];
-    float q_loc[APL], p_loc[APL];
+    float w_loc[APL], q_loc[APL], p_loc[APL];
+    bool net_loc[APL];
     int sum_n = 0;
 #pragma unroll
     for (int i = 0; i < APL; ++i) {
       const int a = gl + i * GW;
       if (a < A) {
-        n_loc[i] = e.N[row + a];
-        q_loc[i] = e.Q[row + a];
+        const int raw = e.N[row + a];
+        n_loc[i] = raw & kCountMask;
+        net_loc[i] = raw < 0;
+        w_loc[i] = e.W[row + a];
         p_loc[i] = e.P[row + a];
         c_loc[i] = e.C[row + a];
       } else {
         n_loc[i] = 0;
-        q_loc[i] = 0.0f;
+        net_loc[i] = false;
+        w_loc[i] = 0.0f;
         p_loc[i] = 0.0f;
         c_loc[i] = -1;
       }
+      q_loc[i] = n_loc[i] > 0 ? __fdiv_rn(w_loc[i], (float)n_loc[i]) : 0.0f;  // value_avg, lib/mcts.py:244
       sum_n += n_loc[i];
     }
 #pragma unroll
@@ -219,8 +224,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
           const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq), (double)(1 + n_loc[i]));
           // Q keeps python-float (float64) precision until a float32 value touched W(s,a)
           double q64 = (double)q_loc[i];
-          const bool f32 = (e.flags[(nb + (size_t)node) * dm.FW + (a >> 5)] >> (a & 31)) & 1u;
-          if (!f32 && n_loc[i] > 0) q64 = __ddiv_rn((double)e.W[row + a], (double)n_loc[i]);
+          if (!net_loc[i] && n_loc[i] > 0) q64 = __ddiv_rn((double)w_loc[i], (double)n_loc[i]);
           const double sc = __dadd_rn(q64, u);
           if (sc > best) {
             best = sc;
@@ -334,36 +338,43 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
   int32_t* path_node = e.d_path_node + di * dm.max_depth;
   uint8_t* path_action = e.d_path_action + di * dm.max_depth;
   while (node >= 0) {
-    const size_t row = (nb + (size_t)node) * dm.Apad;
+    const size_t row = (nb + (size_t)node) * dm.RS;  // the record [N | W | P | C]: 16 * ROWV consecutive words
     int n_loc[ROWV * 4], c_loc[ROWV * 4];
-    float q_loc[ROWV * 4], p_loc[ROWV * 4];
+    float w_loc[ROWV * 4], p_loc[ROWV * 4];
 #pragma unroll
     for (int v = 0; v < ROWV; ++v) {
       const int4 nv = reinterpret_cast<const int4*>(e.N + row)[v];
-      const float4 qv = reinterpret_cast<const float4*>(e.Q + row)[v];
+      const float4 wv = reinterpret_cast<const float4*>(e.W + row)[v];
       const float4 pv = reinterpret_cast<const float4*>(e.P + row)[v];
       const int4 cv = reinterpret_cast<const int4*>(e.C + row)[v];
       n_loc[4 * v] = nv.x; n_loc[4 * v + 1] = nv.y; n_loc[4 * v + 2] = nv.z; n_loc[4 * v + 3] = nv.w;
-      q_loc[4 * v] = qv.x; q_loc[4 * v + 1] = qv.y; q_loc[4 * v + 2] = qv.z; q_loc[4 * v + 3] = qv.w;
+      w_loc[4 * v] = wv.x; w_loc[4 * v + 1] = wv.y; w_loc[4 * v + 2] = wv.z; w_loc[4 * v + 3] = wv.w;
       p_loc[4 * v] = pv.x; p_loc[4 * v + 1] = pv.y; p_loc[4 * v + 2] = pv.z; p_loc[4 * v + 3] = pv.w;
       c_loc[4 * v] = cv.x; c_loc[4 * v + 1] = cv.y; c_loc[4 * v + 2] = cv.z; c_loc[4 * v + 3] = cv.w;
     }
+    unsigned net_bits = 0u;  // bit a: W(s,a) has absorbed a float32 value (bit 31 of the N word)
     int sum_n = 0;
 #pragma unroll
-    for (int a = 0; a < ROWV * 4; ++a) sum_n += (a < A) ? n_loc[a] : 0;
+    for (int a = 0; a < ROWV * 4; ++a) {
+      net_bits |= (n_loc[a] < 0 ? 1u : 0u) << a;
+      n_loc[a] &= kCountMask;
+      sum_n += (a < A) ? n_loc[a] : 0;
+    }
     double best = -INFINITY;
     int best_a = 0, best_c = -1;
     if (depth == 0) {  // root: Dirichlet noise + float64 scores (lib/mcts.py:48-62,131-132)
       const double sq = sqrt((double)sum_n);
-      const uint32_t fl = e.flags[(nb + (size_t)node) * dm.FW];
       const double* z = noise_in + ((size_t)g * batch + j) * A;
 #pragma unroll
       for (int a = 0; a < ROWV * 4; ++a) {
         if (a < A && rules.legal(s, a)) {
           const double pn = __dadd_rn((double)__fmul_rn(keep_f, p_loc[a]), __dmul_rn(sp.explore, z[a]));
           const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq), (double)(1 + n_loc[a]));
-          double q64 = (double)q_loc[a];
-          if (!((fl >> a) & 1u) && n_loc[a] > 0) q64 = __ddiv_rn((double)e.W[row + a], (double)n_loc[a]);
+          // Q keeps python-float (float64) precision until a float32 value touched W(s,a)
+          double q64 = 0.0;
+          if (n_loc[a] > 0)
+            q64 = ((net_bits >> a) & 1u) ? (double)__fdiv_rn(w_loc[a], (float)n_loc[a])
+                                         : __ddiv_rn((double)w_loc[a], (double)n_loc[a]);
           const double sc = __dadd_rn(q64, u);
           if (sc > best) {
             best = sc;
@@ -379,7 +390,8 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
       for (int a = 0; a < ROWV * 4; ++a) {
         if (a < A && rules.legal(s, a)) {
           const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p_loc[a]), sq), (float)(1 + n_loc[a]));
-          const float sc = __fadd_rn(q_loc[a], t);
+          const float q = n_loc[a] > 0 ? __fdiv_rn(w_loc[a], (float)n_loc[a]) : 0.0f;  // value_avg, lib/mcts.py:244
+          const float sc = __fadd_rn(q, t);
           if (sc > bestf) {
             bestf = sc;
             best_a = a;
@@ -591,15 +603,13 @@ expand_backup_serial_kernel(View<typename R::Board> e, Dims dm, int batch, const
       from_net = true;
       if (count < dm.node_cap) {  // _create_node, lib/mcts.py:178-190
         const int node = count++;
-        const size_t row = (nb + (size_t)node) * dm.Apad;
+        const size_t row = (nb + (size_t)node) * dm.RS;
         for (int a = lane; a < dm.Apad; a += 32) {
           e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
           e.N[row + a] = 0;
           e.W[row + a] = 0.0f;
-          e.Q[row + a] = 0.0f;
           e.C[row + a] = -1;
         }
-        for (int w = lane; w < dm.FW; w += 32) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
         if (lane == 0) {
           e.node_board[nb + node] = e.d_board[di];
           e.node_player[nb + node] = e.d_player[di];
@@ -618,14 +628,10 @@ expand_backup_serial_kernel(View<typename R::Board> e, Dims dm, int batch, const
     const uint8_t* pa = e.d_path_action + di * dm.max_depth;
     for (int i = lane; i < d; i += 32) {
       const int a = pa[i];
-      const size_t idx = (nb + (size_t)pn[i]) * dm.Apad + a;
+      const size_t idx = (nb + (size_t)pn[i]) * dm.RS + a;
       const float cur = ((d - 1 - i) & 1) ? v : -v;
-      const int n = e.N[idx] + 1;
-      const float w = __fadd_rn(e.W[idx], cur);
-      e.N[idx] = n;
-      e.W[idx] = w;
-      e.Q[idx] = __fdiv_rn(w, (float)n);
-      if (from_net) e.flags[(nb + (size_t)pn[i]) * dm.FW + (a >> 5)] |= 1u << (a & 31);
+      e.N[idx] = (e.N[idx] + 1) | (from_net ? kNetBit : 0);
+      e.W[idx] = __fadd_rn(e.W[idx], cur);
     }
     __syncwarp();
   }
@@ -704,15 +710,13 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
     if (!cr) continue;
     const int node = __shfl_sync(gmask, my_node, gbase + q);
     const int slot = __shfl_sync(gmask, my_slot, gbase + q);
-    const size_t row = (nb + (size_t)node) * dm.Apad;
+    const size_t row = (nb + (size_t)node) * dm.RS;
     for (int a = lane; a < dm.Apad; a += GW) {
-      e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
       e.N[row + a] = 0;
       e.W[row + a] = 0.0f;
-      e.Q[row + a] = 0.0f;
+      e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
       e.C[row + a] = -1;
     }
-    for (int w = lane; w < dm.FW; w += GW) e.flags[(nb + (size_t)node) * dm.FW + w] = 0u;
   }
   if (lane == 0) e.node_count[tree] = min(count0 + n_new, dm.node_cap);
   // ---- phase 2: _backup, lib/mcts.py:225-246 ---------------------------------------------------------
@@ -722,7 +726,7 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
   for (int i0 = 0; i0 < max_len; i0 += GW) {
     const int i = i0 + lane;
     long long idx[BK];
-    int n_v[BK];
+    int n_v[BK], net[BK];
     float w_v[BK], cur[BK];
 #pragma unroll
     for (int q = 0; q < BK; ++q) {
@@ -732,17 +736,18 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
       const int kind = __shfl_sync(gmask, my_kind, gbase + q);
       idx[q] = -1;
       n_v[q] = 0;
+      net[q] = 0;
       w_v[q] = 0.0f;
       cur[q] = 0.0f;
       if (q < qn && i < len) {
         const size_t pi = (d0 + di) * dm.max_depth + i;
         const int node = e.d_path_node[pi];
         const int a = e.d_path_action[pi];
-        idx[q] = (long long)((nb + (size_t)node) * dm.Apad + a);
+        idx[q] = (long long)((nb + (size_t)node) * dm.RS + a);
         n_v[q] = e.N[idx[q]];
         w_v[q] = e.W[idx[q]];
         cur[q] = ((len - 1 - i) & 1) ? v : -v;
-        if (kind == KIND_EXPAND) atomicOr(e.flags + (nb + (size_t)node) * dm.FW + (a >> 5), 1u << (a & 31));
+        net[q] = kind == KIND_EXPAND ? kNetBit : 0;
       }
     }
 #pragma unroll
@@ -754,7 +759,7 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
           n_v[q] = n_v[p];
           w_v[q] = w_v[p];
         }
-      n_v[q] += 1;
+      n_v[q] = (n_v[q] + 1) | net[q];  // the count lives in bits 0..30, so the +1 never reaches the flag bit
       w_v[q] = __fadd_rn(w_v[q], cur[q]);
     }
 #pragma unroll
@@ -766,7 +771,6 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
       if (last) {
         e.N[idx[q]] = n_v[q];
         e.W[idx[q]] = w_v[q];
-        e.Q[idx[q]] = __fdiv_rn(w_v[q], (float)n_v[q]);
       }
     }
   }
@@ -846,12 +850,12 @@ __global__ void root_policy_kernel(View<typename R::Board> e, R rules, Dims dm, 
     }
     return;
   }
-  const size_t row = (nb + (size_t)node) * dm.Apad;
+  const size_t row = (nb + (size_t)node) * dm.RS;
   const int tau = tau_mode == 2 ? (e.ply[g] < tau_plies ? 1 : 0) : tau_mode;
   long long total = 0;
   int best_n = -1, best_a = 0;
   for (int a = 0; a < A; ++a) {
-    const int n = e.N[row + a];
+    const int n = e.N[row + a] & kCountMask;
     total += n;
     if (n > best_n) {
       best_n = n;
@@ -859,9 +863,9 @@ __global__ void root_policy_kernel(View<typename R::Board> e, R rules, Dims dm, 
     }
   }
   for (int a = 0; a < A; ++a) {
-    const int n = e.N[row + a];
+    const int n = e.N[row + a] & kCountMask;
     if (pi) pi[(size_t)g * A + a] = tau == 0 ? (a == best_a ? 1.0 : 0.0) : __ddiv_rn((double)n, (double)total);
-    if (qout) qout[(size_t)g * A + a] = e.Q[row + a];
+    if (qout) qout[(size_t)g * A + a] = n > 0 ? __fdiv_rn(e.W[row + a], (float)n) : 0.0f;  // value_avg, lib/mcts.py:244
     if (nout) nout[(size_t)g * A + a] = n;
   }
 }
@@ -887,10 +891,10 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
   // visit counts -> pi
   long long total = 0;
   int best_n = -1, best_a = 0;
-  const size_t row = (nb + (size_t)(node < 0 ? 0 : node)) * dm.Apad;
+  const size_t row = (nb + (size_t)(node < 0 ? 0 : node)) * dm.RS;
   if (node >= 0) {
     for (int a = 0; a < A; ++a) {
-      const int n = e.N[row + a];
+      const int n = e.N[row + a] & kCountMask;
       total += n;
       if (n > best_n) {
         best_n = n;
@@ -911,11 +915,11 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
   int action = best_a;
   if (tau != 0 && total > 0) {
     double last = 0.0;
-    for (int a = 0; a < A; ++a) last = __dadd_rn(last, __ddiv_rn((double)e.N[row + a], (double)total));
+    for (int a = 0; a < A; ++a) last = __dadd_rn(last, __ddiv_rn((double)(e.N[row + a] & kCountMask), (double)total));
     double c = 0.0;
     action = A - 1;
     for (int a = 0; a < A; ++a) {
-      c = __dadd_rn(c, __ddiv_rn((double)e.N[row + a], (double)total));
+      c = __dadd_rn(c, __ddiv_rn((double)(e.N[row + a] & kCountMask), (double)total));
       if (__ddiv_rn(c, last) > u) {
         action = a;
         break;
@@ -931,7 +935,7 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
   for (int a = 0; a < A; ++a) {
     float p;
     if (tau == 0 || total <= 0) p = (a == best_a) ? 1.0f : 0.0f;
-    else p = (float)__ddiv_rn((double)e.N[row + a], (double)total);
+    else p = (float)__ddiv_rn((double)(e.N[row + a] & kCountMask), (double)total);
     e.hist_pi[h * A + a] = p;
   }
   if (!rules.legal(s, action)) atomicOr(e.ctr + CTR_ERRORS, ERR_ILLEGAL_ACTION);  // "Impossible action selected"

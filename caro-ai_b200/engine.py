@@ -72,6 +72,32 @@ class SelfPlayEngine:
     def fregion(self, name: str) -> torch.Tensor:
         return self.region(name).view(torch.float32)
 
+    def pool(self, name: str, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+        """Rows [lo, hi) of one statistic of the node records (region "nodes": int32 [nodes, 4, Apad], rows N | W | P | C,
+        csrc/engine.cuh): "N" visit counts, "W" total values, "P" priors, "C" cached child links, "f32" (bool: bit 31 of
+        the N word, W has absorbed a float32 network value) and "Q" = f32(W / N) (0 where N == 0), which the engine does
+        not store but recomputes with exactly this division wherever lib/mcts.py reads value_avg."""
+        rec = self.region("nodes")
+        rows = rec[lo:rec.shape[0] if hi is None else hi]
+        raw = rows[:, 0, :]
+        if name == "N":
+            return raw & 0x7FFFFFFF
+        if name == "f32":
+            return raw < 0
+        if name == "W":
+            return rows[:, 1, :].contiguous().view(torch.float32)
+        if name == "P":
+            return rows[:, 2, :].contiguous().view(torch.float32)
+        if name == "C":
+            return rows[:, 3, :]
+        if name == "Q":  # IEEE float32 division on the host (numpy), the same rounding as __fdiv_rn
+            n = (raw & 0x7FFFFFFF).cpu().numpy()
+            w = rows[:, 1, :].contiguous().view(torch.float32).cpu().numpy()
+            q = np.zeros_like(w)
+            np.divide(w, n.astype(np.float32), out=q, where=n > 0)
+            return torch.from_numpy(q)
+        raise KeyError(name)
+
     def close(self):
         if getattr(self, "handle", None):
             _cabi.lib().caro_engine_destroy(self.handle)
@@ -235,16 +261,16 @@ class SelfPlayEngine:
         cap = self.cfg.node_capacity
         lo, hi = tree * cap, tree * cap + n_nodes
         A = self.A
-        N = self.region("N")[lo:hi, :A].cpu().numpy()
-        W = self.fregion("W")[lo:hi, :A].cpu().numpy()
-        Q = self.fregion("Q")[lo:hi, :A].cpu().numpy()
-        P = self.fregion("P")[lo:hi, :A].cpu().numpy()
-        F = self.region("flags")[lo:hi].cpu().numpy().view(np.uint32)
+        N = self.pool("N", lo, hi)[:, :A].cpu().numpy()
+        W = self.pool("W", lo, hi)[:, :A].cpu().numpy()
+        Q = self.pool("Q", lo, hi)[:, :A].numpy()
+        P = self.pool("P", lo, hi)[:, :A].cpu().numpy()
+        F = self.pool("f32", lo, hi)[:, :A].cpu().numpy()
         boards = self.region("node_board")[lo:hi].cpu().numpy().view(np.uint64)
         states = self.game.states_from_boards(boards)
         out = {}
         for i, s in enumerate(states):
-            f32 = [bool((int(F[i, a >> 5]) >> (a & 31)) & 1) for a in range(A)]
+            f32 = [bool(F[i, a]) for a in range(A)]
             out[s] = {"N": N[i].tolist(), "W": W[i].copy(), "Q": Q[i].copy(), "P": P[i].copy(), "f32": f32}
         return out
 

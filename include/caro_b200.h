@@ -147,7 +147,9 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
 void caro_engine_destroy(caro_engine* e);
 
 /* Offset/size of a named region of the workspace (for zero-copy views from the host language):
- * "N","W","Q","P","flags","node_board","node_count","root_board","root_player","status","ply",
+ * "nodes" (int32 [nodes][4][Apad]: one record per node with rows N | W | P | cached child link; bit 31 of an N word =
+ * "W has absorbed a float32 network value"; Q = f32(W / N) is not stored), "node_board","node_count","root_board",
+ * "root_player","status","ply",
  * "result","leaf_board","leaf_player","leaf_count","desc_kind","desc_value","desc_board",
  * "desc_player","desc_path_len","desc_path_node","desc_path_action","desc_slot","queue_len",
  * "queue_order","counters","replay_board","replay_player","replay_pi","replay_z","replay_cursor".

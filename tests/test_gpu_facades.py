@@ -235,15 +235,11 @@ def test_full_size_properties():
     assert int(nodes.sum()) == c["leaf_evals"]          # every evaluated leaf became exactly one node
     assert nodes.min() > C_ and nodes.max() <= C_ * B * plies
     # per-node algebra on a sample of arenas: Q == f32(W / N), N >= 0, priors form a distribution
-    N = eng.region("N")
-    W = eng.fregion("W")
-    Q = eng.fregion("Q")
-    P = eng.fregion("P")
     cap = eng.cfg.node_capacity
     for g in (0, 17, 4095):
         n_nodes = int(nodes[g])
-        sl = slice(g * cap, g * cap + n_nodes)
-        n, w, q, p = N[sl, :7].cpu().numpy(), W[sl, :7].cpu().numpy(), Q[sl, :7].cpu().numpy(), P[sl, :7].cpu().numpy()
+        lo, hi = g * cap, g * cap + n_nodes
+        n, w, q, p = (eng.pool(name, lo, hi)[:, :7].cpu().numpy() for name in ("N", "W", "Q", "P"))
         assert (n >= 0).all()
         np.testing.assert_array_equal(q[n > 0], (w[n > 0] / n[n > 0].astype(np.float32)).astype(np.float32))
         assert (q[n == 0] == 0).all() and (w[n == 0] == 0).all()
@@ -258,7 +254,7 @@ def test_full_size_properties():
     for e in (eng2, eng3):
         e.play(dn, dn, moves=4, count=12, batch=B, tau_plies=10, auto_restart=True)
     assert eng2.roots() == eng3.roots()
-    assert torch.equal(eng2.region("N")[: 64 * 2048], eng3.region("N")[: 64 * 2048])
+    assert torch.equal(eng2.region("nodes")[: 64 * 2048], eng3.region("nodes")[: 64 * 2048])
 
 
 def test_finished_games_replay_and_restart():
@@ -322,7 +318,7 @@ def test_caro_pipeline_parts_do_not_share_head_scratch():
     for a, b in zip(solo, pair):
         assert a.counters() == b.counters() and a.counters()["errors"] == 0
         assert a.roots() == b.roots()
-        assert torch.equal(a.region("N"), b.region("N")) and torch.equal(a.region("P"), b.region("P"))
+        assert torch.equal(a.region("nodes"), b.region("nodes"))  # every record: N (+ float32 bit), W, P, child links
     dn.close()
 
 
@@ -397,7 +393,7 @@ def test_connect4_pipeline_fused_tree_step_matches_separate_kernels():
             ca, cb = a.counters(), b.counters()
             assert ca == cb and ca["errors"] == 0 and ca["leaf_evals"] > 0, (count, ca, cb)
             assert a.roots() == b.roots()
-            for name in ("N", "W", "Q", "P", "node_count"):
+            for name in ("nodes", "node_count"):
                 assert torch.equal(a.region(name), b.region(name)), (count, name)
         for e in solo + pair:
             e.close()
