@@ -95,9 +95,10 @@ class _DeviceGame(BaseGame):
         d_out = torch.empty_like(d_boards)
         d_won = torch.empty(count, dtype=torch.uint8, device="cuda")
         d_draw = torch.empty(count, dtype=torch.uint8, device="cuda")
-        _cabi.check(_cabi.lib().caro_boards_apply(self.game_kind, self.n, self.k, d_boards.data_ptr(), d_act.data_ptr(),
-                                                  d_pl.data_ptr(), count, d_out.data_ptr(), d_won.data_ptr(),
-                                                  d_draw.data_ptr(), self._stream(torch)))
+        if count:  # an empty torch tensor has a null data pointer, which the C ABI rejects
+            _cabi.check(_cabi.lib().caro_boards_apply(self.game_kind, self.n, self.k, d_boards.data_ptr(), d_act.data_ptr(),
+                                                      d_pl.data_ptr(), count, d_out.data_ptr(), d_won.data_ptr(),
+                                                      d_draw.data_ptr(), self._stream(torch)))
         new_states = self.states_from_boards(d_out.cpu().numpy().view(np.uint64))
         return new_states, d_won.cpu().numpy(), d_draw.cpu().numpy()
 
@@ -108,11 +109,12 @@ class _DeviceGame(BaseGame):
         words = (self.action_space + 31) // 32
         d_boards = torch.from_numpy(self.boards_from_states(states).view(np.int64)).cuda()
         d_mask = torch.empty((count, words), dtype=torch.int32, device="cuda")
-        _cabi.check(_cabi.lib().caro_boards_legal_mask(self.game_kind, self.n, self.k, d_boards.data_ptr(), count,
-                                                       d_mask.data_ptr(), self._stream(torch)))
+        if count:
+            _cabi.check(_cabi.lib().caro_boards_legal_mask(self.game_kind, self.n, self.k, d_boards.data_ptr(), count,
+                                                           d_mask.data_ptr(), self._stream(torch)))
         m = d_mask.cpu().numpy().view(np.uint32)
         bits = (m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
-        return bits.reshape(count, -1)[:, :self.action_space].astype(bool)
+        return bits.reshape(count, words * 32)[:, :self.action_space].astype(bool)
 
     def planes_device(self, d_boards, d_who, count: int):
         """float32 CUDA tensor [count, 2, H, W] from device boards (int64 view) + uint8 movers."""
