@@ -203,7 +203,11 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
     cudaMemcpyAsync(noise_out, noise, sizeof(double) * (size_t)groups * A, cudaMemcpyDeviceToDevice, st);
   }
 #define SELECT(GW, APL) select_kernel<R, GW, APL><<<grid(GW), 256, 0, st>>>(v, rules, dm, sp, batch, src)
-  if (A <= 8) select_thread_kernel<R, 2><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
+  // more descents than the GPU holds at once (5 blocks of 90-register threads per SM): the 72-register build keeps 7 blocks
+  // per SM resident (-20 % at 16 k games, -12 % at 64 k; a few spilled words; CARO_SELECT_DENSE=0 switches it off)
+  static const bool dense = !(getenv("CARO_SELECT_DENSE") && atoi(getenv("CARO_SELECT_DENSE")) == 0);
+  if (A <= 8 && dense && groups > 128ll * 5 * 148) select_thread_dense_kernel<R, 2, 7><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
+  else if (A <= 8) select_thread_kernel<R, 2><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
   else if (A <= 16) select_thread_kernel<R, 4><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
   else if (A <= 32) SELECT(32, 1);
   else if (A <= 64) SELECT(32, 2);

@@ -443,6 +443,17 @@ select_thread_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams s
   select_thread_body<R, ROWV>(e, rules, dm, sp, batch, noise_in, grp);
 }
 
+// The same descent with at most 64 registers (8 blocks per SM instead of 5): for launches of more descents than fit the
+// GPU at once, where the number of resident warps, not the latency of one descent, sets the kernel's duration.
+template <class R, int ROWV, int BPS>
+__global__ void __launch_bounds__(128, BPS)
+select_thread_dense_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
+                           const double* __restrict__ noise_in) {
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp == 0) *e.leaf_count = 0;
+  select_thread_body<R, ROWV>(e, rules, dm, sp, batch, noise_in, grp);
+}
+
 // ------------------------------------------------------------------------------------ plan
 // Serial variant (batch > 32), one thread per game: back-up queue = terminal descents in descent order, then the first
 // occurrence of every distinct new leaf (lib/mcts.py:265-278); unique leaves are appended to the
