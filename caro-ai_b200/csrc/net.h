@@ -53,7 +53,7 @@ struct caro_net {
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
-  alignas(16) float h_rt_consts[6 * 64 + 3 * 64 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
+  alignas(16) float h_rt_consts[6 * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
   float* d_headfeat;    // large boards: exported 1x1 head-convolution sums [leaf][3][HW] for heads_kernel (net_tc.cu)

@@ -72,6 +72,7 @@ constexpr int kRtBlocksNet = kRtRegionsNet * kRtRegionBlocks;             // 66 
 constexpr int kRtLayers = 1 + kBlocks;
 constexpr uint32_t kRtTmemCols = 512;
 constexpr uint32_t kRtLoCol = 384;                           // e5m2 lo residual: tile y at 384 + 16 y
+constexpr int kRtConstFcFloats = 1536;                       // FC weights that travel in the kernel parameters
 constexpr int kRtHeadFloats = 2016;                          // max nb * 3 * H * W (16 Connect4 boards)
 constexpr int kRtFcFloats = 928;                             // max nb * (20 + A) (32 3x3 boards)
 
@@ -89,6 +90,11 @@ struct RtConsts {
   float bias[kRtLayers * 64];   // folded conv biases
   float headw[3 * 64];          // 1x1 head convolutions: value, policy 0, policy 1
   float headb[4];               // their (folded) biases
+  // transposed FC weights, policy [2 HW][A] then value FC1 [HW][20], when they fit (Connect4: 1,428 floats): the FC heads
+  // then read their weights through the constant cache too; read from shared memory they were a quarter of the
+  // kernel's LSU wavefronts, on the pipe that bounds the tower
+  float fcw[kRtConstFcFloats];
+  int fc_in_const, pad_[3];
 };
 
 // CP = channel parts of the epilogue (2 -> 8 epilogue warps x 32 channels, 4 -> 16 warps x 16 channels)
@@ -152,12 +158,47 @@ __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t w) { return make_flo
 template <int TEAM, int BAR>
 __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s, float* fc_s,
                                       float hb0, float hb1, float hb2, const float* fcv, const float* polw, const float* valw,
-                                      float* __restrict__ probs, float* __restrict__ values) {
+                                      float* __restrict__ probs, float* __restrict__ values, const RtConsts& consts) {
   // fcv (shared memory): value FC1 bias [20], value FC2 weights [20], value FC2 bias [1], policy FC bias [A]
   const int HW = gm.H * gm.W, A = gm.A;
   const int per_board = 20 + A;
   float* hid = fc_s;  // [nb][20] value hidden units, logits behind them
   float* logit = fc_s + gm.nb * 20;
+  if (consts.fc_in_const && gm.nb == 16) {
+    // Weights from the constant cache: a warp works on two outputs (i, i + 1) for all 16 boards at once (lane = board +
+    // 16 * (output & 1)), so a weight is one of two constant addresses per instruction and a feature one conflict-free
+    // shared-memory wavefront (boards are 3 HW floats apart); bias + LeakyReLU of the 1x1 convolutions on the fly.  The
+    // summation order of every output is that of the general path below (four partial sums by cell index mod 4).
+    const int lane = ttid & 31, b = lane & 15, odd = lane >> 4;
+    const int vpairs = 10, ppairs = (A + 1) >> 1;
+    const float* fb = headf_s + (size_t)b * 3 * HW;
+#pragma unroll 1
+    for (int item = ttid >> 5; item < vpairs + ppairs; item += TEAM / 32) {
+      const bool is_val = item < vpairs;
+      const int i = is_val ? 2 * item + odd : 2 * (item - vpairs) + odd;   // output index within its head
+      const bool live = b < nvalid && (is_val || i < A);
+      const int stride = is_val ? 20 : A;
+      const int woff = (is_val ? 2 * HW * A : 0) + (live ? i : 0);
+      const int n = is_val ? HW : 2 * HW;
+      const float* f = is_val ? fb : fb + HW;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      auto feat = [&](int c) { return lrelu_tc(f[c] + (is_val ? hb0 : (c < HW ? hb1 : hb2))); };
+      int c = 0;
+#pragma unroll 2
+      for (; c + 3 < n; c += 4) {
+        a0 = fmaf(consts.fcw[woff + c * stride], feat(c), a0);
+        a1 = fmaf(consts.fcw[woff + (c + 1) * stride], feat(c + 1), a1);
+        a2 = fmaf(consts.fcw[woff + (c + 2) * stride], feat(c + 2), a2);
+        a3 = fmaf(consts.fcw[woff + (c + 3) * stride], feat(c + 3), a3);
+      }
+      for (; c < n; ++c) a0 = fmaf(consts.fcw[woff + c * stride], feat(c), a0);
+      const float acc = (a0 + a1) + (a2 + a3);
+      if (live) {
+        if (is_val) hid[b * 20 + i] = lrelu_tc(fcv[i] + acc);
+        else logit[b * A + i] = fcv[41 + i] + acc;
+      }
+    }
+  } else {
 #pragma unroll 1
   for (int b = 0; b < nvalid; ++b) {  // bias + LeakyReLU of the 1x1 head convolutions, in place
     float* fb = headf_s + (size_t)b * 3 * HW;
@@ -186,6 +227,7 @@ __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long le
     const float acc = (a0 + a1) + (a2 + a3);
     if (is_val) hid[b * 20 + i] = lrelu_tc(fcv[i] + acc);
     else logit[b * A + (i - 20)] = fcv[41 + (i - 20)] + acc;
+  }
   }
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
 #pragma unroll 1
@@ -333,7 +375,9 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     const int fcw_floats = HW * (2 * gm.A + 20);
     const float* polw = pol_fc_t;
     const float* valw = val_fc1_t;
-    if (fcv_floats + fcw_floats <= K::kFcWFloats) {  // both transposed matrices are contiguous in global memory (net_tc.cu pack)
+    if (consts.fc_in_const && nb == 16) {
+      // the FC weights come through the constant cache (rt_heads): nothing to stage
+    } else if (fcv_floats + fcw_floats <= K::kFcWFloats) {  // both transposed matrices are contiguous in global memory (net_tc.cu pack)
       float* fcw_s = fcv + fcv_floats;
       for (int i = htid; i < fcw_floats; i += K::kHeadThreads) fcw_s[i] = pol_fc_t[i];
       polw = fcw_s;
@@ -345,7 +389,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const int nvalid = (int)min((long long)nb, count - leaf0);
       mbar_wait_relaxed(bar_feat + 0, (uint32_t)gi & 1u);
       rt_heads<K::kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, fc_s, consts.headb[0], consts.headb[1], consts.headb[2], fcv, polw,
-                                   valw, probs, values);
+                                   valw, probs, values, consts);
       mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
       if (htid == 0) TC_TRACE(5, gi);
     }
@@ -355,7 +399,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const int nvalid = (int)min((long long)nb, count - leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
       rt_heads<K::kEpiThreads + K::kHeadThreads, 3>(gm, nvalid, leaf0, K::kEpiThreads + htid, headf_s, fc_s, consts.headb[0],
-                                                    consts.headb[1], consts.headb[2], fcv, polw, valw, probs, values);
+                                                    consts.headb[1], consts.headb[2], fcv, polw, valw, probs, values, consts);
       if (htid == 0) TC_TRACE(5, gi);
     }
   } else if (warp == K::kLoadWarp) {
@@ -636,7 +680,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         const float* polw = staged ? fcv + fcv_floats : pol_fc_t;
         const float* valw = staged ? fcv + fcv_floats + 2 * HW * gm.A : val_fc1_t;
         rt_heads<K::kEpiThreads + K::kHeadThreads, 3>(gm, nvalid, leaf0, tid, headf_s, fc_s, consts.headb[0], consts.headb[1],
-                                                      consts.headb[2], fcv, polw, valw, probs, values);
+                                                      consts.headb[2], fcv, polw, valw, probs, values, consts);
       }
     }
   }
@@ -707,6 +751,18 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
   hc->headb[1] = h[L.pol_conv_b];
   hc->headb[2] = h[L.pol_conv_b + 1];
   hc->headb[3] = 0.0f;
+  {
+    const int HW = net->H * net->W, A = net->A;
+    const int n = HW * (2 * A + 20);
+    hc->fc_in_const = n <= kRtConstFcFloats ? 1 : 0;
+    for (int i = 0; i < kRtConstFcFloats; ++i) hc->fcw[i] = 0.0f;
+    if (hc->fc_in_const) {  // the layout of caro_net::d_pol_fc_t (net_tc.cu): policy [2 HW][A], then value FC1 [HW][20]
+      for (int a = 0; a < A; ++a)
+        for (int i = 0; i < 2 * HW; ++i) hc->fcw[(size_t)i * A + a] = h[L.pol_fc_w + (size_t)a * 2 * HW + i];
+      for (int i = 0; i < 20; ++i)
+        for (int c = 0; c < HW; ++c) hc->fcw[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
+    }
+  }
   cudaError_t ce = cudaSuccess;
   if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
