@@ -154,3 +154,30 @@ def test_all_games_finished_is_a_no_op():
     assert c1 == c0 and eng.leaf_count() == 0
     eng.close()
     dn.close()
+
+
+def test_large_launch_select_matches_small_launch():
+    """More descents per launch than fit the GPU at once (> 94,720) take the 72-register build of the select kernel: the
+    first 64 of 12,288 games must grow exactly the trees of a 64-game engine with the same seed (Philox streams are
+    addressed by game, the network's result for a leaf does not depend on the batch it travels in)."""
+    import torch
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour
+    from caro_ai_b200.model import DeviceNet, Net
+    g = ConnectFour()
+    torch.manual_seed(0)
+    dn = DeviceNet(Net(g.obs_shape, g.action_space).eval(), g)
+    cap = 128
+    big = SelfPlayEngine(g, 12288, max_batch=8, node_capacity=cap, seed=21)
+    small = SelfPlayEngine(g, 64, max_batch=8, node_capacity=cap, seed=21)
+    for e in (big, small):
+        e.search(dn, 6, 8)
+    torch.cuda.synchronize()
+    assert big.counters()["errors"] == 0 and small.counters()["errors"] == 0
+    assert big.roots()[1][:64] == small.roots()[1]
+    assert torch.equal(big.region("node_count")[:64], small.region("node_count")[:64])
+    assert int(small.region("node_count").min().item()) > 6
+    assert torch.equal(big.region("nodes")[: 64 * cap], small.region("nodes")[: 64 * cap])
+    big.close()
+    small.close()
+    dn.close()
