@@ -136,7 +136,7 @@ noise_kernel(const uint64_t* __restrict__ uid_g, const int32_t* __restrict__ ply
 // ---------------------------------------------------------------------------------- select
 // One group of GW lanes per descent, APL actions per lane (action = lane + i*GW).
 template <class R, int GW, int APL>
-__global__ void __launch_bounds__(256, (APL == 1 && sizeof(typename R::Board) <= 16) ? 7 : 1)
+__global__ void __launch_bounds__(256, (APL == 1 && sizeof(typename R::Board) <= 16) ? 7 : (APL == 8 ? 2 : 1))
 select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch,
               const double* __restrict__ noise_in) {
   using Board = typename R::Board;
@@ -179,7 +179,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   while (node >= 0) {
     const size_t row = (nb + (size_t)node) * dm.RS;
     int n_loc[APL], c_loc[APL];
-    float w_loc[APL], q_loc[APL], p_loc[APL];
+    float w_loc[APL], p_loc[APL];
     bool net_loc[APL];
     int sum_n = 0;
 #pragma unroll
@@ -199,7 +199,6 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
         p_loc[i] = 0.0f;
         c_loc[i] = -1;
       }
-      q_loc[i] = n_loc[i] > 0 ? __fdiv_rn(w_loc[i], (float)n_loc[i]) : 0.0f;  // value_avg, lib/mcts.py:244
       sum_n += n_loc[i];
     }
 #pragma unroll
@@ -223,8 +222,9 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
           const double pn = __dadd_rn((double)__fmul_rn(keep_f, p_loc[i]), __dmul_rn(sp.explore, z[i]));
           const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq), (double)(1 + n_loc[i]));
           // Q keeps python-float (float64) precision until a float32 value touched W(s,a)
-          double q64 = (double)q_loc[i];
-          if (!net_loc[i] && n_loc[i] > 0) q64 = __ddiv_rn((double)w_loc[i], (double)n_loc[i]);
+          double q64 = 0.0;  // value_avg (lib/mcts.py:244) is not stored: f32(W/N), or the float64 quotient of a python-float edge
+          if (n_loc[i] > 0)
+            q64 = net_loc[i] ? (double)__fdiv_rn(w_loc[i], (float)n_loc[i]) : __ddiv_rn((double)w_loc[i], (double)n_loc[i]);
           const double sc = __dadd_rn(q64, u);
           if (sc > best) {
             best = sc;
@@ -242,7 +242,8 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
         const int a = gl + i * GW;
         if (a < A && rules.legal(s, a)) {
           const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p_loc[i]), sq), (float)(1 + n_loc[i]));
-          const double sc = (double)__fadd_rn(q_loc[i], t);
+          const float q = n_loc[i] > 0 ? __fdiv_rn(w_loc[i], (float)n_loc[i]) : 0.0f;  // value_avg, lib/mcts.py:244
+          const double sc = (double)__fadd_rn(q, t);
           if (sc > best) {
             best = sc;
             best_a = a;
