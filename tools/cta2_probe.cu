@@ -133,14 +133,18 @@ probe_kernel(const __nv_bfloat16* __restrict__ a_img,   // [CTAS][kK/8][128][8]
 
 // The tower's operand footprint: activations as 8 chunks of 800 rows (chunk stride 12,800 B), 12 weight blocks of 6 KB, one
 // tile = 12 MMAs (3 horizontal taps x 4 k-steps) accumulating into one 192-column range.  Timing only (operands are zeros).
-__global__ void __launch_bounds__(128)
-tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int rotate) {
+__global__ void __launch_bounds__(448)
+tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int rotate, int spinners, int commit_per_tile) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int kActRows = 800, kChunk = kActRows * 16, kBlock = 6144;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * kChunk + 12 * kBlock);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  for (int i = threadIdx.x; i < (8 * kChunk + 12 * kBlock) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) mbar_init(bar, 1);
+  for (int i = threadIdx.x; i < (8 * kChunk + 12 * kBlock) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  uint64_t* tile_bar = bar + 2;  // [8] per-tile commit targets (nobody waits on them; phases just keep flipping)
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(tile_bar + i, 1);
+  }
   fence_async_smem();
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -167,29 +171,35 @@ tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int
         const uint64_t bd = b0 + (uint64_t)(i * (kBlock / 16));
         umma_bf16(d, ad, bd, idesc, 1u);
       }
+      if (commit_per_tile) {
+        umma_commit(tile_bar + (t & 7));
+        if (commit_per_tile > 1) tc_fence_after();
+      }
     }
     umma_commit(bar);
     mbar_wait(bar, 0);
     cycles[blockIdx.x] = clock64() - t0;
+  } else if (warp >= 2 && warp < 2 + spinners) {
+    mbar_wait(bar, 0);  // like the tower's epilogue warps while they have nothing to do: spin on mbarrier.try_wait
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-static void run_tower_tile(int n, int dxs, int rotate) {
+static void run_tower_tile(int n, int dxs, int rotate, int spinners = 0, int commit_per_tile = 0) {
   const int ctas = 148, tiles = 600;
   long long* dc;
   cudaMalloc(&dc, ctas * 8);
-  const size_t smem = 8 * 800 * 16 + 12 * 6144 + 64;
+  const size_t smem = 8 * 800 * 16 + 12 * 6144 + 128;
   cudaFuncSetAttribute(tower_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tower_tile_kernel<<<ctas, 128, smem>>>(dc, n, dxs, tiles, rotate);
+  tower_tile_kernel<<<ctas, 448, smem>>>(dc, n, dxs, tiles, rotate, spinners, commit_per_tile);
   const cudaError_t err = cudaDeviceSynchronize();
   std::vector<long long> cyc(ctas);
   cudaMemcpy(cyc.data(), dc, ctas * 8, cudaMemcpyDeviceToHost);
   long long mx = 0;
   for (auto v : cyc) mx = v > mx ? v : mx;
-  printf("tower tile footprint: N=%d, horizontal step %d rows, %s: %.1f cycles per MMA (%s)\n", n, dxs,
-         rotate ? "tiles 0..3 in turn" : "one tile", (double)mx / (tiles * 12), cudaGetErrorString(err));
+  printf("tower tile footprint: N=%d, horizontal step %d rows, %s, %d warps spinning on an mbarrier, commit per tile %d: %.1f cycles per MMA (%s)\n", n, dxs,
+         rotate ? "tiles 0..3 in turn" : "one tile", spinners, commit_per_tile, (double)mx / (tiles * 12), cudaGetErrorString(err));
   cudaFree(dc);
 }
 
@@ -292,6 +302,13 @@ int main() {
   run_tower_tile(192, 16, 0);
   run_tower_tile(192, 16, 1);
   run_tower_tile(128, 16, 1);
+  run_tower_tile(192, 1, 1, 8);
+  run_tower_tile(128, 1, 1, 8);
+  run_tower_tile(192, 1, 1, 12);
+  run_tower_tile(128, 1, 1, 12);
+  run_tower_tile(192, 1, 1, 8, 1);
+  run_tower_tile(128, 1, 1, 8, 1);
+  run_tower_tile(192, 1, 1, 8, 2);
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad;
 }

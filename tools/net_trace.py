@@ -36,7 +36,7 @@ def main():
     for kind in range(8):
         for idx in range(1000):
             v = int(t[kind * 1000 + idx])
-            if v:
+            if v and not (kind == 7 and idx >= 4):  # trace[7998], trace[7999] are mode flags, not stamps
                 ev.append((v, kind, idx))
     ev.sort()
     t0 = ev[0][0]
