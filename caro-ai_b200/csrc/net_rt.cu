@@ -253,6 +253,31 @@ __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long le
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");  // hid / logit / features are reused by the next group
 }
 
+// mbarrier wait / tcgen05.commit on a 32-bit shared-memory ADDRESS: the MMA warp's loop keeps its barriers as addresses, so that
+// no generic -> shared conversion (an S2UR of the shared window + 64-bit arithmetic per barrier) sits between two tiles, where the
+// issuing thread's time is not hidden by queued MMAs (tools/cta2_probe.cu: ~95 cycles next to a commit, ~265 elsewhere)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // The MMAs of one source tile.  POS: 0 = first board row (no out[-1]: B slot 0 is skipped, the accumulators of
 // out[0], out[1] are overwritten by the first MMA; it is also the tile that waits for the weight blocks to land),
 // 1 = interior row (N = 192; the very first MMA is split so that out[y+1] is overwritten while out[y-1], out[y]
@@ -260,17 +285,18 @@ __device__ __noinline__ void rt_heads(const RtGeom& gm, int nvalid, long long le
 // tile base and the TMEM addresses is a compile-time constant, so that the MMAs issue back to back.
 template <int POS, bool FIRST>
 __device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
-                                              uint32_t d_new, uint64_t* full0, uint64_t* full1, uint32_t ph0, uint32_t ph1,
-                                              uint64_t* empty0, uint64_t* empty1, uint64_t* next_bar, uint64_t* next_bar2, uint32_t next_par) {
+                                              uint32_t d_new, uint32_t full0, uint32_t full1, uint32_t ph0, uint32_t ph1,
+                                              uint32_t empty0, uint32_t empty1, uint32_t next_bar, uint32_t next_bar2, uint32_t next_par) {
+  // all barriers are shared-memory addresses; next_bar / next_bar2 == 0: nothing to poll
   constexpr int NB = FIRST ? 3 : 12;
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int dx = FIRST ? i - 1 : i / 4 - 1, kk = FIRST ? 0 : i % 4;
-    if (POS == 0) mbar_wait(i < 6 ? full0 + i : full1 + (i - 6), i < 6 ? ph0 : ph1);  // first use of the block in this layer
+    if (POS == 0) mbar_wait_a(i < 6 ? full0 + 8u * i : full1 + 8u * (i - 6), i < 6 ? ph0 : ph1);  // first use of the block in this layer
     // the barrier the NEXT tile needs is polled while this tile's MMAs are still queued in the tensor pipe
-    if (i == (FIRST ? 1 : 8) && next_bar != nullptr) {
-      mbar_wait(next_bar, next_par);
-      if (next_bar2 != nullptr) mbar_wait(next_bar2, next_par);
+    if (i == (FIRST ? 1 : 8) && next_bar != 0u) {
+      mbar_wait_a(next_bar, next_par);
+      if (next_bar2 != 0u) mbar_wait_a(next_bar2, next_par);
     }
     if (elected) {
       const uint64_t ad = a_tile + (uint64_t)(int64_t)(dx + kk * 2 * kRtActRows);
@@ -281,7 +307,7 @@ __device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile,
       } else {
         umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc(192) : rt_idesc(128), (POS == 0 && i == 0) ? 0u : 1u);
       }
-      if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit(i < 6 ? empty0 : empty1);
+      if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit_a(i < 6 ? empty0 : empty1);
     }
   }
 }
@@ -434,6 +460,14 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
     const uint64_t a_desc0 = make_desc(smem_u32(act) + (uint32_t)kRtHalo * 16u, (uint32_t)kRtChunkBytes, 128u);
     const uint64_t b_desc0 = make_desc(smem_u32(wgt), 192u * 16u, 128u);
+    uint32_t full_a = smem_u32(bar_full), empty_a = smem_u32(bar_empty), acc_a = smem_u32(bar_acc), act_a = smem_u32(bar_act);
+    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(acc_a), "+r"(act_a));  // opaque: not re-derived from the CTA's shared window per tile
+    // the timeline's condition is evaluated once: between two tiles every instruction of this warp is exposed
+    const bool tr = elected && trace != nullptr && blockIdx.x == 0;
+#define RT_MMA_TRACE(kind, idx)                                                 \
+  do {                                                                          \
+    if (tr && (idx) < 1000) trace[(kind) * 1000 + (idx)] = clock64();           \
+  } while (0)
     const int total_layers = my_groups * kRtLayers;
     int reg = 0;
     uint32_t rphase = 0;
@@ -441,20 +475,20 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     bool pre_waited = false;
     for (int gl = 0; gl < total_layers; ++gl) {
       const uint32_t par = (uint32_t)gl & 1u;
-      if (elected) TC_TRACE(6, gl * 2);      // layer iteration entered
+      RT_MMA_TRACE(6, gl * 2);      // layer iteration entered
       const bool first = layer == 0;
       const uint64_t rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
-      uint64_t* full0 = bar_full + reg * kRtRegionBlocks;
-      uint64_t* empty0 = bar_empty + reg;
+      const uint32_t full0 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
+      const uint32_t empty0 = empty_a + 8u * (uint32_t)reg;
       const uint32_t ph0 = rphase;
       if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
       uint64_t rb1 = rb0;
-      uint64_t *full1 = full0, *empty1 = empty0;
+      uint32_t full1 = full0, empty1 = empty0;
       uint32_t ph1 = ph0;
       if (!first) {
         rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
-        full1 = bar_full + reg * kRtRegionBlocks;
-        empty1 = bar_empty + reg;
+        full1 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
+        empty1 = empty_a + 8u * (uint32_t)reg;
         ph1 = rphase;
         if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
       }
@@ -463,12 +497,12 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         // tile y reads act[y] and writes out[y-1..y+1]: it needs the barriers of tiles y-1, y, y+1 at this stage.
         // All but the first tile's were already polled while the previous tile's MMAs were being issued.
         if (y == 0 && !pre_waited) {
-          mbar_wait(bar_act + 0, par);
-          mbar_wait(bar_act + 1, par);
+          mbar_wait_a(act_a, par);
+          mbar_wait_a(act_a + 8u, par);
         }
-        if (elected && y == 0) TC_TRACE(6, gl * 2 + 1);  // first tile: barriers passed
+        if (y == 0) RT_MMA_TRACE(6, gl * 2 + 1);  // first tile: barriers passed
         tc_fence_after();  // orders this tile's MMAs after the barrier observations (also the early ones)
-        if (elected) TC_TRACE(0, gl * 8 + y);
+        RT_MMA_TRACE(0, gl * 8 + y);
         const uint64_t a_tile = a_desc0 + (uint64_t)(uint32_t)(y * 128);
         // keep the 24 weight descriptors of the layer from being hoisted in front of the tile loop (110 uniform-datapath
         // instructions during which the tensor pipe ran dry at every layer start): recomputed per tile, they interleave
@@ -478,14 +512,14 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         // D columns: out[y-1] | out[y] | out[y+1]; the first tile has no out[-1], the last no out[H]
         const uint32_t d_main = tmem_base + (uint32_t)(y == 0 ? 0 : (y - 1) * 64);
         const uint32_t d_new = tmem_base + (uint32_t)((y + 1) * 64);
-        uint64_t *nb0 = nullptr, *nb1 = nullptr;
+        uint32_t nb0 = 0u, nb1 = 0u;
         uint32_t npar = par;
         if (y + 2 < H) {
-          nb0 = bar_act + y + 2;  // for tile y+1
+          nb0 = act_a + 8u * (uint32_t)(y + 2);  // for tile y+1
         } else if (y == H - 1 && H >= 4 && gl + 1 < total_layers) {
           // next layer's first tile: its barriers depend on commits issued two or more tiles ago (H >= 4)
-          nb0 = bar_act + 0;
-          nb1 = bar_act + 1;
+          nb0 = act_a;
+          nb1 = act_a + 8u;
           npar = par ^ 1u;
         }
         if (first) {
@@ -497,15 +531,14 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           else if (y == H - 1) rt_issue_tile<2, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
           else rt_issue_tile<1, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
         }
-        if (elected) {
-          umma_commit(bar_acc + y);
-          TC_TRACE(1, gl * 8 + y);
-        }
+        if (elected) umma_commit_a(acc_a + 8u * (uint32_t)y);
+        RT_MMA_TRACE(1, gl * 8 + y);
         __syncwarp();
       }
       pre_waited = H >= 4 && gl + 1 < total_layers;
       if (++layer == kRtLayers) layer = 0;
     }
+#undef RT_MMA_TRACE
   } else {
     // ========================================= epilogue warps =========================================
     const int quarter = warp & 3, cp = warp >> 2;

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -133,8 +134,11 @@ probe_kernel(const __nv_bfloat16* __restrict__ a_img,   // [CTAS][kK/8][128][8]
 
 // The tower's operand footprint: activations as 8 chunks of 800 rows (chunk stride 12,800 B), 12 weight blocks of 6 KB, one
 // tile = 12 MMAs (3 horizontal taps x 4 k-steps) accumulating into one 192-column range.  Timing only (operands are zeros).
+// GAP_AT (compile time, so that the other positions carry no extra instruction): where the issuing thread spends `gap` cycles
+// elsewhere -- after MMA GAP_AT of every tile, 12 = between the last MMA and the commit, 13 = after the commit, -1 = nowhere.
+template <int GAP_AT>
 __global__ void __launch_bounds__(448)
-tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int rotate, int spinners, int commit_per_tile) {
+tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int rotate, int spinners, int commit_per_tile, int gap) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int kActRows = 800, kChunk = kActRows * 16, kBlock = 6144;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * kChunk + 12 * kBlock);
@@ -170,10 +174,22 @@ tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int
         const uint64_t ad = a_tile + (uint64_t)(int64_t)(dx * dxs + kk * 2 * kActRows);
         const uint64_t bd = b0 + (uint64_t)(i * (kBlock / 16));
         umma_bf16(d, ad, bd, idesc, 1u);
+        if (GAP_AT == i) {  // the issuing thread is busy elsewhere for `gap` cycles in the middle of a tile
+          const long long g0 = clock64();
+          while (clock64() - g0 < gap) {}
+        }
+      }
+      if (GAP_AT == 12) {  // ... or between the tile's last MMA and its commit
+        const long long g0 = clock64();
+        while (clock64() - g0 < gap) {}
       }
       if (commit_per_tile) {
         umma_commit(tile_bar + (t & 7));
         if (commit_per_tile > 1) tc_fence_after();
+      }
+      if (GAP_AT == 13) {  // ... or after the commit, where the tower's tile loop has its ~300-cycle loop head
+        const long long g0 = clock64();
+        while (clock64() - g0 < gap) {}
       }
     }
     umma_commit(bar);
@@ -186,20 +202,27 @@ tower_tile_kernel(long long* __restrict__ cycles, int n, int dxs, int tiles, int
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-static void run_tower_tile(int n, int dxs, int rotate, int spinners = 0, int commit_per_tile = 0) {
+static void run_tower_tile(int n, int dxs, int rotate, int spinners = 0, int commit_per_tile = 0, int gap = 0, int gap_at = -1) {
   const int ctas = 148, tiles = 600;
   long long* dc;
   cudaMalloc(&dc, ctas * 8);
   const size_t smem = 8 * 800 * 16 + 12 * 6144 + 128;
-  cudaFuncSetAttribute(tower_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tower_tile_kernel<<<ctas, 448, smem>>>(dc, n, dxs, tiles, rotate, spinners, commit_per_tile);
+  auto launch = [&](auto at) {
+    constexpr int AT = decltype(at)::value;
+    cudaFuncSetAttribute(tower_tile_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tower_tile_kernel<AT><<<ctas, 448, smem>>>(dc, n, dxs, tiles, rotate, spinners, commit_per_tile, gap);
+  };
+  if (gap_at == 5) launch(std::integral_constant<int, 5>{});
+  else if (gap_at == 12) launch(std::integral_constant<int, 12>{});
+  else if (gap_at == 13) launch(std::integral_constant<int, 13>{});
+  else launch(std::integral_constant<int, -1>{});
   const cudaError_t err = cudaDeviceSynchronize();
   std::vector<long long> cyc(ctas);
   cudaMemcpy(cyc.data(), dc, ctas * 8, cudaMemcpyDeviceToHost);
   long long mx = 0;
   for (auto v : cyc) mx = v > mx ? v : mx;
-  printf("tower tile footprint: N=%d, horizontal step %d rows, %s, %d warps spinning on an mbarrier, commit per tile %d: %.1f cycles per MMA (%s)\n", n, dxs,
-         rotate ? "tiles 0..3 in turn" : "one tile", spinners, commit_per_tile, (double)mx / (tiles * 12), cudaGetErrorString(err));
+  printf("tower tile footprint: N=%d, horizontal step %d rows, %s, %d warps spinning on an mbarrier, commit per tile %d, issuing thread away for %d cycles at position %d: %.1f cycles per MMA, %.0f per tile (%s)\n", n, dxs,
+         rotate ? "tiles 0..3 in turn" : "one tile", spinners, commit_per_tile, gap, gap_at, (double)mx / (tiles * 12), (double)mx / tiles, cudaGetErrorString(err));
   cudaFree(dc);
 }
 
@@ -309,6 +332,15 @@ int main() {
   run_tower_tile(192, 1, 1, 8, 1);
   run_tower_tile(128, 1, 1, 8, 1);
   run_tower_tile(192, 1, 1, 8, 2);
+  // how deep is the MMA queue?  a gap of the issuing thread is hidden only while queued MMAs keep the tensor pipe busy
+  for (int n : {192, 128})
+    for (int gap : {0, 100, 200, 300, 500}) {
+      run_tower_tile(n, 1, 1, 8, 0, gap, 5);    // mid-tile, no per-tile commit
+      run_tower_tile(n, 1, 1, 8, 1, gap, 5);    // mid-tile, commit per tile
+      run_tower_tile(n, 1, 1, 8, 1, gap, 12);   // between the last MMA and the commit
+      run_tower_tile(n, 1, 1, 8, 1, gap, 13);   // after the commit (the tower's loop head)
+      run_tower_tile(n, 1, 1, 8, 0, gap, 13);   // same place without a commit
+    }
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad;
 }
