@@ -21,7 +21,7 @@
 //     the 1e-3 contract;
 //   * weights stream through three 36 KB regions (half a layer = six 6 KB blocks of one (horizontal tap, k-step)
 //     each): layer L occupies two, the first half of L+1 is prefetched into the third; cp.async.bulk + one "full"
-//     mbarrier per block by a producer warp, one "empty" mbarrier per region arrived by tcgen05.commit when the
+//     mbarrier per region by a producer warp, one "empty" mbarrier per region arrived by tcgen05.commit when the
 //     layer's last tile has used it;
 //   * biases and 1x1 head weights come through the constant cache (__grid_constant__ struct), the last layer
 //     stores every head feature exactly once (tiles split by parity between the two channel halves): no
@@ -292,7 +292,7 @@ __device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile,
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int dx = FIRST ? i - 1 : i / 4 - 1, kk = FIRST ? 0 : i % 4;
-    if (POS == 0) mbar_wait_a(i < 6 ? full0 + 8u * i : full1 + 8u * (i - 6), i < 6 ? ph0 : ph1);  // first use of the block in this layer
+    if (POS == 0 && (i == 0 || i == 6)) mbar_wait_a(i < 6 ? full0 : full1, i < 6 ? ph0 : ph1);  // first use of the region in this layer
     // the barrier the NEXT tile needs is polled while this tile's MMAs are still queued in the tensor pipe
     if (i == (FIRST ? 1 : 8) && next_bar != 0u) {
       mbar_wait_a(next_bar, next_par);
@@ -333,7 +333,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   uint8_t* wgt = smem + K::kWgt;
   float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
   float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [regions][6] weight block landed
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [regions][6], slot 0 used: the region's weight blocks landed
   uint64_t* bar_empty = bar_full + kRtRegions * kRtRegionBlocks;          // [regions] region consumed by the last tile
   uint64_t* bar_acc = bar_empty + kRtRegions;                             // [H] MMAs of source tile y complete
   uint64_t* bar_act = bar_acc + kRtMaxH;                                  // [H] activation tile rewritten + accumulator drained
@@ -437,18 +437,15 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       int reg = 0, src = 0;
       uint32_t round = 0;
       for (int n = 0; n < total; ++n) {
-        if (round > 0) mbar_wait_relaxed(bar_empty + reg, (round - 1u) & 1u);
-        const int nblk = src == 0 ? 3 : kRtRegionBlocks;  // conv_in: three real blocks, the others keep their phases in step
-        for (int b = 0; b < kRtRegionBlocks; ++b) {
-          uint64_t* bar = bar_full + reg * kRtRegionBlocks + b;
-          if (b < nblk) {
-            mbar_expect_tx(bar, (uint32_t)kRtBlockBytes);
-            bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * kRtBlockBytes, wimg + (size_t)(src * kRtRegionBlocks + b) * kRtBlockBytes,
-                     (uint32_t)kRtBlockBytes, bar);
-          } else {
-            mbar_arrive(bar);
-          }
-        }
+        if (round > 0) mbar_wait_relaxed(bar_empty + reg, (round - 1u) & 1u);  // spinning instead: no gain (profiles/r1_net_bench_issue_loop.txt)
+        const int nblk = src == 0 ? 3 : kRtRegionBlocks;  // conv_in: three real blocks
+        // ONE barrier per region (slot 0 of its six): the first tile of a layer polls two barriers instead of twelve -- its
+        // N = 128 MMAs issue at the tensor pipe's own rate, so every poll between two of them is exposed (tools/cta2_probe.cu)
+        uint64_t* bar = bar_full + reg * kRtRegionBlocks;
+        mbar_expect_tx(bar, (uint32_t)(nblk * kRtBlockBytes));
+        for (int b = 0; b < nblk; ++b)
+          bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * kRtBlockBytes, wimg + (size_t)(src * kRtRegionBlocks + b) * kRtBlockBytes,
+                   (uint32_t)kRtBlockBytes, bar);
         if (++reg == kRtRegions) { reg = 0; ++round; }
         if (++src == kRtRegionsNet) src = 0;
       }
