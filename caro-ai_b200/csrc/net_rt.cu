@@ -283,8 +283,10 @@ __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
 // 1 = interior row (N = 192; the very first MMA is split so that out[y+1] is overwritten while out[y-1], out[y]
 // accumulate), 2 = last row (no out[H]; it releases the weight regions).  Everything but the two region bases, the
 // tile base and the TMEM addresses is a compile-time constant, so that the MMAs issue back to back.
-template <int POS, bool FIRST>
-__device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
+// `mid` (run when do_mid, in the middle of the tile): work of the issuing warp that would otherwise sit between two layers; in the
+// middle of an N = 192 tile the MMAs already queued hide ~265 cycles of it, next to a commit only ~95 (tools/cta2_probe.cu).
+template <int POS, bool FIRST, class Mid>
+__device__ __forceinline__ void rt_issue_tile(bool do_mid, Mid&& mid, uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
                                               uint32_t d_new, uint32_t full0, uint32_t full1, uint32_t ph0, uint32_t ph1,
                                               uint32_t empty0, uint32_t empty1, uint32_t next_bar, uint32_t next_bar2, uint32_t next_par) {
   // all barriers are shared-memory addresses; next_bar / next_bar2 == 0: nothing to poll
@@ -294,6 +296,7 @@ __device__ __forceinline__ void rt_issue_tile(uint32_t elected, uint64_t a_tile,
     const int dx = FIRST ? i - 1 : i / 4 - 1, kk = FIRST ? 0 : i % 4;
     if (POS == 0 && (i == 0 || i == 6)) mbar_wait_a(i < 6 ? full0 : full1, i < 6 ? ph0 : ph1);  // first use of the region in this layer
     // the barrier the NEXT tile needs is polled while this tile's MMAs are still queued in the tensor pipe
+    if (i == (FIRST ? 1 : 4) && do_mid) mid();
     if (i == (FIRST ? 1 : 8) && next_bar != 0u) {
       mbar_wait_a(next_bar, next_par);
       if (next_bar2 != 0u) mbar_wait_a(next_bar2, next_par);
@@ -470,25 +473,45 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     uint32_t rphase = 0;
     int layer = 0;
     bool pre_waited = false;
+    // weight regions of a layer: descriptor bases, "landed" / "consumed" barriers and the phases to wait for
+    struct LayerW {
+      uint64_t rb0, rb1;
+      uint32_t full0, full1, empty0, empty1, ph0, ph1;
+    };
+    auto take_regions = [&](bool first_l) {
+      LayerW w;
+      w.rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+      w.full0 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
+      w.empty0 = empty_a + 8u * (uint32_t)reg;
+      w.ph0 = rphase;
+      if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
+      w.rb1 = w.rb0;
+      w.full1 = w.full0;
+      w.empty1 = w.empty0;
+      w.ph1 = w.ph0;
+      if (!first_l) {
+        w.rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+        w.full1 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
+        w.empty1 = empty_a + 8u * (uint32_t)reg;
+        w.ph1 = rphase;
+        if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
+      }
+      return w;
+    };
+    LayerW nxt = take_regions(true);
     for (int gl = 0; gl < total_layers; ++gl) {
       const uint32_t par = (uint32_t)gl & 1u;
       RT_MMA_TRACE(6, gl * 2);      // layer iteration entered
       const bool first = layer == 0;
-      const uint64_t rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
-      const uint32_t full0 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
-      const uint32_t empty0 = empty_a + 8u * (uint32_t)reg;
-      const uint32_t ph0 = rphase;
-      if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
-      uint64_t rb1 = rb0;
-      uint32_t full1 = full0, empty1 = empty0;
-      uint32_t ph1 = ph0;
-      if (!first) {
-        rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
-        full1 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
-        empty1 = empty_a + 8u * (uint32_t)reg;
-        ph1 = rphase;
-        if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
-      }
+      const LayerW cur = nxt;
+      const uint64_t rb0 = cur.rb0, rb1 = cur.rb1;
+      const uint32_t full0 = cur.full0, full1 = cur.full1, empty0 = cur.empty0, empty1 = cur.empty1, ph0 = cur.ph0, ph1 = cur.ph1;
+      // the next layer's regions are worked out in the middle of tile 1 (H >= 2), not between two layers, and pinned there
+      auto mid = [&]() {
+        nxt = take_regions(layer + 1 == kRtLayers);
+        asm volatile("" : "+l"(nxt.rb0), "+l"(nxt.rb1), "+r"(nxt.full0), "+r"(nxt.full1), "+r"(nxt.empty0), "+r"(nxt.empty1), "+r"(nxt.ph0),
+                     "+r"(nxt.ph1));
+      };
 #pragma unroll 1
       for (int y = 0; y < H; ++y) {
         // tile y reads act[y] and writes out[y-1..y+1]: it needs the barriers of tiles y-1, y, y+1 at this stage.
@@ -520,13 +543,13 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           npar = par ^ 1u;
         }
         if (first) {
-          if (y == 0) rt_issue_tile<0, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, true>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
         } else {
-          if (y == 0) rt_issue_tile<0, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, false>(elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else if (y == H - 1) rt_issue_tile<2, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          else rt_issue_tile<1, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
         }
         if (elected) umma_commit_a(acc_a + 8u * (uint32_t)y);
         RT_MMA_TRACE(1, gl * 8 + y);
