@@ -13,8 +13,9 @@
 //     into the three neighbouring output tiles, which are adjacent column ranges of TMEM (out[y] at 64y):
 //     12 MMAs of 128x192x16 per tile and layer instead of 36 of 128x64x16, 10 KB of operands per 96-cycle MMA
 //     (in isolation these MMAs issue at the 96-cycle tensor floor with 80 operand wavefronts each, tools/cta2_probe.cu;
-//     inside the tower ~115 cycles with the epilogue idle and ~125 with it running: operand fetches, the epilogue's
-//     loads / stores and the eight epilogue warps' own pace limit each other);
+//     inside the tower ~103 cycles with the epilogue idle -- what the issuing warp does between two tiles is only
+//     hidden while MMAs are queued, ~95 cycles next to a commit -- and ~115 with it running: the epilogue chain
+//     bounds the layer, see DESIGN.md sections 4 and 8);
 //   * the fp32 accumulators of all H output tiles fill 384 of the 512 TMEM columns, so the residual stream
 //     v <- v + lrelu(conv(v)) is kept as bf16 hi (the shared-memory activations themselves) + an e5m2 lo part
 //     (4 channels per TMEM column, 96 columns): ~11 mantissa bits, indistinguishable from the fp32 stream at
