@@ -333,6 +333,10 @@ int main() {
   run_tower_tile(128, 1, 1, 8, 1);
   run_tower_tile(192, 1, 1, 8, 2);
   // how deep is the MMA queue?  a gap of the issuing thread is hidden only while queued MMAs keep the tensor pipe busy
+  // issue-rate floor: do narrower MMAs (the 128x64x16 ones of net_tc.cu) issue at their tensor time (32 / 16 cycles)?
+  run_tower_tile(64, 1, 1, 8);
+  run_tower_tile(32, 1, 1, 8);
+  run_tower_tile(64, 1, 1, 8, 1);
   for (int n : {192, 128})
     for (int gap : {0, 100, 200, 300, 500}) {
       run_tower_tile(n, 1, 1, 8, 0, gap, 5);    // mid-tile, no per-tile commit
