@@ -77,21 +77,37 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------- CPU baseline
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # the UNMODIFIED reference (lib/ + config.py), vendored by build() in the
+                                                  # build container (git-ignored; travels to the GPU box with the snapshot)
+
+
+def reference_kind():
+    return "reference" if os.path.exists(os.path.join(REF_DIR, "lib", "mcts.py")) else "port"
+
+
 def cpu_reference_worker(args):
-    """One process of the reference arm / cpu_baseline: the oracle port of lib/utils.py:play_game +
-    lib/mcts.py + lib/model.py (train-mode BatchNorm and autograd left on, exactly as the reference
-    runs its self-play), timed per ply.  Returns (leaf_evals, plies, games, seconds)."""
-    seed, steps, warmup, threads = args
+    """One process of the reference arm / cpu_baseline: self-play plies driven exactly like lib/utils.py:76-99 drives
+    them (search_batch -> get_policy_value(tau) -> np.random.choice -> game.move, one tree per game as in train.py:185),
+    train-mode BatchNorm and autograd left on, as the reference runs its self-play.  Classes: the unmodified reference's
+    lib.mcts.MCTS / lib.model.Net / ConnectFour when baseline/_ref holds it (kind "reference"), else the oracle port
+    (kind "port").  Returns (leaf_evals, plies, games, seconds)."""
+    seed, steps, warmup, threads, kind = args
     import numpy as np
     import torch
     torch.set_num_threads(threads)
-    from oracle.games import ConnectFourOracle
-    from oracle.mcts import OracleMCTS
-    from oracle.net import OracleNet
+    if kind == "reference":
+        sys.path.insert(0, REF_DIR)
+        from lib.game.connect_four.connect_four import ConnectFour as Game
+        from lib.mcts import MCTS as Tree
+        from lib.model import Net
+    else:
+        from oracle.games import ConnectFourOracle as Game
+        from oracle.mcts import OracleMCTS as Tree
+        from oracle.net import OracleNet as Net
     np.random.seed(seed)
     torch.manual_seed(0)
-    game = ConnectFourOracle()
-    net = OracleNet(game.obs_shape, game.action_space)
+    game = Game()
+    net = Net(game.obs_shape, game.action_space)
     counter = {"rows": 0}
     fwd = net.forward
 
@@ -100,7 +116,7 @@ def cpu_reference_worker(args):
         return fwd(x)
 
     net.forward = counting_forward
-    state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), OracleMCTS(game), 0
+    state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), Tree(game), 0
     leaf = plies = games = 0
     t0 = None
     for step in range(warmup + steps):
@@ -117,7 +133,7 @@ def cpu_reference_worker(args):
         ply += 1
         if won or not game.possible_moves(state):
             games += 1
-            state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), OracleMCTS(game), 0
+            state, cur, tree, ply = game.initial_state, int(np.random.choice(2)), Tree(game), 0
     dt = time.perf_counter() - t0
     leaf = counter["rows"]
     return leaf, plies, games, dt
@@ -126,7 +142,8 @@ def cpu_reference_worker(args):
 def run_cpu_reference(steps, warmup, procs, threads):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    jobs = [(1000 + i, steps, warmup, threads) for i in range(procs)]
+    kind = reference_kind()
+    jobs = [(1000 + i, steps, warmup, threads, kind) for i in range(procs)]
     if procs == 1:
         res = [cpu_reference_worker(jobs[0])]
     else:
@@ -137,7 +154,9 @@ def run_cpu_reference(steps, warmup, procs, threads):
     games = sum(r[2] for r in res)
     dt = max(r[3] for r in res)
     return {"leaf_evals_per_s": leaf / dt, "plies_per_s": plies / dt, "games_per_s": games / dt, "seconds": dt,
-            "leaf_evals": leaf, "plies": plies}
+            "leaf_evals": leaf, "plies": plies, "kind": kind,
+            "what": "unmodified reference (lib.mcts.MCTS + lib.model.Net from baseline/_ref)" if kind == "reference"
+                    else "oracle port of the reference (baseline/_ref absent)"}
 
 
 def reference_arm(args):
@@ -154,14 +173,130 @@ def reference_arm(args):
         "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, random-init 5x64 net, CPU",
                    "games": procs, "sims_per_move": SIMS_COUNT * SIMS_BATCH},
         "games_per_sec": r["games_per_s"], "plies_per_sec": r["plies_per_s"],
-        "cpu_baseline": {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": procs, "kind": "port",
-                         "sample": "%d processes x %d plies of oracle self-play (search_batch(100,8) per ply), 1 torch thread each"
-                                   % (procs, args.steps)},
+        "cpu_baseline": {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": procs, "kind": r["kind"],
+                         "sample": "%d processes x %d plies of CPU self-play (search_batch(100,8) per ply), 1 torch thread each; %s"
+                                   % (procs, args.steps, r["what"])},
         "e2e": {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ----------------------------------------------------------------------------------------- extras (not the headline)
+def _cuda_ms(torch, fn, repeat=1):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(repeat):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / repeat
+
+
+def extra_train(torch, dist, game, ring_engine, world, rank, rounds=20):
+    """The only collectives this design has, at this run's world size: `rounds` SGD rounds of
+    train.py:82-111 on batches drawn from the self-play engine's DEVICE replay ring -- every rank gathers BATCH_SIZE / N rows
+    (CUDA gather kernel), one NCCL all-gather assembles the 256-row batch, forward / backward in plain PyTorch, one NCCL
+    all-reduce of the persistent flat gradient bucket (753 KB), SGD step -- then one weight broadcast (best-net promotion)
+    and one 3-integer W/L/D reduction (arena).  Times are CUDA-event milliseconds on this rank, max over ranks."""
+    import torch.optim as optim
+    from caro_ai_b200 import config as cfg, distributed as D, train as T
+    from caro_ai_b200.model import Net
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    net = Net(game.obs_shape, game.action_space).to(dev)
+    D.broadcast_state_dict(net)
+    opt = optim.SGD(net.parameters(), lr=cfg.LEARNING_RATE, momentum=0.9)
+    bucket = D.FlatGradients(net.parameters())
+    net.train()
+    per = cfg.BATCH_SIZE // world if cfg.BATCH_SIZE % world == 0 else cfg.BATCH_SIZE
+    live = ring_engine.replay_live()
+    if live < per:
+        return {"skipped": "replay ring holds %d entries" % live}
+    acc = {"sample": 0.0, "gather": 0.0, "fwd_bwd": 0.0, "allreduce": 0.0, "step": 0.0}
+    losses = []
+
+    def one_round(timed):
+        box = {}
+        t_s = _cuda_ms(torch, lambda: box.__setitem__("rows", ring_engine.replay_sample(per)))
+        t_g = _cuda_ms(torch, lambda: box.__setitem__("batch", D.all_gather_rows(box["rows"]) if per != cfg.BATCH_SIZE else box["rows"]))
+
+        def fb():
+            bucket.zero()
+            loss, _, _ = T.sgd_losses(net, *box["batch"])
+            loss.backward()
+            box["loss"] = loss.detach()
+        t_f = _cuda_ms(torch, fb)
+        t_a = _cuda_ms(torch, bucket.allreduce)
+        t_o = _cuda_ms(torch, opt.step)
+        if timed:
+            for k, v in zip(("sample", "gather", "fwd_bwd", "allreduce", "step"), (t_s, t_g, t_f, t_a, t_o)):
+                acc[k] += v
+            losses.append(float(box["loss"].item()))
+
+    for _ in range(3):
+        one_round(False)
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        one_round(True)
+    wall = time.perf_counter() - t0
+    bcast_ms = _cuda_ms(torch, lambda: D.broadcast_state_dict(net), 3)
+    tally_ms = _cuda_ms(torch, lambda: D.reduce_tallies(1, 2, 3, device=dev), 3)
+    # a bare all-reduce of the bucket, back to back: the collective's own latency without the host gaps around it
+    bare_ms = _cuda_ms(torch, bucket.allreduce, 20) if world > 1 else 0.0
+    out = {"rounds": rounds, "batch": cfg.BATCH_SIZE, "rows_per_rank": per, "gradient_bytes": int(bucket.flat.numel() * 4),
+           "sgd_ms_per_round": 1e3 * wall / rounds, "replay_gather_us": 1e3 * acc["sample"] / rounds,
+           "allgather_us": 1e3 * acc["gather"] / rounds if world > 1 else None,
+           "fwd_bwd_ms": acc["fwd_bwd"] / rounds, "allreduce_us": 1e3 * acc["allreduce"] / rounds if world > 1 else None,
+           "allreduce_bare_us": 1e3 * bare_ms if world > 1 else None, "optimizer_step_us": 1e3 * acc["step"] / rounds,
+           "broadcast_us": 1e3 * bcast_ms if world > 1 else None, "reduce_tallies_us": 1e3 * tally_ms if world > 1 else None,
+           "loss_first": losses[0], "loss_last": losses[-1],
+           "limiter": "NCCL launch + all-reduce latency for 753 KB (NVLS / ring, tens of us); the SGD round itself is "
+                      "plain PyTorch autograd at batch 256 (launch-bound)"}
+    if world > 1:
+        t = torch.tensor([out[k] for k in ("sgd_ms_per_round", "allreduce_us", "allgather_us", "broadcast_us")], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["sgd_ms_per_round"], out["allreduce_us"], out["allgather_us"], out["broadcast_us"] = [float(x) for x in t]
+    return out
+
+
+def extra_configs(torch, rank, seed, small=False):
+    """Short, honestly sized runs of the other BASELINE.json configurations on THIS rank's GPU (every number below is
+    measured by CUDA events around the plies named in `plies`; nothing is scaled or extrapolated)."""
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import DeviceNet, Net
+    out = {}
+
+    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note):
+        torch.manual_seed(0)
+        dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
+        engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h) for h in range(parts)]
+        SelfPlayEngine.play_multi(engs, dn, moves=warm, count=count, batch=batch, tau_plies=TAU_PLIES, auto_restart=True)
+        torch.cuda.synchronize()
+        c0 = [e.counters() for e in engs]
+        ms = _cuda_ms(torch, lambda: SelfPlayEngine.play_multi(engs, dn, moves=plies, count=count, batch=batch, tau_plies=TAU_PLIES,
+                                                                auto_restart=True))
+        c1 = [e.counters() for e in engs]
+        d = {k: sum(b[k] - a[k] for a, b in zip(c0, c1)) for k in c1[0]}
+        out[tag] = {"workload": note, "games": parts * games_per_part, "parts": parts, "plies": plies, "warmup_plies": warm,
+                    "ms_per_ply": ms / plies, "leaf_evals_per_sec": d["leaf_evals"] / (ms / 1e3), "descents_per_sec": d["descents"] / (ms / 1e3),
+                    "plies_per_sec": d["plies"] / (ms / 1e3), "precision": dn.precision, "errors": sum(c["errors"] for c in c1)}
+        for e in engs:
+            e.close()
+        dn.close()
+
+    if small:  # the contract test: the same code on toy sizes
+        run("connect4_4096_games", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)")
+        run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)")
+        return out
+    run("connect4_4096_games", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 12288, 3, 12,
+        "BASELINE configs[1] at exactly 4,096 concurrent games (2 pipeline parts of 2,048), search_batch(100,8)")
+    run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 4,
+        "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
+        "1,024 concurrent games (2 pipeline parts of 512)")
+    return out
 
 
 # ----------------------------------------------------------------------------------------- CUDA engine
@@ -246,10 +381,16 @@ def engine_arm(args):
         e.profile(0)
     c1 = counters()
 
-    # ---- end-to-end: same plies driven through HOST buffers (pinned H2D of the roots, D2H of the new roots)
+    # ---- end-to-end: same plies driven through HOST buffers: pinned H2D of every game's root position + side to move,
+    # D2H of the positions after the move AND of the self-play product -- the replay tuples (position, side, pi, z;
+    # lib/utils.py:101-106) the finished games wrote during the ply
     Gh = G // halves
     boards_h = [torch.empty((Gh, 2), dtype=torch.int64).pin_memory() for _ in engs]
     players_h = [torch.empty((Gh,), dtype=torch.uint8).pin_memory() for _ in engs]
+    rcap = engs[0].cfg.replay_capacity
+    replay_h = [{"board": torch.empty((rcap, 2), dtype=torch.int64).pin_memory(), "player": torch.empty((rcap,), dtype=torch.uint8).pin_memory(),
+                 "pi": torch.empty((rcap, game.action_space), dtype=torch.float32).pin_memory(),
+                 "z": torch.empty((rcap,), dtype=torch.float32).pin_memory()} for _ in engs]
     for e, bh, ph in zip(engs, boards_h, players_h):
         bh.copy_(e.region("root_board"))
         ph.copy_(e.region("root_player"))
@@ -257,15 +398,19 @@ def engine_arm(args):
     e2e_steps = max(1, args.steps // 2)
     barrier()
     ce0 = counters()
+    cursors = [e.replay_cursor() for e in engs]
+    d2h_bytes = 0
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(stream)
     for _ in range(e2e_steps):
         for e, bh, ph in zip(engs, boards_h, players_h):
             e.set_roots_pinned(bh, ph)                      # H2D: this ply's positions + side to move
         play(1)
-        for e, bh, ph in zip(engs, boards_h, players_h):
+        for i, (e, bh, ph) in enumerate(zip(engs, boards_h, players_h)):
             bh.copy_(e.region("root_board"), non_blocking=True)   # D2H: positions after the move (re-seated if finished)
             ph.copy_(e.region("root_player"), non_blocking=True)
+            cursors[i], nb = e.replay_to_pinned(cursors[i], replay_h[i])  # D2H: the replay tuples of the games that ended
+            d2h_bytes += nb + Gh * 17
         stream.synchronize()  # the host owns the buffers between plies
     ee1.record(stream)
     barrier()
@@ -274,6 +419,18 @@ def engine_arm(args):
     e2e_ms = ee0.elapsed_time(ee1)
     ce1 = counters()
     workspace_gb = sum(e.workspace_bytes for e in engs) / 1e9
+    extra = {}
+    if not args.no_extra:
+        extra["train"] = extra_train(torch, dist, game, engs[0], world, rank)
+        for e in engs[1:]:
+            e.close()
+        if rank == 0:  # the other configurations are per-GPU workloads: one rank measures them
+            del engs[1:]
+            engs[0].close()
+            torch.cuda.empty_cache()
+            extra["configs"] = extra_configs(torch, rank, 4321, small=args.extra_small)
+        if world > 1:
+            dist.barrier()
 
     def allmax(x):
         if world == 1:
@@ -324,7 +481,8 @@ def engine_arm(args):
                                 % workspace_gb},
             "games_per_sec": games / sec, "plies_per_sec": plies / sec, "descents_per_sec": desc / sec,
             "e2e": {"value": e2e_leaf / (e2e_max / 1000.0), "unit": "leaf_evals/s", "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(world * G * 17), "d2h_bytes_per_step": int(world * G * 17)},
+                    "h2d_bytes_per_step": int(world * G * 17), "d2h_bytes_per_step": int(world * d2h_bytes / e2e_steps),
+                    "d2h": "new root positions (17 B/game) + the replay tuples written during the ply (49 B/entry) + ring cursor"},
             "gpu_launches": int(prof["launches"]) + int(graph_launches),
             "roofline": {"kernel": "net_rt_kernel (row-tiled tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
@@ -338,14 +496,17 @@ def engine_arm(args):
             "phase_ms_per_step": {k: prof[k] / max(1, evented) for k in ("select_ms", "plan_ms", "net_ms", "expand_backup_ms")
                                   if args.profile_level >= 2 or k == "net_ms"},
             "clocks": sampler.summary(), "engine_errors": int(errors),
+            "net_precision": {"selected": dnet.precision, "calibration": dnet.calibration},
         }
+        if extra:
+            line["extra"] = extra
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
             r = run_cpu_reference(args.cpu_plies, 1, cores, 1)  # one process per host core, like the reference arm
-            line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": cores, "kind": r["kind"],
                                     "games_per_sec": r["games_per_s"],
-                                    "sample": "%d processes x 1 torch thread, %d plies of oracle self-play each "
-                                              "(search_batch(100,8) per ply) after 1 warm-up ply" % (cores, args.cpu_plies)}
+                                    "sample": "%d processes x 1 torch thread, %d plies of CPU self-play each "
+                                              "(search_batch(100,8) per ply) after 1 warm-up ply; %s" % (cores, args.cpu_plies, r["what"])}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -367,6 +528,8 @@ def main():
     ap.add_argument("--net-sms", type=int, default=0, help="SMs the network kernel may occupy (0 = all); the rest serve the tree kernels")
     ap.add_argument("--profile-level", type=int, default=1, help="1: CUDA events around the network kernel only, 2: all phases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-small", action="store_true", help="toy sizes for extra.configs (tests)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.train / extra.configs measurements after the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -46,14 +46,14 @@ _SIGNATURES = {
     "caro_engine_select": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "caro_engine_plan": (C.c_int, [_P, C.c_int, _P]),
     "caro_engine_expand_backup": (C.c_int, [_P, C.c_int, _P, _P, _P]),
-    "caro_engine_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "caro_engine_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "caro_engine_root_policy": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "caro_engine_advance": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "caro_engine_play": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "caro_engine_profile": (C.c_int, [_P, C.c_int]),
     "caro_engine_profile_read": (C.c_int, [_P, C.POINTER(C.c_double * 4), C.POINTER(C.c_uint64), _P]),
-    "caro_engine_play_pair": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "caro_engine_play_multi": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "caro_engine_replay_gather": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "caro_engine_counters": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8), _P]),
 }
 
@@ -77,7 +77,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.caro_abi_version() != 1:
+        if handle.caro_abi_version() != 2:
             raise CaroError("libcaro_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/caro_b200.h"
@@ -65,6 +66,7 @@ struct caro_engine {
   unsigned long long launches = 0;
   cudaEvent_t sync_a = nullptr, sync_b = nullptr;  // cross-stream hand-offs (pair pipeline)
   bool lean_tree = false;  // set while the parts pipeline issues launches: prefer tree kernels with few warps
+  unsigned long long serial = 0;  // unique per created engine (keys the cached ply graph; heap addresses are reused)
   size_t next_event() {
     if (events_used == events.size()) {
       cudaEvent_t ev;
@@ -129,7 +131,7 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   CARVE(q_order, "queue_order", uint8_t, dm.G, dm.B);
   CARVE(leaf_board, "leaf_board", Board, GB);
   CARVE(leaf_player, "leaf_player", uint8_t, GB);
-  CARVE(leaf_count, "leaf_count", int32_t, 2);  // [0]: the stepwise API; the fused tree step alternates [0] / [1] by minibatch
+  CARVE(leaf_count, "leaf_count", int32_t, 2);
   CARVE(noise, "noise", double, dm.G, dm.B, dm.A);
   CARVE(probs, "probs", float, GB, dm.A);
   CARVE(values, "values", float, GB);
@@ -147,7 +149,7 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
   if (!cfg) return caro_fail(CARO_E_ARG, "null config");
   if (cfg->games <= 0 || cfg->node_capacity <= 0) return caro_fail(CARO_E_ARG, "games and node_capacity must be positive");
   if (cfg->trees_per_game != 1 && cfg->trees_per_game != 2) return caro_fail(CARO_E_ARG, "trees_per_game must be 1 or 2");
-  if (cfg->max_batch <= 0 || cfg->max_batch > 64) return caro_fail(CARO_E_ARG, "max_batch must be in 1..64");
+  if (cfg->max_batch <= 0 || cfg->max_batch > 32) return caro_fail(CARO_E_ARG, "max_batch must be in 1..32");
   int A, plies;
   if (cfg->game == CARO_GAME_CONNECT4) {
     A = 7;
@@ -208,11 +210,13 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
   static const bool dense = !(getenv("CARO_SELECT_DENSE") && atoi(getenv("CARO_SELECT_DENSE")) == 0);
   if (A <= 8 && dense && groups > 128ll * 5 * 148) select_thread_dense_kernel<R, 2, 7><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
   else if (A <= 8) select_thread_kernel<R, 2><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
-  else if (A <= 16) select_thread_kernel<R, 4><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
-  else if (A <= 32) SELECT(32, 1);
-  else if (A <= 64) SELECT(32, 2);
-  else if (A <= 128) SELECT(32, 4);
-  else SELECT(32, 8);
+  else if constexpr (!std::is_same<R, C4Rules>::value) {  // lane-group kernels: m,n,k boards only (Connect4 has 7 actions)
+    if (A <= 16) select_thread_kernel<R, 4><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(v, rules, dm, sp, batch, src);
+    else if (A <= 32) SELECT(32, 1);
+    else if (A <= 64) SELECT(32, 2);
+    else if (A <= 128) SELECT(32, 4);
+    else SELECT(32, 8);
+  }
 #undef SELECT
   return caro_check_launch("select_kernel");
 }
@@ -220,25 +224,9 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
 }  // namespace
 
 static int do_reset(caro_engine* e, const uint8_t* h_game_mask, int first_player, int bump, void* stream);
+void caro_pipeline_forget(unsigned long long engine_serial, unsigned long long net_serial);
 
 extern "C" {
-
-// Experiment switch (CARO_TREE_CARVEOUT=1): ask for the same maximal shared-memory carve-out as the tensor-core
-// tower for the Connect4 tree kernels, so that the SM does not have to be reconfigured for their blocks and they
-// can become resident next to a running tower CTA (which leaves ~15 K registers and one block reservation free).
-static void apply_tree_carveout() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  const char* env = getenv("CARO_TREE_CARVEOUT");
-  if (!env || env[0] != '1') return;
-  const int v = cudaSharedmemCarveoutMaxShared;
-  cudaFuncSetAttribute(select_thread_kernel<C4Rules, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-  cudaFuncSetAttribute(noise_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-  cudaFuncSetAttribute(plan_kernel<C4Board, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-  cudaFuncSetAttribute(expand_backup_kernel<C4Rules, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-  cudaFuncSetAttribute(advance_kernel<C4Rules>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-}
 
 size_t caro_engine_workspace_bytes(const caro_engine_config* cfg) {
   Dims dm;
@@ -257,7 +245,6 @@ size_t caro_engine_workspace_bytes(const caro_engine_config* cfg) {
 
 int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t bytes, caro_engine** out, void* stream) {
   if (!out || !d_workspace) return caro_fail(CARO_E_ARG, "null argument");
-  apply_tree_carveout();
   if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the engine has no CPU fallback");
   Dims dm;
   int plies;
@@ -265,7 +252,9 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
   if (rc != CARO_OK) return rc;
   const size_t need = caro_engine_workspace_bytes(cfg);
   if (bytes < need) return caro_fail(CARO_E_ARG, "workspace too small");
+  static unsigned long long next_serial = 0;
   caro_engine* e = new caro_engine();
+  e->serial = ++next_serial;
   e->cfg = *cfg;
   e->dm = dm;
   e->max_plies = plies;
@@ -296,6 +285,7 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
 
 void caro_engine_destroy(caro_engine* e) {
   if (!e) return;
+  caro_pipeline_forget(e->serial, 0);
   for (cudaEvent_t ev : e->events) cudaEventDestroy(ev);
   if (e->sync_a) cudaEventDestroy(e->sync_a);
   if (e->sync_b) cudaEventDestroy(e->sync_b);
@@ -404,12 +394,7 @@ int caro_engine_plan(caro_engine* e, int batch, void* stream) {
   } while (0)
   if (batch <= 8) LAUNCH_PLAN(8);
   else if (batch <= 16) LAUNCH_PLAN(16);
-  else if (batch <= 32) LAUNCH_PLAN(32);
-  else {
-    const unsigned grid = (unsigned)((G + 127) / 128);
-    if (c4) plan_serial_kernel<C4Board><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch);
-    else plan_serial_kernel<MnkBoard><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch);
-  }
+  else LAUNCH_PLAN(32);
 #undef LAUNCH_PLAN
   return caro_check_launch("plan_kernel");
 }
@@ -431,11 +416,7 @@ int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, c
     expand_backup_group8_kernel<C4Rules><<<g8, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
   } else if (batch <= 8) LAUNCH_EB(8);
   else if (batch <= 16) LAUNCH_EB(16);
-  else if (batch <= 32) LAUNCH_EB(32);
-  else {
-    if (c4) expand_backup_serial_kernel<C4Rules><<<grid, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
-    else expand_backup_serial_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->dm, batch, d_probs, d_values);
-  }
+  else LAUNCH_EB(32);
 #undef LAUNCH_EB
   return caro_check_launch("expand_backup_kernel");
 }
@@ -496,132 +477,96 @@ static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_
   return rc;
 }
 
-// Fused variant of a search step for the self-play pipeline (Connect4, batch 8): ONE tree kernel per minibatch --
-// expand+backup of minibatch i-1, select and plan of minibatch i (tree_step_kernel) -- then the tower.  The expansion
-// of the LAST minibatch of a ply is issued by fused_flush.  Both streams may be the same.
-// Measured (bench.py, A/B on one box): select+plan fused 56.0 M leaf evals/s, all three fused 54.4 M (a warp expands its
-// four games one after the other), five separate kernels 56.0 M -- the kernel boundaries are not what makes the chain
-// slow next to a tower CTA, so the fused step stays an opt-in experiment: CARO_FUSED_TREE=1 (+ CARO_FUSE_EXPAND=1).
-static bool fused_ok(const caro_engine* e, int batch) {
-  static const bool on = getenv("CARO_FUSED_TREE") && atoi(getenv("CARO_FUSED_TREE")) != 0;
-  return on && e->cfg.game == CARO_GAME_CONNECT4 && batch == 8 && e->dm.A <= 8;
+// ------------------------------------------------------------------------------ parts pipeline
+// Streams, events and the captured ply graph of the multi-part self-play pipeline, one context per CUDA device.  The
+// graph bakes in workspace pointers, dimensions, network weight pointers, the tower's by-value constants and its grid,
+// so it is keyed by the SERIAL NUMBERS of the engines and of the network (never reused, unlike heap addresses), the
+// network's weight version and grid limit, and every scalar parameter; destroying an engine or a network drops any
+// graph that refers to it (caro_pipeline_forget).
+namespace {
+
+constexpr int kMaxParts = 8;
+constexpr int kMaxDevices = 64;
+
+struct MultiGraph {  // one captured ply, replayed while its key stays the same
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long engine_serial[kMaxParts] = {0};
+  unsigned long long net_serial = 0, net_version = 0;
+  int n = 0, count = 0, batch = 0, tau = 0, restart = 0, first = 0, impl = 0, grid_limit = 0;
+  unsigned long long launches_per_ply = 0;
+};
+
+struct PipelineCtx {
+  bool ready = false;
+  cudaStream_t s_side[kMaxParts] = {nullptr};
+  cudaStream_t s_cap = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts] = {nullptr};
+  MultiGraph mg;
+};
+
+PipelineCtx g_pipeline[kMaxDevices];
+
+PipelineCtx* pipeline_ctx() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  PipelineCtx* c = &g_pipeline[dev];
+  if (!c->ready) {
+    for (int h = 0; h < kMaxParts; ++h) {
+      cudaStreamCreateWithFlags(&c->s_side[h], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming);
+    }
+    cudaStreamCreateWithFlags(&c->s_cap, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    c->ready = true;
+  }
+  return c;
 }
 
-static int fused_step(caro_engine* e, caro_net* net, int i, int net_impl, cudaStream_t st, bool more) {
-  const int batch = 8;
-  View<C4Board> v = e->v_c4;
-  int32_t* counts = e->v_c4.leaf_count;
-  v.leaf_count = counts + (i & 1);
-  int rc = CARO_OK;
-  if (i == 0) {
-    cudaMemsetAsync(counts, 0, sizeof(int32_t), st);       // counts[0] may hold the previous ply's last value
-    rc = select_phase(e, batch, 0, 1, st);                 // this minibatch's noise (later ones are prefetched below)
-    e->launches += 1;
-  }
-  static const int fuse_expand = getenv("CARO_FUSE_EXPAND") ? atoi(getenv("CARO_FUSE_EXPAND")) : 0;
-  if (!fuse_expand && i > 0 && rc == CARO_OK) {  // expand+backup of the previous minibatch as its own kernel (one warp per game)
-    e->span_begin(3, st);
-    rc = caro_engine_expand_backup(e, batch, e->v_c4.probs, e->v_c4.values, st);
-    e->span_end(3, st);
-    e->launches += 1;
-  }
-  e->span_begin(0, st);
-  if (rc == CARO_OK) {
-    const unsigned grid = (unsigned)((e->dm.G + 15) / 16);
-    tree_step_kernel<C4Rules><<<grid, 128, 0, st>>>(v, C4Rules(), e->dm, e->sp, e->v_c4.noise, e->v_c4.probs, e->v_c4.values,
-                                                    (fuse_expand && i > 0) ? 1 : 0, counts + ((i + 1) & 1));
-    rc = caro_check_launch("tree_step_kernel");
-  }
-  e->span_end(0, st);
-  if (more && rc == CARO_OK) {
-    rc = select_phase(e, batch, i + 1, 1, st);             // next minibatch's noise, underneath this tower
-    e->launches += 1;
-  }
-  e->span_begin(2, st);
-  if (rc == CARO_OK)
-    rc = caro_net_forward(net, e->cfg.game, e->cfg.n, e->cfg.k, e->v_c4.leaf_board, e->v_c4.leaf_player, v.leaf_count,
-                          (int64_t)e->dm.G * batch, e->v_c4.probs, e->v_c4.values, net_impl, st);
-  e->span_end(2, st);
-  e->launches += 2;
-  return rc;
+void drop_graph(MultiGraph* mg) {
+  if (mg->exec) cudaGraphExecDestroy(mg->exec);
+  *mg = MultiGraph();
 }
 
-static int fused_flush(caro_engine* e, cudaStream_t st) {  // expand+backup of the ply's last minibatch
-  e->span_begin(3, st);
-  const int rc = caro_engine_expand_backup(e, 8, e->v_c4.probs, e->v_c4.values, st);
-  e->span_end(3, st);
-  e->launches += 1;
-  return rc;
+}  // namespace
+
+// Called by caro_engine_destroy / caro_net_destroy / caro_net_update: a cached ply graph that refers to the object
+// must never be replayed again (its workspace / weight images may be freed or rewritten).
+void caro_pipeline_forget(unsigned long long engine_serial, unsigned long long net_serial) {
+  for (int d = 0; d < kMaxDevices; ++d) {
+    MultiGraph* mg = &g_pipeline[d].mg;
+    if (!mg->exec) continue;
+    bool hit = net_serial != 0 && mg->net_serial == net_serial;
+    for (int h = 0; h < mg->n; ++h) hit = hit || (engine_serial != 0 && mg->engine_serial[h] == engine_serial);
+    if (hit) drop_graph(mg);
+  }
 }
 
 extern "C" {
 
-int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl, void* stream) {
+int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int first_minibatch, int net_impl, void* stream) {
   if (!e || !net) return caro_fail(CARO_E_ARG, "null argument");
+  if (first_minibatch < 0) return caro_fail(CARO_E_ARG, "first_minibatch must be >= 0");
   for (int i = 0; i < count; ++i) {
-    const int rc = search_step(e, net, i, batch, net_impl, S(stream), S(stream));
+    const int rc = search_step(e, net, first_minibatch + i, batch, net_impl, S(stream), S(stream));
     if (rc != CARO_OK) return rc;
   }
   return CARO_OK;
 }
 
 // One ply of the multi-part pipeline: `count` minibatches of every part (round robin), then the advance kernels.
+// Every part keeps its tree kernels AND its network passes on its own side stream: the parts are independent chains,
+// and the tail of one part's network kernel (CTAs that ran out of groups) overlaps the head of the next part's.
 static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batch, int tau_plies, int auto_restart,
-                     int first_player, int net_impl, cudaStream_t* s_side, cudaStream_t s_net) {
+                     int first_player, int net_impl, cudaStream_t* s_side) {
   int rc = CARO_OK;
-  // Every part keeps its network passes on its own side stream: the parts are independent chains, and the tail of
-  // one part's network kernel (CTAs that ran out of groups) overlaps the head of the next part's.  CARO_SPLIT_NET=0
-  // restores the older scheme (all network passes on one stream, event hand-offs to the tree streams).
-  // CARO_SPLIT_NET=2: per-part network streams of LOW priority next to the part's HIGH-priority tree stream (event
-  // hand-offs), so that pending tree blocks are dispatched ahead of pending tower CTAs.
-  static const int split = getenv("CARO_SPLIT_NET") ? atoi(getenv("CARO_SPLIT_NET")) : 1;
-  static cudaStream_t s_tree_hi[8] = {nullptr}, s_net_lo[8] = {nullptr};
-  if (split == 2 && !s_tree_hi[0]) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority (numerically greatest)
-    for (int h = 0; h < 8; ++h) {
-      cudaStreamCreateWithPriority(&s_tree_hi[h], cudaStreamNonBlocking, hi);
-      cudaStreamCreateWithPriority(&s_net_lo[h], cudaStreamNonBlocking, lo);
-    }
-  }
-  if (split == 2) {  // fork the priority streams off the part streams (also inside a graph capture)
-    static cudaEvent_t ev_f[8] = {nullptr};
-    for (int h = 0; h < n; ++h) {
-      if (!ev_f[h]) cudaEventCreateWithFlags(&ev_f[h], cudaEventDisableTiming);
-      cudaEventRecord(ev_f[h], s_side[h]);
-      cudaStreamWaitEvent(s_tree_hi[h], ev_f[h], 0);
-      cudaStreamWaitEvent(s_net_lo[h], ev_f[h], 0);
-    }
-  }
   for (int h = 0; h < n; ++h) es[h]->lean_tree = n >= 2;
   struct LeanOff {
     caro_engine** es;
     int n;
     ~LeanOff() { for (int h = 0; h < n; ++h) es[h]->lean_tree = false; }
   } lean_off{es, n};
-  bool fused = split == 1 && count > 0;
-  for (int h = 0; h < n; ++h) fused = fused && fused_ok(es[h], batch);
   for (int i = 0; i < count && rc == CARO_OK; ++i)
-    for (int h = 0; h < n && rc == CARO_OK; ++h) {
-      if (fused) rc = fused_step(es[h], net, i, net_impl, s_side[h], i + 1 < count);
-      else if (split == 2) rc = search_step(es[h], net, i, batch, net_impl, s_tree_hi[h], s_net_lo[h], 1, i + 1 < count);
-      else rc = search_step(es[h], net, i, batch, net_impl, s_side[h], split ? s_side[h] : s_net, 1, i + 1 < count);
-    }
-  if (fused)
-    for (int h = 0; h < n && rc == CARO_OK; ++h) rc = fused_flush(es[h], s_side[h]);
-  if (split == 2) {  // join back
-    static cudaEvent_t ev_j[16] = {nullptr};
-    for (int h = 0; h < n; ++h) {
-      if (!ev_j[2 * h]) {
-        cudaEventCreateWithFlags(&ev_j[2 * h], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_j[2 * h + 1], cudaEventDisableTiming);
-      }
-      cudaEventRecord(ev_j[2 * h], s_tree_hi[h]);
-      cudaEventRecord(ev_j[2 * h + 1], s_net_lo[h]);
-      cudaStreamWaitEvent(s_side[h], ev_j[2 * h], 0);
-      cudaStreamWaitEvent(s_side[h], ev_j[2 * h + 1], 0);
-    }
-  }
+    for (int h = 0; h < n && rc == CARO_OK; ++h) rc = search_step(es[h], net, i, batch, net_impl, s_side[h], s_side[h], 1, i + 1 < count);
   for (int h = 0; h < n && rc == CARO_OK; ++h) {
     rc = caro_engine_advance(es[h], tau_plies, nullptr, auto_restart, first_player, nullptr, s_side[h]);
     es[h]->launches += 1;
@@ -629,46 +574,25 @@ static int multi_ply(caro_engine** es, int n, caro_net* net, int count, int batc
   return rc;
 }
 
-constexpr int kMaxParts = 8;
-
-struct MultiGraph {  // one captured ply, replayed while its parameters stay the same
-  cudaGraphExec_t exec = nullptr;
-  caro_engine* es[kMaxParts] = {nullptr};
-  caro_net* net = nullptr;
-  int n = 0, count = 0, batch = 0, tau = 0, restart = 0, first = 0, impl = 0;
-  unsigned long long launches_per_ply = 0;
-};
-
 int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int moves, int count, int batch, int tau_plies,
                            int auto_restart, int first_player, int net_impl, void* stream) {
   if (!engines || !net || n < 1 || n > kMaxParts) return caro_fail(CARO_E_ARG, "need 1..8 engines and a network");
   for (int h = 0; h < n; ++h)
     if (!engines[h]) return caro_fail(CARO_E_ARG, "null engine");
-  static cudaStream_t s_side[kMaxParts] = {nullptr};
-  static cudaStream_t s_cap = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts] = {nullptr};
-  static MultiGraph mg;
-  if (!s_cap) {
-    for (int h = 0; h < kMaxParts; ++h) {
-      cudaStreamCreateWithFlags(&s_side[h], cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&ev_join[h], cudaEventDisableTiming);
-    }
-    cudaStreamCreateWithFlags(&s_cap, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-  }
-  // The network passes of all parts stay on one stream, each part's tree kernels go to its own side stream.  With
-  // profiling off the whole ply (n x count x 5 kernels + n) is captured once into a CUDA graph and replayed per
+  PipelineCtx* cx = pipeline_ctx();
+  if (!cx) return caro_fail(CARO_E_CUDA, "no current CUDA device for the parts pipeline");
+  // With profiling off the whole ply (n x count x 5 kernels + n) is captured once into a CUDA graph and replayed per
   // ply: the host issues one graph launch instead of ~500 n kernel launches and ~400 n event operations.
   bool profiling = false;
   for (int h = 0; h < n; ++h) profiling = profiling || engines[h]->profiling != 0;
   const bool use_graph = !profiling && !getenv("CARO_NO_GRAPH");
-  auto fork_join = [&](cudaStream_t s_net, auto&& body) {
-    cudaEventRecord(ev_fork, s_net);
-    for (int h = 0; h < n; ++h) cudaStreamWaitEvent(s_side[h], ev_fork, 0);
+  auto fork_join = [&](cudaStream_t s_main, auto&& body) {
+    cudaEventRecord(cx->ev_fork, s_main);
+    for (int h = 0; h < n; ++h) cudaStreamWaitEvent(cx->s_side[h], cx->ev_fork, 0);
     const int rc = body();
     for (int h = 0; h < n; ++h) {
-      cudaEventRecord(ev_join[h], s_side[h]);
-      cudaStreamWaitEvent(s_net, ev_join[h], 0);
+      cudaEventRecord(cx->ev_join[h], cx->s_side[h]);
+      cudaStreamWaitEvent(s_main, cx->ev_join[h], 0);
     }
     return rc;
   };
@@ -683,41 +607,45 @@ int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int move
     ~PipelineGrid() { net->pipeline_limit = 0; }
   } pipeline_grid(net, n);
   if (use_graph) {
-    bool same = mg.exec && mg.n == n && mg.net == net && mg.count == count && mg.batch == batch && mg.tau == tau_plies &&
+    MultiGraph& mg = cx->mg;
+    bool same = mg.exec && mg.n == n && mg.net_serial == net->serial && mg.net_version == net->version &&
+                mg.grid_limit == net->grid_limit && mg.count == count && mg.batch == batch && mg.tau == tau_plies &&
                 mg.restart == auto_restart && mg.first == first_player && mg.impl == net_impl;
-    for (int h = 0; h < n && same; ++h) same = mg.es[h] == engines[h];
+    for (int h = 0; h < n && same; ++h) same = mg.engine_serial[h] == engines[h]->serial;
     if (!same) {
-      if (mg.exec) cudaGraphExecDestroy(mg.exec);
-      mg = MultiGraph();
+      drop_graph(&mg);
       unsigned long long before = 0, after = 0, saved[kMaxParts];
       for (int h = 0; h < n; ++h) {
         saved[h] = engines[h]->launches;
         before += engines[h]->launches;
       }
       cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamBeginCapture(s_cap, cudaStreamCaptureModeThreadLocal);
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(cx->s_cap, cudaStreamCaptureModeThreadLocal);
       int rc = CARO_OK;
       if (ce == cudaSuccess) {
-        rc = fork_join(s_cap, [&] {
-          return multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, s_side, s_cap);
+        rc = fork_join(cx->s_cap, [&] {
+          return multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, cx->s_side);
         });
-        ce = cudaStreamEndCapture(s_cap, &graph);
+        ce = cudaStreamEndCapture(cx->s_cap, &graph);
       }
-      if (ce == cudaSuccess && rc == CARO_OK) ce = cudaGraphInstantiate(&mg.exec, graph, 0);
+      if (ce == cudaSuccess && rc == CARO_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
       if (graph) cudaGraphDestroy(graph);
       for (int h = 0; h < n; ++h) {
         after += engines[h]->launches;
         engines[h]->launches = saved[h];  // capturing launches nothing
       }
-      mg.launches_per_ply = after - before;
       if (ce != cudaSuccess || rc != CARO_OK) {
-        mg = MultiGraph();
+        if (exec) cudaGraphExecDestroy(exec);
         cudaGetLastError();
         return caro_fail(CARO_E_CUDA, "CUDA graph capture of the self-play pipeline failed");
       }
-      mg.n = n; mg.net = net; mg.count = count; mg.batch = batch; mg.tau = tau_plies;
+      mg.exec = exec;
+      mg.launches_per_ply = after - before;
+      mg.n = n; mg.net_serial = net->serial; mg.net_version = net->version; mg.grid_limit = net->grid_limit;
+      mg.count = count; mg.batch = batch; mg.tau = tau_plies;
       mg.restart = auto_restart; mg.first = first_player; mg.impl = net_impl;
-      for (int h = 0; h < n; ++h) mg.es[h] = engines[h];
+      for (int h = 0; h < n; ++h) mg.engine_serial[h] = engines[h]->serial;
     }
     for (int m = 0; m < moves; ++m) {
       const cudaError_t ce = cudaGraphLaunch(mg.exec, S(stream));
@@ -726,19 +654,12 @@ int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int move
     }
     return CARO_OK;
   }
-  cudaStream_t s_net = S(stream);
-  return fork_join(s_net, [&] {
+  return fork_join(S(stream), [&] {
     int rc = CARO_OK;
     for (int m = 0; m < moves && rc == CARO_OK; ++m)
-      rc = multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, s_side, s_net);
+      rc = multi_ply(engines, n, net, count, batch, tau_plies, auto_restart, first_player, net_impl, cx->s_side);
     return rc;
   });
-}
-
-int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch, int tau_plies,
-                          int auto_restart, int first_player, int net_impl, void* stream) {
-  caro_engine* es[2] = {e0, e1};
-  return caro_engine_play_multi(es, 2, net, moves, count, batch, tau_plies, auto_restart, first_player, net_impl, stream);
 }
 
 int caro_engine_root_policy(caro_engine* e, int tau_mode, int tau_plies, double* d_pi, float* d_q, int32_t* d_n, void* stream) {
@@ -772,12 +693,25 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
   for (int m = 0; m < moves; ++m) {
     caro_net* net = net_p0;
     if (net_p0 != net_p1) net = ((first_player ^ (m & 1)) == 0) ? net_p0 : net_p1;
-    int rc = caro_engine_search(e, net, count, batch, net_impl, stream);
+    int rc = caro_engine_search(e, net, count, batch, 0, net_impl, stream);
     if (rc == CARO_OK) rc = caro_engine_advance(e, tau_plies, nullptr, auto_restart, first_player, nullptr, stream);
     if (rc != CARO_OK) return rc;
     e->launches += 1;
   }
   return CARO_OK;
+}
+
+int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, int64_t count, float* d_planes, float* d_pi, float* d_z,
+                              void* stream) {
+  if (!e || !d_entries || !d_planes || !d_pi || !d_z) return caro_fail(CARO_E_ARG, "null argument");
+  if (e->dm.replay_cap <= 0) return caro_fail(CARO_E_STATE, "the engine was created without a replay ring");
+  if (count <= 0) return CARO_OK;
+  const long long* ent = reinterpret_cast<const long long*>(d_entries);
+  if (e->cfg.game == CARO_GAME_CONNECT4)
+    replay_gather_kernel<C4Rules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_c4, C4Rules(), e->dm, ent, (long long)count, d_planes, d_pi, d_z);
+  else
+    replay_gather_kernel<MnkRules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, ent, (long long)count, d_planes, d_pi, d_z);
+  return caro_check_launch("replay_gather_kernel");
 }
 
 int caro_engine_counters(caro_engine* e, uint64_t h_out[8], void* stream) {

@@ -69,22 +69,6 @@ __device__ __forceinline__ int ht_lookup1(const HashSlot* __restrict__ ht, int c
   return -1;
 }
 
-__device__ __forceinline__ void ht_insert1(HashSlot* __restrict__ ht, int cap, uint32_t gen, uint64_t key_lo, int node) {
-  uint32_t idx = slot_home(key_lo, cap);
-  for (int it = 0; it < cap; ++it) {
-    if (ht[idx].gen != gen) {
-      uint4 v;
-      v.x = (uint32_t)key_lo;
-      v.y = (uint32_t)(key_lo >> 32);
-      v.z = (uint32_t)node;
-      v.w = gen;
-      *reinterpret_cast<uint4*>(ht + idx) = v;
-      return;
-    }
-    idx = (idx + 1u) & (uint32_t)(cap - 1);
-  }
-}
-
 template <class R>
 struct RulesTraits {
   static constexpr bool kHasKeyHi = true;
@@ -456,64 +440,10 @@ select_thread_dense_kernel(View<typename R::Board> e, R rules, Dims dm, SearchPa
 }
 
 // ------------------------------------------------------------------------------------ plan
-// Serial variant (batch > 32), one thread per game: back-up queue = terminal descents in descent order, then the first
-// occurrence of every distinct new leaf (lib/mcts.py:265-278); unique leaves are appended to the
-// compact batch (order across games is arbitrary; results do not depend on it).
-template <class Board>
-__global__ void __launch_bounds__(128)
-plan_serial_kernel(View<Board> e, Dims dm, int batch) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int n_term = 0, n_new = 0;
-  uint8_t order[64];
-  const bool live = g < dm.G && e.status[g] == ST_ACTIVE;
-  const size_t d0 = (size_t)(g < dm.G ? g : 0) * dm.B;
-  if (live) {
-    for (int j = 0; j < batch; ++j)
-      if (e.d_kind[d0 + j] == KIND_TERMINAL) order[n_term++] = (uint8_t)j;
-    for (int j = 0; j < batch; ++j) {
-      if (e.d_kind[d0 + j] != KIND_EXPAND) continue;
-      const uint64_t lo = e.d_key_lo[d0 + j], hi = e.d_key_hi[d0 + j];
-      bool dup = false;
-      for (int q = n_term; q < n_term + n_new; ++q) {
-        const int jj = order[q];
-        dup = dup || (e.d_key_lo[d0 + jj] == lo && e.d_key_hi[d0 + jj] == hi);
-      }
-      if (!dup) order[n_term + n_new++] = (uint8_t)j;
-    }
-  }
-  // warp-aggregated reservation in the compact leaf batch
-  int incl = n_new;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= off) incl += v;
-  }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  int base = 0;
-  if (lane == 31 && warp_total > 0) base = atomicAdd(e.leaf_count, warp_total);
-  base = __shfl_sync(0xffffffffu, base, 31) + incl - n_new;
-  if (!live) {
-    if (g < dm.G) e.q_len[g] = 0;
-    return;
-  }
-  e.q_len[g] = n_term + n_new;
-  for (int q = 0; q < n_term + n_new; ++q) {
-    const int j = order[q];
-    e.q_order[d0 + q] = (uint8_t)j;
-    if (q >= n_term) {
-      const int slot = base + (q - n_term);
-      e.d_slot[d0 + j] = slot;
-      e.leaf_board[slot] = e.d_board[d0 + j];
-      e.leaf_player[slot] = e.d_player[d0 + j];
-    }
-  }
-  if (n_new) atomicAdd(e.ctr + CTR_LEAVES, (unsigned long long)n_new);
-  atomicAdd(e.ctr + CTR_DESCENTS, (unsigned long long)batch);
-}
-
-// Lane-parallel variant (batch <= 32): GP lanes per game, lane j owns descent j, so every load of the
-// per-descent records is issued at once instead of as a dependent chain.
+// Back-up queue = terminal descents in descent order, then the first occurrence of every distinct new leaf
+// (lib/mcts.py:265-278); unique leaves are appended to the compact batch (order across games is arbitrary; results do
+// not depend on it).  GP lanes per game (batch <= GP <= 32), lane j owns descent j, so every load of the per-descent
+// records is issued at once instead of as a dependent chain.
 template <class Board, int GP>
 __device__ __forceinline__ void plan_body(const View<Board>& e, const Dims& dm, int batch, int gthread) {
   const int g = gthread / GP;
@@ -586,70 +516,6 @@ plan_kernel(View<Board> e, Dims dm, int batch) {
 }
 
 // --------------------------------------------------------------------------- expand + backup
-// One warp per game.  Queue entries are applied strictly in order (float32 W sums are order
-// dependent); inside an entry the lanes take one edge of the path each (edges of one path are
-// distinct nodes, and an edge always sits at the same depth, hence on the same lane).
-template <class R>
-__global__ void __launch_bounds__(128)
-expand_backup_serial_kernel(View<typename R::Board> e, Dims dm, int batch, const float* __restrict__ probs,
-                     const float* __restrict__ values) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= dm.G || e.status[g] != ST_ACTIVE) return;
-  const int who0 = e.root_player[g];
-  const int tree = g * dm.tpg + (dm.tpg == 2 ? who0 : 0);
-  const uint32_t gen = e.tree_gen[tree];
-  HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
-  const size_t nb = (size_t)tree * dm.node_cap;
-  const size_t d0 = (size_t)g * dm.B;
-  const int qn = e.q_len[g];
-  int count = e.node_count[tree];
-  for (int q = 0; q < qn; ++q) {
-    const size_t di = d0 + e.q_order[d0 + q];
-    const int kind = e.d_kind[di];
-    float v;
-    bool from_net = false;
-    if (kind == KIND_EXPAND) {
-      const int slot = e.d_slot[di];
-      v = values[slot];
-      from_net = true;
-      if (count < dm.node_cap) {  // _create_node, lib/mcts.py:178-190
-        const int node = count++;
-        const size_t row = (nb + (size_t)node) * dm.RS;
-        for (int a = lane; a < dm.Apad; a += 32) {
-          e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
-          e.N[row + a] = 0;
-          e.W[row + a] = 0.0f;
-          e.C[row + a] = -1;
-        }
-        if (lane == 0) {
-          e.node_board[nb + node] = e.d_board[di];
-          e.node_player[nb + node] = e.d_player[di];
-          if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + node] = e.d_key_hi[di];
-          ht_insert1(ht, dm.hash_cap, gen, e.d_key_lo[di], node);
-        }
-      } else if (lane == 0) {
-        atomicOr(e.ctr + CTR_ERRORS, ERR_ARENA_FULL);
-      }
-    } else {
-      v = e.d_value[di];
-    }
-    // _backup, lib/mcts.py:225-246
-    const int d = e.d_path_len[di];
-    const int32_t* pn = e.d_path_node + di * dm.max_depth;
-    const uint8_t* pa = e.d_path_action + di * dm.max_depth;
-    for (int i = lane; i < d; i += 32) {
-      const int a = pa[i];
-      const size_t idx = (nb + (size_t)pn[i]) * dm.RS + a;
-      const float cur = ((d - 1 - i) & 1) ? v : -v;
-      e.N[idx] = (e.N[idx] + 1) | (from_net ? kNetBit : 0);
-      e.W[idx] = __fadd_rn(e.W[idx], cur);
-    }
-    __syncwarp();
-  }
-  if (lane == 0) e.node_count[tree] = count;
-}
-
 // Claim a hash slot for `key_lo` with a CAS on the generation word, so that the (<= batch) insertions of one
 // minibatch can proceed concurrently from different lanes.  Keys of one minibatch are distinct (plan dedup).
 __device__ __forceinline__ void ht_insert_cas(HashSlot* __restrict__ ht, int cap, uint32_t gen, uint64_t key_lo, int node) {
@@ -804,32 +670,6 @@ expand_backup_group8_kernel(View<typename R::Board> e, Dims dm, int batch, const
                             const float* __restrict__ values) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   expand_backup_body<R, 8, 8>(e, dm, batch, probs, values, t >> 3, threadIdx.x & 31);
-}
-
-// ------------------------------------------------------------------------------ fused tree step
-// expand+backup of minibatch i-1, then select and plan of minibatch i, for 16 games per block of 128 threads (batch = 8,
-// A <= 8).  The three phases only depend on each other PER GAME (a game's descents need its own tree updated, its plan
-// needs its own descents), so one kernel with two block-level barriers replaces three kernels with grid-wide
-// boundaries: inside the self-play pipeline the tree kernels run in the few warp slots a tower CTA leaves, in several
-// waves each, and every kernel boundary drained all of them -- the chain tower -> expand -> select -> plan -> tower, not
-// the tower, set the pipeline's period (tools/pipeline_trace.py).  The compact-leaf counter is double-buffered by
-// minibatch parity (e.leaf_count = this minibatch's, `other_count` = the next one's, zeroed here) because blocks
-// reach the plan phase at different times.
-template <class R>
-__global__ void __launch_bounds__(128)
-tree_step_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, const double* __restrict__ noise_in,
-                 const float* __restrict__ probs, const float* __restrict__ values, int do_expand, int32_t* other_count) {
-  constexpr int kBatch = 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (do_expand) {
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) expand_backup_body<R, 8>(e, dm, kBatch, probs, values, blockIdx.x * 16 + warp * 4 + k, lane);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *other_count = 0;
-  __syncthreads();
-  select_thread_body<R, 2>(e, rules, dm, sp, kBatch, noise_in, (long long)blockIdx.x * 128 + threadIdx.x);
-  __syncthreads();
-  plan_body<typename R::Board, 8>(e, dm, kBatch, blockIdx.x * 128 + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------ root policy
@@ -1008,6 +848,29 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
       e.tree_gen[g * dm.tpg + t] += 1u;
     }
   }
+}
+
+// ----------------------------------------------------------------------------- replay -> SGD batch
+// train.py:85-94 on the device: the sampled replay rows become the training tensors without leaving HBM -- network
+// planes (game.states_to_training_batch of the stored position, from the side to move's point of view), the MCTS
+// policy target and the outcome z.  `entry[i]` = absolute number of the sampled ring entry (slot = entry % capacity;
+// the host draws the numbers with random.sample, like the reference).  One block per sample.
+template <class R>
+__global__ void __launch_bounds__(64)
+replay_gather_kernel(View<typename R::Board> e, R rules, Dims dm, const long long* __restrict__ entry, long long count,
+                     float* __restrict__ planes, float* __restrict__ pi, float* __restrict__ z) {
+  const long long i = blockIdx.x;
+  if (i >= count) return;
+  const size_t slot = (size_t)(entry[i] % (long long)dm.replay_cap);
+  const typename R::Board s = e.rp_board[slot];
+  const int who = e.rp_player[slot];
+  const int H = rules.rows(), W = rules.cols(), HW = H * W;
+  for (int t = threadIdx.x; t < 2 * HW; t += blockDim.x) {
+    const int plane = t / HW, cell = t - plane * HW;
+    planes[(size_t)i * 2 * HW + t] = (float)rules.plane_value(s, who, plane, cell / W, cell % W);
+  }
+  for (int a = threadIdx.x; a < dm.A; a += blockDim.x) pi[(size_t)i * dm.A + a] = e.rp_pi[slot * dm.A + a];
+  if (threadIdx.x == 0) z[i] = e.rp_z[slot];
 }
 
 // ------------------------------------------------------------------------------------- reset

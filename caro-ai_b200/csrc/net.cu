@@ -145,6 +145,8 @@ size_t caro_net_blob_floats(int rows, int cols, int actions) { return blob_layou
 int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats) {
   if (!net || !h_blob) return caro_fail(CARO_E_ARG, "null argument");
   if (n_floats != net->layout.total) return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
+  caro_pipeline_forget(0, net->serial);  // a captured ply holds the previous constants by value
+  net->version += 1;
   cudaError_t ce = cudaMemcpy(net->d_blob, h_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   const int rc = caro_net_tc_pack(net, h_blob);
@@ -156,7 +158,10 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   if (!out || !h_blob) return caro_fail(CARO_E_ARG, "null argument");
   if (rows < 2 || cols < 2 || rows > 15 || cols > 15 || actions < 1 || actions > 255) return caro_fail(CARO_E_ARG, "bad net shape");
   if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the network has no CPU fallback");
+  static unsigned long long next_serial = 0;
   caro_net* net = new caro_net();
+  net->serial = ++next_serial;
+  net->version = 0;
   net->H = rows;
   net->W = cols;
   net->A = actions;
@@ -216,6 +221,7 @@ int caro_net_set_trace(caro_net* net, void* d_trace) {
 
 void caro_net_destroy(caro_net* net) {
   if (!net) return;
+  caro_pipeline_forget(0, net->serial);
   caro_net_tc_free(net);
   caro_net_rt_free(net);
   if (net->d_blob) cudaFree(net->d_blob);

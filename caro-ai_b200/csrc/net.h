@@ -62,8 +62,13 @@ struct caro_net {
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
   int sm_count;         // multiprocessors of the device the handle was created on
   int grid_limit;       // > 0: CTAs (= SMs) the persistent tower may occupy (caro_net_set_grid_limit), 0 = all
+  unsigned long long serial;   // unique per created handle (keys the cached ply graph of the parts pipeline)
+  unsigned long long version;  // bumped by every caro_net_update: the tower's constants travel BY VALUE in its kernel parameters
   int pipeline_limit;   // > 0 while the parts pipeline issues / captures a ply and the user has set no limit: sm_count - sm_count / 9
 };
+
+// engine.cu: drop cached ply graphs that refer to an engine / a network (0 = none)
+void caro_pipeline_forget(unsigned long long engine_serial, unsigned long long net_serial);
 
 // net_tc.cu
 int caro_net_tc_pack(caro_net* net, const float* h_blob);

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing (one process per GPU, ``torch.distributed``; NCCL over NVLink on the box, gloo in the CPU
 tests).  Self-play needs no collective -- games shard by rank -- so the only exchanges are the ones SURVEY.md
-section 8(e) lists: a flattened-gradient all-reduce per SGD step, a weight broadcast after best-net promotion and the
-3-integer W/L/D reduction of the arena evaluation."""
+section 8(e) lists: a flattened-gradient all-reduce per SGD step, the all-gather of the ranks' replay samples into the
+step's batch, a weight broadcast before an evaluation / after a best-net promotion, the 3-integer W/L/D reduction of
+the arena evaluation and the MIN-reduction behind every "do we train this step?" decision."""
 from __future__ import annotations
 
 from typing import Iterable, List, Tuple
@@ -78,6 +79,32 @@ def broadcast_state_dict(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in module.state_dict().values():
         dist.broadcast(t, src=src)
+
+
+def all_min(value: int, device=None) -> int:
+    """Smallest ``value`` over the ranks: collective decisions (train.py:199 "is the replay buffer large enough?") must be
+    taken on a reduced quantity, or the ranks fall out of step with each other's collectives."""
+    _, ws = world()
+    if ws == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t[0])
+
+
+def all_gather_rows(tensors):
+    """Concatenation over ranks (rank order) of every tensor's rows: the SGD batch assembled from the ranks' replay
+    samples (BATCH_SIZE / world rows each).  One all-gather per tensor (planes, pi, z)."""
+    _, ws = world()
+    if ws == 1:
+        return tuple(tensors)
+    out = []
+    for t in tensors:
+        t = t.contiguous()
+        full = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t)
+        out.append(full)
+    return tuple(out)
 
 
 def reduce_tallies(wins: int, losses: int, draws: int, device=None) -> Tuple[int, int, int]:

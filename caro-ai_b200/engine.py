@@ -102,6 +102,8 @@ class SelfPlayEngine:
         if getattr(self, "handle", None):
             _cabi.lib().caro_engine_destroy(self.handle)
             self.handle = None
+            self._views = {}
+            self.workspace = None  # the arenas go back to torch's allocator
 
     def __del__(self):
         try:
@@ -157,10 +159,11 @@ class SelfPlayEngine:
                                                           self._stream()))
 
     # ------------------------------------------------------------------ fused paths
-    def search(self, net: DeviceNet, count: int, batch: int, impl: int = None):
-        """MCTS.search_batch(count, batch, ...) for all games with the built-in network."""
+    def search(self, net: DeviceNet, count: int, batch: int, impl: int = None, first_minibatch: int = 0):
+        """MCTS.search_batch(count, batch, ...) for all games with the built-in network.  ``first_minibatch`` numbers
+        the minibatches for the Philox noise address (a running index when the same game / ply is searched again)."""
         impl = net.impl if impl is None else impl
-        _cabi.check(_cabi.lib().caro_engine_search(self.handle, net.handle, count, batch, impl, self._stream()))
+        _cabi.check(_cabi.lib().caro_engine_search(self.handle, net.handle, count, batch, first_minibatch, impl, self._stream()))
 
     def search_with(self, evaluate, count: int, batch: int, noise_fn=None):
         """Same, with a caller-supplied evaluator ``evaluate(planes[L,2,H,W]) -> (priors[L,A], values[L])``
@@ -225,14 +228,6 @@ class SelfPlayEngine:
         out_pinned["boards"].copy_(self.region("root_board"), non_blocking=True)
         out_pinned["players"].copy_(self.region("root_player"), non_blocking=True)
 
-    def play_pair(self, other: "SelfPlayEngine", net: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
-                  auto_restart: bool = True, first_player: int = -1, impl: int = None):
-        """Self-play of two engines (two halves of the game batch) as a software pipeline: one half's tree kernels
-        run on a side stream underneath the other half's network pass (caro_engine_play_pair)."""
-        impl = net.impl if impl is None else impl
-        _cabi.check(_cabi.lib().caro_engine_play_pair(self.handle, other.handle, net.handle, moves, count, batch, tau_plies,
-                                                      1 if auto_restart else 0, first_player, impl, self._stream()))
-
     @staticmethod
     def play_multi(engines: Sequence["SelfPlayEngine"], net: DeviceNet, moves: int, count: int, batch: int, tau_plies: int,
                    auto_restart: bool = True, first_player: int = -1, impl: int = None):
@@ -274,10 +269,72 @@ class SelfPlayEngine:
             out[s] = {"N": N[i].tolist(), "W": W[i].copy(), "Q": Q[i].copy(), "P": P[i].copy(), "f32": f32}
         return out
 
+    def replay_cursor(self) -> int:
+        """Total number of replay entries ever written (one host read)."""
+        return int(self.region("replay_cursor").item())
+
+    def replay_live(self) -> int:
+        """Entries currently held by the ring = ``len(replay_buffer)`` of train.py:199."""
+        return min(self.replay_cursor(), max(0, self.cfg.replay_capacity))
+
+    def replay_sample(self, count: int, rng=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """train.py:85-94 without the host round trip: ``random.sample`` draws ``count`` of the live ring entries (the
+        reference's sampler, on the entry NUMBERS only), the CUDA gather kernel turns them into the SGD tensors
+        (planes float32 [count,2,H,W], pi float32 [count,A], z float32 [count]) straight from the ring."""
+        import random as _random
+        rng = rng or _random
+        cursor = self.replay_cursor()
+        live = min(cursor, max(0, self.cfg.replay_capacity))
+        assert count <= live, "sample larger than the replay ring's content"
+        picks = rng.sample(range(live), count)
+        entries = torch.tensor([cursor - live + i for i in picks], dtype=torch.int64).to(self.device, non_blocking=True)
+        _, h, w = self.game.obs_shape
+        planes = torch.empty((count, 2, h, w), dtype=torch.float32, device=self.device)
+        pi = torch.empty((count, self.A), dtype=torch.float32, device=self.device)
+        z = torch.empty((count,), dtype=torch.float32, device=self.device)
+        _cabi.check(_cabi.lib().caro_engine_replay_gather(self.handle, entries.data_ptr(), count, planes.data_ptr(),
+                                                          pi.data_ptr(), z.data_ptr(), self._stream()))
+        return planes, pi, z
+
+    def replay_load(self, entries) -> None:
+        """Appends reference tuples (state_int, player, probs, z) to the ring (tests / warm starts)."""
+        cap = self.cfg.replay_capacity
+        assert cap > 0 and len(entries) <= cap
+        cursor = self.replay_cursor()
+        idx = (torch.arange(cursor, cursor + len(entries), device=self.device) % cap)
+        boards = torch.from_numpy(self.game.boards_from_states([e[0] for e in entries]).view(np.int64)).to(self.device)
+        self.region("replay_board")[idx] = boards
+        self.region("replay_player")[idx] = torch.tensor([e[1] for e in entries], dtype=torch.uint8, device=self.device)
+        self.fregion("replay_pi")[idx] = torch.tensor([list(e[2]) for e in entries], dtype=torch.float32, device=self.device)
+        self.fregion("replay_z")[idx] = torch.tensor([float(e[3]) for e in entries], dtype=torch.float32, device=self.device)
+        self.region("replay_cursor").fill_(cursor + len(entries))
+
+    def replay_to_pinned(self, start: int, pinned: Dict[str, torch.Tensor]) -> Tuple[int, int]:
+        """Copies the ring entries [start, cursor) -- the product of self-play, lib/utils.py:101-106 -- into caller-owned
+        PINNED host tensors ``board`` int64 [cap,words], ``player`` uint8 [cap], ``pi`` float32 [cap,A], ``z`` float32 [cap]
+        at the same ring slots (at most two contiguous device->host copies per field, asynchronous on the current
+        stream after the one synchronous read of the cursor).  Returns (cursor, bytes copied)."""
+        cap = self.cfg.replay_capacity
+        cursor = self.replay_cursor()
+        start = max(start, cursor - cap)
+        if cap <= 0 or cursor <= start:
+            return cursor, 8
+        lo, hi = start % cap, cursor % cap
+        spans = [(lo, hi)] if lo < hi else [(lo, cap), (0, hi)]
+        nbytes = 8
+        for name, view in (("board", self.region("replay_board")), ("player", self.region("replay_player")),
+                           ("pi", self.fregion("replay_pi")), ("z", self.fregion("replay_z"))):
+            for a, b in spans:
+                if b > a:
+                    pinned[name][a:b].copy_(view[a:b], non_blocking=True)
+                    nbytes += (b - a) * view[0].numel() * view.element_size() if view.dim() > 1 else (b - a) * view.element_size()
+        return cursor, nbytes
+
     def drain_replay(self, start: int = 0):
         """Replay entries [start, cursor) as reference tuples (state_int, player, probs, z)
-        (lib/utils.py:101-106).  Returns (entries, cursor)."""
-        cursor = int(self.region("replay_cursor").item())
+        (lib/utils.py:101-106).  Returns (entries, cursor).  Host path for the reference-style deque; the trainer
+        samples on the device (``replay_sample``)."""
+        cursor = self.replay_cursor()
         cap = self.cfg.replay_capacity
         if cap <= 0 or cursor == start:
             return [], cursor

@@ -9,12 +9,15 @@ Differences worth knowing (all documented in DESIGN.md):
   * the tree is keyed per engine (per ``MCTS`` object), exactly like the reference's dicts;
   * Dirichlet noise comes from the engine's Philox streams unless ``noise_fn`` is set (the reference draws from
     the global numpy RNG, which cannot be shared with a GPU);
-  * a ``net`` that is a ``caro_ai_b200.model.Net`` / ``DeviceNet`` runs through the fused tensor-core tower
-    (eval-mode BatchNorm); any other callable is evaluated as ``net(planes) -> (logits, values)`` + softmax,
+  * a ``net`` that is a ``caro_ai_b200.model.Net`` / ``DeviceNet`` runs through the fused tensor-core tower with
+    EVAL-mode BatchNorm (folded running statistics).  The reference never calls ``.eval()`` and searches with
+    train-mode batch statistics that depend on what else is in the leaf batch; that quirk is
+    deliberately not reproduced; any other callable is evaluated as ``net(planes) -> (logits, values)`` + softmax,
     i.e. exactly ``lib/mcts.py:212-218``, on the leaf planes produced by the CUDA encode kernel.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -36,12 +39,12 @@ class MCTS:
                  noise_fn: Optional[Callable[[int, int], np.ndarray]] = None):
         """``noise_fn(batch, actions) -> float64 [batch, actions]`` injects the Dirichlet draws (tests)."""
         self.c_puct = C_PUCT
-        self.precision = "bf16x3"  # nn.Module nets handed to this facade are folded at fp32-class accuracy
+        self.precision = "auto"  # nn.Module nets: one-pass bf16 tower while it holds 1e-3 on probe positions, else bf16x3
         self.game = game
         self.noise_fn = noise_fn
         self._engine: Optional[SelfPlayEngine] = None
         self._cfg = dict(node_capacity=node_capacity, max_batch=max_batch, seed=seed)
-        self._device_nets: Dict[int, DeviceNet] = {}
+        self._device_nets: Dict[int, tuple] = {}
         self._overlay: Optional[Dict[str, dict]] = None  # host-assigned statistics (lib/test_mcts.py:15-21)
         self._minibatches = 0
 
@@ -55,20 +58,49 @@ class MCTS:
                                           explore=EXPLORE, seed=self._cfg["seed"])
         return self._engine
 
+    @staticmethod
+    def _weights_version(net: Net) -> int:
+        """Changes whenever a parameter or buffer of ``net`` is written in place (optimizer step, load_state_dict,
+        BatchNorm running statistics): torch bumps every tensor's version counter on an in-place write."""
+        return sum(t._version for t in net.state_dict(keep_vars=True).values())
+
     def _device_net(self, net) -> Optional[DeviceNet]:
+        """The folded device twin of ``net``.  The reference always searches with the module's LIVE weights, so the twin
+        is re-folded whenever the module's tensors have been written since the last search; the cache holds a weak
+        reference (a recycled ``id()`` of a collected module can never alias another network)."""
         if isinstance(net, DeviceNet):
             return net
         if isinstance(net, Net):
             key = id(net)
-            if key not in self._device_nets:
-                self._device_nets[key] = DeviceNet(net, self.game, precision=self.precision)
-            return self._device_nets[key]
+            entry = self._device_nets.get(key)
+            version = self._weights_version(net)
+            if entry is not None and entry[0]() is net:
+                if entry[2] != version:
+                    entry[1].update(net)
+                    self._device_nets[key] = (entry[0], entry[1], version)
+                return entry[1]
+            if entry is not None:
+                entry[1].close()
+            dn = DeviceNet(net, self.game, precision=self.precision)
+            self._device_nets[key] = (weakref.ref(net), dn, version)
+            return dn
         return None
 
     def refresh_net(self, net: Net) -> None:
-        """Re-fold the weights of an ``nn.Module`` that was trained since the last search."""
-        if id(net) in self._device_nets:
-            self._device_nets[id(net)].update(net)
+        """Force a re-fold of ``net`` (kept for callers of the first release; the facade now notices weight changes by
+        itself through the tensors' version counters)."""
+        entry = self._device_nets.get(id(net))
+        if entry is not None and entry[0]() is net:
+            entry[1].update(net)
+            self._device_nets[id(net)] = (entry[0], entry[1], self._weights_version(net))
+
+    def _check_engine(self) -> None:
+        """Engine error bits (include/caro_b200.h, counters[7]) become exceptions: a full arena on a long-lived shared
+        tree must not pass silently (the reference's dicts simply grow)."""
+        err = self._engine.counters()["errors"] if self._engine is not None else 0
+        if err & 1:
+            raise _cabi.CaroError("MCTS node arena is full (node_capacity=%d): construct MCTS(game, node_capacity=...) larger "
+                                  "or clear() the tree" % self._cfg["node_capacity"])
 
     # ------------------------------------------------------------------ reference surface
     def clear(self) -> None:  # lib/mcts.py:39-43
@@ -106,14 +138,14 @@ class MCTS:
         eng.set_roots([state_int], [player])
         dn = self._device_net(net)
         if dn is not None and self.noise_fn is None:
-            eng.search(dn, count, batch_size)
+            eng.search(dn, count, batch_size, first_minibatch=self._minibatches & 0x3FFFF)
             self._minibatches += count
             return
         for _ in range(count):
             self._step(eng, batch_size, net)
 
     def _step(self, eng: SelfPlayEngine, batch: int, net) -> None:
-        eng.select(batch, self._minibatches, self._noise(batch))
+        eng.select(batch, self._minibatches & 0x3FFFF, self._noise(batch))
         self._minibatches += 1
         eng.plan(batch)
         n = eng.leaf_count()
@@ -139,7 +171,7 @@ class MCTS:
         """lib/mcts.py:97-148: one descent on the current tree (nothing is expanded or backed up)."""
         eng = self._eng()
         eng.set_roots([state_int], [player])
-        eng.select(1, self._minibatches, self._noise(1))
+        eng.select(1, self._minibatches & 0x3FFFF, self._noise(1))
         kind = int(eng.region("desc_kind")[0, 0].item())
         depth = int(eng.region("desc_path_len")[0, 0].item())
         nodes = eng.region("desc_path_node")[0, 0, :depth].cpu().numpy()
@@ -158,6 +190,7 @@ class MCTS:
         if roots[0] != state_int:
             eng.set_roots([state_int], [players[0]])
         pi, q, _ = eng.root_policy(0 if tau == 0 else 1)
+        self._check_engine()
         return [float(x) for x in pi[0].cpu().numpy()], [float(x) for x in q[0].cpu().numpy()]
 
     # ------------------------------------------------------------------ dict views (lib/mcts.py:29-36)

@@ -107,19 +107,60 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], rows: int, cols: int, actions: 
 
 
 IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3 = 0, 1, 2
+PRIOR_TOLERANCE = 1e-3      # BASELINE.json north_star: priors / values within 1e-3 of the fp32 reference
+CALIBRATION_MARGIN = 0.8    # the probe set is a sample: switch to the split mode at 0.8 x the tolerance
+_PROBE_BOARDS: Dict[tuple, tuple] = {}
+
+
+def probe_positions(game, count: int = 256, seed: int = 2026):
+    """(d_boards, d_who): ``count`` positions reached by random legal play-outs of 0 .. ~2/3 of the longest game, played
+    with the CUDA board kernels (no host rules).  Cached per game shape; used to pick the tower's precision."""
+    key = (game.game_kind, game.n, game.k, count, seed, torch.cuda.current_device())
+    if key not in _PROBE_BOARDS:
+        rng = np.random.default_rng(seed)
+        A = game.action_space
+        max_plies = 42 if game.game_kind == _cabi.GAME_CONNECT4 else A
+        states = [game.initial_state] * count
+        players = [int(x) for x in rng.integers(0, 2, count)]
+        target = rng.integers(0, max(1, min(60, (2 * max_plies) // 3)), count)
+        for ply in range(int(target.max())):
+            masks = game.legal_masks(states)
+            acts, idx = [], []
+            for i in range(count):
+                legal = np.nonzero(masks[i])[0]
+                if ply < target[i] and legal.size:
+                    idx.append(i)
+                    acts.append(int(rng.choice(legal)))
+            if not idx:
+                break
+            new_states, won, draw = game.apply_batch([states[i] for i in idx], acts, [players[i] for i in idx])
+            for j, i in enumerate(idx):
+                if won[j] or draw[j]:
+                    target[i] = 0  # keep the last non-terminal position
+                else:
+                    states[i], players[i] = new_states[j], 1 - players[i]
+        d_boards = torch.from_numpy(game.boards_from_states(states).view(np.int64)).cuda()
+        d_who = torch.tensor(players, dtype=torch.uint8, device="cuda")
+        _PROBE_BOARDS[key] = (d_boards, d_who)
+    return _PROBE_BOARDS[key]
 
 
 class DeviceNet:
     """Folded network resident on the GPU (``caro_net`` handle)."""
 
-    def __init__(self, net_or_state_dict, game, precision: str = "bf16"):
-        """``precision``: "bf16" (one bf16 tensor-core pass, fp32 accumulate: the throughput mode, within 1e-3 of
-        fp32 for networks whose logits are O(10)) or "bf16x3" (hi/lo split, fp32-class accuracy: use it for trained
-        checkpoints with large logits, e.g. the shipped Connect4 nets)."""
+    def __init__(self, net_or_state_dict, game, precision: str = "auto"):
+        """``precision``:
+        "auto"   (default) -- after every weight upload 256 probe positions run through the fp32 SIMT tower and the
+                 one-pass bf16 tensor-core tower; the fast tower is used only while BOTH priors and values agree within
+                 CALIBRATION_MARGIN x 1e-3 (lib/mcts.py:212-218 contract), otherwise the split-precision tower is selected.
+                 Random-init networks (the benchmark) stay on "bf16"; trained checkpoints whose policy logits span +-100
+                 (the shipped Connect4 nets) switch to "bf16x3" (DESIGN.md section 2).
+        "bf16"   one bf16 tensor-core pass, fp32 accumulate (forced; the caller vouches for the tolerance),
+        "bf16x3" hi/lo split of activations and weights, three MMAs per product: fp32-class accuracy,
+        "fp32-simt" the SIMT numerics-reference kernel."""
         _cabi.require_cuda()
-        assert precision in ("bf16", "bf16x3", "fp32-simt")
-        self.precision = precision
-        self.impl = {"bf16": IMPL_TCGEN05, "bf16x3": IMPL_TCGEN05_X3, "fp32-simt": IMPL_SIMT}[precision]
+        assert precision in ("auto", "bf16", "bf16x3", "fp32-simt")
+        self.requested = precision
         sd = net_or_state_dict.state_dict() if isinstance(net_or_state_dict, nn.Module) else net_or_state_dict
         _, self.rows, self.cols = game.obs_shape
         self.actions = game.action_space
@@ -129,12 +170,37 @@ class DeviceNet:
         _cabi.check(_cabi.lib().caro_net_create(self.rows, self.cols, self.actions, blob.ctypes.data, blob.size,
                                                 C.byref(handle)))
         self.handle = handle
+        self.calibration = None
+        self._select(precision)
+
+    def _select(self, precision: str) -> None:
+        if precision == "auto":
+            precision = self.calibrate()
+        self.precision = precision
+        self.impl = {"bf16": IMPL_TCGEN05, "bf16x3": IMPL_TCGEN05_X3, "fp32-simt": IMPL_SIMT}[precision]
+
+    def calibrate(self, d_boards=None, d_who=None) -> str:
+        """Max |prior| / |value| deviation of the one-pass bf16 tower from the fp32 SIMT tower on probe positions
+        (``d_boards`` / ``d_who``: caller-supplied device boards, e.g. replay positions; default: cached random play-outs).
+        Returns the precision that keeps the 1e-3 contract and records the measurement in ``self.calibration``."""
+        if d_boards is None:
+            d_boards, d_who = probe_positions(self.game)
+        n = int(d_who.numel())
+        p32, v32 = self.forward_boards(d_boards, d_who, n, IMPL_SIMT)
+        p16, v16 = self.forward_boards(d_boards, d_who, n, IMPL_TCGEN05)
+        dp = float((p16 - p32).abs().max().item())
+        dv = float((v16 - v32).abs().max().item())
+        ok = dp <= CALIBRATION_MARGIN * PRIOR_TOLERANCE and dv <= CALIBRATION_MARGIN * PRIOR_TOLERANCE
+        self.calibration = {"positions": n, "max_abs_prior_diff": dp, "max_abs_value_diff": dv,
+                            "selected": "bf16" if ok else "bf16x3"}
+        return self.calibration["selected"]
 
     def update(self, net_or_state_dict):
-        """NetWrapper.sync() on the device side: re-fold and re-upload."""
+        """NetWrapper.sync() on the device side: re-fold, re-upload and (precision "auto") re-check the tolerance."""
         sd = net_or_state_dict.state_dict() if isinstance(net_or_state_dict, nn.Module) else net_or_state_dict
         blob = fold_state_dict(sd, self.rows, self.cols, self.actions)
         _cabi.check(_cabi.lib().caro_net_update(self.handle, blob.ctypes.data, blob.size))
+        self._select(self.requested)
 
     def forward_boards(self, d_boards, d_who, count: int, impl: int = None):
         """(priors [count,A], values [count]) float32 CUDA tensors for device boards."""

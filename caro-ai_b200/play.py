@@ -23,8 +23,8 @@ def main(argv=None):
     parser.add_argument("-r", "--rounds", type=int, default=2, help="Count of rounds to perform for every pair")
     parser.add_argument("--cuda", default=False, action="store_true", help="accepted for compatibility (always CUDA)")
     parser.add_argument("-g", "--game", required=True, choices=["0", "1"], help="The type of game. 0: Connect4, 1: TicTacToe")
-    parser.add_argument("--precision", default="bf16x3", choices=["bf16", "bf16x3"],
-                        help="tensor-core precision: bf16x3 (default) reproduces trained checkpoints' priors to 1e-3")
+    parser.add_argument("--precision", default="auto", choices=["auto", "bf16", "bf16x3"],
+                        help="tensor-core precision: auto (default) keeps the one-pass bf16 tower only while it reproduces the fp32 priors to 1e-3 on probe positions")
     args = parser.parse_args(argv)
     game = get_game(args.game)
     nets = []

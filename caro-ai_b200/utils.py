@@ -72,6 +72,24 @@ def play_game(game, mcts_stores, replay_buffer: Optional[collections.deque], net
     return net1_result, step
 
 
+def _max_plies(game) -> int:
+    return game.action_space if game.game_kind != 0 else 42
+
+
+def run_to_completion(eng: SelfPlayEngine, dn1, dn2, steps_before_tau_0: int, mcts_searches: int, mcts_batch_size: int,
+                      first_player: int) -> None:
+    """Plays every game of ``eng`` to its end (no re-seating): chunks of 8 plies, one status read between chunks."""
+    max_plies = _max_plies(eng.game)
+    plies = 0
+    while plies < max_plies:
+        chunk = min(8, max_plies - plies)
+        eng.play(dn1, dn2, moves=chunk, count=mcts_searches, batch=mcts_batch_size, tau_plies=steps_before_tau_0,
+                 auto_restart=False, first_player=first_player)
+        plies += chunk
+        if int((eng.region("status") == 0).sum().item()) == 0:
+            break
+
+
 def play_games_batched(game, n_games: int, net1, net2, steps_before_tau_0: int, mcts_searches: int,
                        mcts_batch_size: int, replay_buffer: Optional[collections.deque] = None,
                        net1_plays_first: Optional[bool] = None, trees_per_game: int = 2, node_capacity: Optional[int] = None,
@@ -81,11 +99,14 @@ def play_games_batched(game, n_games: int, net1, net2, steps_before_tau_0: int, 
     net1's point of view plus counters; finished games' ``(state, player, probs, z)`` tuples are appended to
     ``replay_buffer`` (lib/utils.py:101-106).
 
+    ``nn.Module`` networks are folded with ``DeviceNet(precision="auto")``: the one-pass bf16 tower only while it
+    reproduces the fp32 priors / values within 1e-3 on probe positions, the split-precision tower otherwise.
+
     Two different networks require lock-step plies, so each half of the games gets a fixed first player when
     ``net1_plays_first`` is None (the reference draws it per game: same distribution, lib/utils.py:66)."""
     dn1 = net1 if isinstance(net1, model.DeviceNet) else model.DeviceNet(net1, game)
     dn2 = dn1 if net2 is net1 else (net2 if isinstance(net2, model.DeviceNet) else model.DeviceNet(net2, game))
-    max_plies = game.action_space if game.game_kind != 0 else 42
+    max_plies = _max_plies(game)
     cap = node_capacity or min(1 << 16, mcts_searches * mcts_batch_size * max_plies + 8)
     totals = {"wins": 0, "losses": 0, "draws": 0, "games": 0, "plies": 0, "leaf_evals": 0}
     if dn1 is dn2:
@@ -100,14 +121,7 @@ def play_games_batched(game, n_games: int, net1, net2, steps_before_tau_0: int, 
         eng = SelfPlayEngine(game, count, trees_per_game=trees_per_game, max_batch=mcts_batch_size, node_capacity=cap,
                              replay_capacity=count * max_plies if replay_buffer is not None else 0, seed=seed + part)
         eng.reset(first_player=first)
-        plies = 0
-        while plies < max_plies:
-            chunk = min(8, max_plies - plies)
-            eng.play(dn1, dn2, moves=chunk, count=mcts_searches, batch=mcts_batch_size, tau_plies=steps_before_tau_0,
-                     auto_restart=False, first_player=first if dn1 is not dn2 else first)
-            plies += chunk
-            if int((eng.region("status") == 0).sum().item()) == 0:
-                break
+        run_to_completion(eng, dn1, dn2, steps_before_tau_0, mcts_searches, mcts_batch_size, first)
         c = eng.counters()
         assert c["errors"] == 0, "engine reported errors: %d" % c["errors"]
         totals["wins"] += c["wins_p0"]
@@ -120,7 +134,48 @@ def play_games_batched(game, n_games: int, net1, net2, steps_before_tau_0: int, 
             entries, _ = eng.drain_replay()
             replay_buffer.extend(entries)
         eng.close()
+    for dn, src in ((dn1, net1), (dn2, net2)):
+        if dn is not src:
+            dn.close()
     return totals
+
+
+class SelfPlayWorker:
+    """The trainer's self-play side (train.py:25-59 for ``games`` games at once): ONE engine that lives as long as the
+    training run -- its arenas are re-seated every step, not re-allocated -- and whose device replay ring is the
+    replay buffer (``replay_capacity`` entries; SURVEY.md section 8(d)-3: the reference's 5,000 positions are ~200
+    single-game steps, so the ring is sized in steps of ``games`` games, not in positions)."""
+
+    def __init__(self, game, games: int, mcts_searches: int, mcts_batch_size: int, steps_before_tau_0: int,
+                 replay_steps: int = 4, min_replay: int = 5000, seed: int = 0, node_capacity: Optional[int] = None):
+        self.game, self.games = game, int(games)
+        self.searches, self.batch, self.tau_plies = mcts_searches, mcts_batch_size, steps_before_tau_0
+        max_plies = _max_plies(game)
+        cap = node_capacity or min(1 << 16, mcts_searches * mcts_batch_size * max_plies + 8)
+        self.replay_capacity = max(int(min_replay), replay_steps * self.games * max_plies)
+        self.engine = SelfPlayEngine(game, self.games, trees_per_game=1, max_batch=mcts_batch_size, node_capacity=cap,
+                                     replay_capacity=self.replay_capacity, seed=seed)
+        self._last = self.engine.counters()
+
+    def play_step(self, net: "model.DeviceNet") -> Dict[str, int]:
+        """Every game slot plays one fresh game to its end with ``net`` on both sides; the finished games' positions go
+        to the ring.  Returns this step's counters (plies, leaf_evals, games, wins / losses / draws of player 0)."""
+        eng = self.engine
+        eng.reset(first_player=-1)  # new game ids -> new Philox streams, cleared trees (MCTS.clear, no memset)
+        run_to_completion(eng, net, net, self.tau_plies, self.searches, self.batch, -1)
+        c = eng.counters()
+        if c["errors"]:
+            raise RuntimeError("self-play engine reported error bits %d" % c["errors"])
+        d = {k: c[k] - self._last[k] for k in c}
+        self._last = c
+        return {"wins": d["wins_p0"], "losses": d["wins_p1"], "draws": d["draws"], "games": d["games"], "plies": d["plies"],
+                "leaf_evals": d["leaf_evals"]}
+
+    def replay_len(self) -> int:
+        return self.engine.replay_live()
+
+    def close(self):
+        self.engine.close()
 
 
 class TBMeanTracker:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CARO_ABI_VERSION 1
+#define CARO_ABI_VERSION 2
 
 enum { CARO_OK = 0, CARO_E_ARG = -1, CARO_E_CUDA = -2, CARO_E_STATE = -3, CARO_E_CAPACITY = -4 };
 
@@ -130,7 +130,7 @@ typedef struct {
   int32_t n, k;            /* m,n,k only */
   int32_t games;           /* G */
   int32_t trees_per_game;  /* 1 or 2 */
-  int32_t max_batch;       /* largest batch_size (descents per minibatch) that will be used */
+  int32_t max_batch;       /* largest batch_size (descents per minibatch) that will be used, 1..32 */
   int32_t node_capacity;   /* nodes per tree arena */
   int32_t replay_capacity; /* entries in the device replay ring (0 = no replay recording) */
   double c_puct;           /* config.py:26 */
@@ -182,9 +182,12 @@ int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs,
                               const float* d_values, void* stream);
 
 /* MCTS.search_batch (lib/mcts.py:162-176) with the built-in network: `count` x
- * (select, plan, net forward, expand_backup), no host synchronisation inside. */
-int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int net_impl,
-                       void* stream);
+ * (select, plan, net forward, expand_backup), no host synchronisation inside.  The minibatches are
+ * numbered first_minibatch .. first_minibatch + count - 1 for the Philox noise address (the reference draws
+ * fresh Dirichlet noise for every descent, lib/mcts.py:131-132: a caller that searches the same game, ply and
+ * side repeatedly passes a running index so that no noise vector is replayed). */
+int caro_engine_search(caro_engine* e, caro_net* net, int count, int batch, int first_minibatch,
+                       int net_impl, void* stream);
 
 /* MCTS.get_policy_value (lib/mcts.py:289-313) for every game's root:
  * d_pi float64 [G][A], d_q float32 [G][A], d_n int32 [G][A].  tau_mode: 0 -> tau = 0, 1 -> tau = 1,
@@ -205,17 +208,22 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
                      int batch, int tau_plies, int auto_restart, int first_player, int net_impl,
                      void* stream);
 
-/* Same for two engines (two halves of the game batch) as a software pipeline: the network passes of both run
- * back to back on `stream`, the tree kernels (noise/select/plan, expand+backup, advance) of each engine on a
- * private side stream, chained by CUDA events -- one half's tree kernels execute underneath the other half's
- * network pass.  Self-play only (one network).  `stream` is joined with the side streams before returning. */
-int caro_engine_play_pair(caro_engine* e0, caro_engine* e1, caro_net* net, int moves, int count, int batch,
-                          int tau_plies, int auto_restart, int first_player, int net_impl, void* stream);
-/* General form: n = 1..8 parts in round robin.  With three parts the tree kernels of one part have two network
+/* The same plies for n = 1..8 engines (parts of the game batch) as a software pipeline: every part's kernels run
+ * on a private side stream, chained by CUDA events -- one part's tree kernels (noise / select / plan, expand+backup,
+ * advance) execute underneath the other parts' network passes.  Self-play only (one network).  `stream` is joined
+ * with the side streams before returning. General form: n = 1..8 parts in round robin.  With three parts the tree kernels of one part have two network
  * passes to hide under (they run 3-5x slower next to the persistent network kernel than alone).  While profiling
  * is off, one ply (n x count x 5 kernels + n) is captured into a CUDA graph once and replayed per ply. */
 int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int moves, int count, int batch,
                            int tau_plies, int auto_restart, int first_player, int net_impl, void* stream);
+
+/* train.py:85-94 (`random.sample(replay_buffer, BATCH_SIZE)` -> states_to_training_batch / probs / values tensors) on the
+ * device: `d_entries` int64 [count] are absolute entry numbers of the replay ring (entry k lives in slot k % replay_capacity;
+ * valid numbers are [cursor - min(cursor, capacity), cursor), "replay_cursor" region); the rows are written as
+ * d_planes float32 [count][2][H][W] (from the stored side to move's point of view), d_pi float32 [count][A] and
+ * d_z float32 [count] (lib/utils.py:101-106) without a host round trip. */
+int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, int64_t count, float* d_planes, float* d_pi,
+                              float* d_z, void* stream);
 
 /* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
  * profile_read synchronises `stream` and returns the summed milliseconds of

@@ -37,3 +37,13 @@ def golden_play():
 @pytest.fixture(scope="session")
 def golden_net():
     return load_golden("net.json")
+
+
+@pytest.fixture(scope="session")
+def golden_render():
+    return load_golden("render.json")
+
+
+@pytest.fixture(scope="session")
+def golden_train():
+    return load_golden("train.json")

@@ -55,7 +55,17 @@ def _worker(rank, world_size, port, results):
     ok_grad = ok_grad and ok_bucket
     tall = D.reduce_tallies(rank + 1, 10 * (rank + 1), 0)
     first, count = D.shard_games(4097, rank, world_size)
-    results[rank] = (same, ok_grad, n, tall, first, count)
+    # train.py:199 taken collectively: rank 0 holds 2,500 replay entries, rank 1 only 1,500 -> BOTH skip the SGD rounds
+    # (a per-rank decision would leave rank 0 alone inside its gradient all-reduces)
+    decision = D.all_min(2500 if rank == 0 else 1500) >= 2000
+    # the SGD batch assembled from the ranks' replay samples: rank order, every rank gets the same 256 rows
+    rows = 128
+    mine = (torch.full((rows, 2, 6, 7), float(rank)), torch.full((rows, 7), float(rank) + 0.5), torch.full((rows,), float(-rank)))
+    planes, pi, z = D.all_gather_rows(mine)
+    ok_gather = planes.shape == (256, 2, 6, 7) and pi.shape == (256, 7) and z.shape == (256,) \
+        and bool((planes[:rows] == 0).all()) and bool((planes[rows:] == 1).all()) \
+        and bool((pi[:rows] == 0.5).all()) and bool((pi[rows:] == 1.5).all()) and bool((z[rows:] == -1).all())
+    results[rank] = (same, ok_grad, n, tall, first, count, decision, ok_gather)
     dist.destroy_process_group()
 
 
@@ -70,3 +80,5 @@ def test_two_rank_collectives():
     assert r0[2] == r1[2] == 188301  # trainable parameters of the Connect4 network
     assert r0[3] == r1[3] == (3, 30, 0)
     assert (r0[4], r0[5], r1[4], r1[5]) == (0, 2049, 2049, 2048)
+    assert r0[6] is False and r1[6] is False, "train-or-skip must be decided on the smallest ring"
+    assert r0[7] and r1[7], "all_gather_rows did not assemble the batch in rank order"

@@ -218,7 +218,7 @@ def _net_errors(game, net, impl, rng):
     pos = [random_position(og, rng, int(rng.integers(0, min(40, max(1, cells - 4))))) for _ in range(count)]
     states, players = [p[0] for p in pos], [p[1] for p in pos]
     ref_p, ref_v = _reference_outputs(game, net, states, players)
-    dn = DeviceNet(net, game)
+    dn = DeviceNet(net, game, precision="bf16")  # the implementation under test is passed explicitly
     p, v = dn.forward_states(states, players, impl=impl)
     p, v = p.cpu().numpy(), v.cpu().numpy()
     dn.close()
@@ -236,15 +236,17 @@ def test_net_fp32_kernel_matches_pytorch(torch_cuda):
 
 
 def test_net_tcgen05_matches_pytorch(torch_cuda):
-    """bf16 tcgen05 tower vs PyTorch fp32: 1e-3 absolute on priors AND values for random-init networks (the
-    benchmark configuration, BASELINE.json north_star).  Trained checkpoints have policy logits of +-100, which
-    a single bf16 pass cannot resolve to 1e-3: they get the stated looser gate below."""
+    """One-pass bf16 tcgen05 tower (impl 0) vs PyTorch fp32: 1e-3 absolute on priors AND values for the random-init
+    networks (the benchmark configuration, BASELINE.json north_star).  Trained checkpoints have policy logits of +-100,
+    which a single bf16 pass cannot resolve to 1e-3: the product never runs them through impl 0 --
+    `DeviceNet(precision="auto")` moves them to the split-precision tower, and THAT selection is held to 1e-3 on every
+    network, trained ones included, in tests/test_gpu_round2.py::test_auto_precision_keeps_the_contract_on_every_network."""
     rng = np.random.default_rng(3)
-    gates = {"c4-trained": (0.5, 0.3, 0.97), "ttt-trained": (1e-2, 2e-2, 0.99)}
     for tag, game, net in _net_cases():
+        if tag.endswith("-trained"):
+            continue
         dp, dv, agree = _net_errors(game, net, 0, rng)
-        gp, gv, ga = gates.get(tag, (1e-3, 1e-3, 0.99))
-        assert dp < gp and dv < gv and agree >= ga, (tag, dp, dv, agree)
+        assert dp < 1e-3 and dv < 1e-3 and agree >= 0.99, (tag, dp, dv, agree)
 
 
 def test_net_tcgen05_x3_matches_pytorch_on_trained_checkpoints(torch_cuda):

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(_cabi.exported_symbols()) <= declared, set(_cabi.exported_symbols()) - declared
-    assert lib.caro_abi_version() == 1
+    assert lib.caro_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
@@ -50,7 +50,7 @@ def test_engine_config_validation():
     bad = [_cabi.EngineConfig(7, 0, 0, 4, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0),      # unknown game
            _cabi.EngineConfig(1, 16, 5, 4, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0),     # n > 15
            _cabi.EngineConfig(0, 0, 0, 4, 3, 8, 64, 0, 1.0, 0.3, 0.25, 0),      # trees_per_game
-           _cabi.EngineConfig(0, 0, 0, 4, 1, 65, 64, 0, 1.0, 0.3, 0.25, 0),     # max_batch
+           _cabi.EngineConfig(0, 0, 0, 4, 1, 33, 64, 0, 1.0, 0.3, 0.25, 0),     # max_batch
            _cabi.EngineConfig(0, 0, 0, 0, 1, 8, 64, 0, 1.0, 0.3, 0.25, 0)]      # no games
     for cfg in bad:
         assert lib.caro_engine_workspace_bytes(C.byref(cfg)) == 0
@@ -155,9 +155,72 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "connect4_mcts_leaf_evals_per_sec" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    vendored = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "lib", "mcts.py"))  # build() copies the unmodified reference
+    assert d["cpu_baseline"]["kind"] == ("reference" if vendored else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     # ranks other than 0 stay silent under torchrun
     env["RANK"] = "1"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_render_strings_match_the_reference(golden_render):
+    """game.render (connect_four.py:267-281, tictactoe.py:237-259) and Session.render (play_session.py:38-49) byte for
+    byte against strings produced by the unmodified reference (tests/golden/make_golden2.py)."""
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.play_session import Session
+
+    def game_of(tag):
+        if tag == "connect4":
+            return ConnectFour()
+        _, n, k = tag.split(":")
+        return TicTacToe(int(n), int(k))
+    total = 0
+    for block in golden_render["games"]:
+        g = game_of(block["game"])
+        for row in block["positions"]:
+            assert g.render(row["state"]) == row["render"], (block["game"], row["state"])
+            total += 1
+    assert total >= 60
+    for row in golden_render["sessions"]:
+        s = Session.__new__(Session)  # the string needs no checkpoint, tree or GPU
+        s.game, s.state, s.value = game_of(row["game"]), row["state"], row["value"]
+        assert s.render() == row["render"]
+
+
+def test_sgd_losses_match_the_reference_train_step(golden_train):
+    """train.py:95-106 (MSE + soft-target cross-entropy) on the first batch the reference's train_neural_net drew from the
+    fixture's replay buffer (same `random` seed, same Net seed): value / policy loss to 1e-5.  CPU, like the reference ran
+    it; the planes come from the oracle's encoder here (the CUDA encoder's parity is a -m gpu test)."""
+    import random
+    from caro_ai_b200 import config as cfg
+    from caro_ai_b200.model import Net
+    from caro_ai_b200.train import sgd_losses
+    from helpers import oracle_game
+    for case in golden_train:
+        og = oracle_game(case["game"])
+        replay = collections.deque([(s, p, pi, z) for s, p, pi, z in case["replay"]], maxlen=cfg.REPLAY_BUFFER)
+        random.seed(case["sample_seed"])
+        batch = random.sample(replay, cfg.BATCH_SIZE)
+        assert [b[0] for b in batch[:8]] == case["first_batch_states"]
+        torch.manual_seed(case["net_seed"])
+        net = Net(og.obs_shape, og.action_space)
+        for k, v in net.state_dict().items():
+            if v.dtype.is_floating_point:
+                assert abs(float(v.double().sum()) - case["init_sum"][k]) < 1e-9, k  # same initial weights as the reference's Net
+        net.train()
+        planes = torch.tensor(og.states_to_training_batch([b[0] for b in batch], [b[1] for b in batch]))
+        total, lv, lp = sgd_losses(net, planes, torch.FloatTensor([b[2] for b in batch]), torch.FloatTensor([b[3] for b in batch]))
+        assert abs(lv.item() - case["round0"]["loss_value"]) < 1e-5
+        assert abs(lp.item() - case["round0"]["loss_policy"]) < 1e-5
+        assert abs(total.item() - (lv.item() + lp.item())) < 1e-6
+
+
+def test_single_rank_collective_helpers_are_identities():
+    from caro_ai_b200 import distributed as D
+    assert D.all_min(1234) == 1234
+    t = (torch.ones(3, 2), torch.zeros(3))
+    out = D.all_gather_rows(t)
+    assert out[0] is t[0] and out[1] is t[1]
+    assert D.reduce_tallies(1, 2, 3) == (1, 2, 3)
