@@ -151,7 +151,9 @@ int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats) {
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   const int rc = caro_net_tc_pack(net, h_blob);
   if (rc != CARO_OK) return rc;
-  return caro_net_rt_supports(net) ? caro_net_rt_pack(net, h_blob) : CARO_OK;
+  if (!caro_net_rt_supports(net)) return CARO_OK;
+  const int rc2 = caro_net_rt_pack(net, h_blob);
+  return rc2 != CARO_OK ? rc2 : caro_net_rx_pack(net, h_blob);
 }
 
 int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t n_floats, caro_net** out) {
@@ -169,6 +171,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_blob = nullptr;
   net->d_tc_weights = nullptr;
   net->d_rt_weights = nullptr;
+  net->d_rx_weights = nullptr;
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;
   net->d_trace = nullptr;
@@ -184,6 +187,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
     cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
     int prc = caro_net_tc_prepare();
     if (prc == CARO_OK) prc = caro_net_rt_prepare();
+    if (prc == CARO_OK) prc = caro_net_rx_prepare();
     if (prc != CARO_OK) {
       delete net;
       return prc;
@@ -224,6 +228,7 @@ void caro_net_destroy(caro_net* net) {
   caro_pipeline_forget(0, net->serial);
   caro_net_tc_free(net);
   caro_net_rt_free(net);
+  caro_net_rx_free(net);
   if (net->d_blob) cudaFree(net->d_blob);
   delete net;
 }
@@ -246,8 +251,10 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
   }
   if (impl == 0 && caro_net_rt_supports(net))
     return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
-  if (impl == 0 || impl == 2 || impl == 3)
-    return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 2 ? 1 : 0, st);
+  if (impl == 2 && caro_net_rt_supports(net))
+    return caro_net_rx_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if (impl == 0 || impl == 2 || impl == 3 || impl == 4)
+    return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, (impl == 2 || impl == 4) ? 1 : 0, st);
   return caro_fail(CARO_E_ARG, "unknown net impl");
 }
 

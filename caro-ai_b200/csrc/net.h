@@ -53,6 +53,7 @@ struct caro_net {
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
+  void* d_rx_weights;   // fp16 hi / lo UMMA B-operand blocks of the split-precision row-tiled tower -- see net_rx.cu
   alignas(16) float h_rt_consts[6 * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
@@ -83,4 +84,11 @@ int caro_net_rt_prepare();
 void caro_net_rt_free(caro_net* net);
 bool caro_net_rt_supports(const caro_net* net);
 int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);
+
+// net_rx.cu (split-precision row-tiled tower, fp16 hi + lo, boards up to 6 x 7)
+int caro_net_rx_pack(caro_net* net, const float* h_blob);
+int caro_net_rx_prepare();
+void caro_net_rx_free(caro_net* net);
+int caro_net_rx_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                         const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);

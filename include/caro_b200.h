@@ -111,8 +111,11 @@ int caro_net_set_grid_limit(caro_net* net, int ctas);
  *   impl    : 0 = tcgen05 bf16 tensor-core tower (product path: one bf16 pass, fp32 accumulate); boards up to
  *                 6 x 7 run the row-tiled kernel (net_rt.cu), larger ones the tap-per-MMA kernel (net_tc.cu),
  *             3 = tcgen05 bf16 tower, tap-per-MMA kernel for every board size (A/B comparisons),
- *             2 = tcgen05 "bf16x3" tower (hi/lo split of activations and weights, 3 MMAs per product:
- *                 fp32-class accuracy for trained checkpoints with large logits, ~1/3.5 of the speed),
+ *             2 = split-precision tcgen05 tower (hi / lo pairs of activations and weights, 3 MMAs per product:
+ *                 fp32-class accuracy for trained checkpoints with large logits).  Boards up to 6 x 7 run the
+ *                 row-tiled fp16 hi + lo kernel (net_rx.cu, ~2.2x the one-pass time), larger ones the
+ *                 tap-per-MMA bf16 hi + lo kernel (net_tc.cu, ~3.5x),
+ *             4 = the tap-per-MMA split-precision kernel for every board size (A/B comparisons),
  *             1 = fp32 SIMT tower (numerics reference kernel used by the tests). */
 int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards,
                      const uint8_t* d_who, const int32_t* d_count, int64_t max_count,

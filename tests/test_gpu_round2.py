@@ -239,6 +239,49 @@ def test_auto_precision_keeps_the_contract_on_every_network(torch_cuda):
         d.close()
 
 
+def test_split_precision_row_tiled_tower(torch_cuda):
+    """net_rx.cu (impl 2 for boards <= 6 x 7: fp16 hi + lo activations and weights, three MMAs per product, block-major
+    weight streaming) vs PyTorch fp32: 5e-4 on priors and values for the shipped trained checkpoints (policy logits of
+    +-100; the one-pass bf16 tower is off by 0.2 there) and for random-init networks on every geometry class the
+    row-tiled towers serve, ragged leaf counts and several passes per CTA included; bit-identical from run to run; and
+    agreement with the tap-per-MMA split kernel (impl 4)."""
+    torch = torch_cuda
+    from test_gpu_parity import _net_cases, _random_net, _reference_outputs
+    from harness import random_position
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(21)
+    cases = [(tag, game, net, (300,)) for tag, game, net in _net_cases() if game.obs_shape[1] <= 6]
+    cases += [("c4-ragged", ConnectFour(), _random_net(ConnectFour()), (1, 15, 16, 17, 2400, 5000)),
+              ("ttt-ragged", TicTacToe(3, 3), _random_net(TicTacToe(3, 3)), (1, 31, 33, 4800)),
+              ("mnk43", TicTacToe(4, 3), _random_net(TicTacToe(4, 3)), (5, 40)),
+              ("mnk64", TicTacToe(6, 4), _random_net(TicTacToe(6, 4)), (3, 37))]
+    for tag, game, net, counts in cases:
+        og = oracle_for(game)
+        cells = game.obs_shape[1] * game.obs_shape[2]
+        dn = DeviceNet(net, game, precision="bf16x3")
+        for count in counts:
+            base = [random_position(og, rng, int(rng.integers(0, max(1, cells - 3)))) for _ in range(min(count, 300))]
+            pos = [base[i % len(base)] for i in range(count)]
+            states, players = [p[0] for p in pos], [p[1] for p in pos]
+            ref_p, ref_v = _reference_outputs(game, net, states[:len(base)], players[:len(base)])
+            p2, v2 = dn.forward_states(states, players, impl=2)
+            p2b, v2b = dn.forward_states(states, players, impl=2)
+            p4, v4 = dn.forward_states(states, players, impl=4)
+            torch.cuda.synchronize()
+            assert torch.equal(p2, p2b) and torch.equal(v2, v2b), (tag, count)
+            p2, v2, p4, v4 = p2.cpu().numpy(), v2.cpu().numpy(), p4.cpu().numpy(), v4.cpu().numpy()
+            assert np.isfinite(p2).all() and np.isfinite(v2).all()
+            n = len(base)
+            for i in range(0, count, n):
+                m = min(n, count - i)
+                dp, dv = np.abs(p2[i:i + m] - ref_p[:m]).max(), np.abs(v2[i:i + m] - ref_v[:m]).max()
+                assert dp < 5e-4 and dv < 5e-4, (tag, count, i, dp, dv)
+                assert (p2[i:i + m].argmax(1) == ref_p[:m].argmax(1)).all()
+            assert np.abs(p2 - p4).max() < 1e-3 and np.abs(v2 - v4).max() < 1e-3
+        dn.close()
+
+
 # --------------------------------------------------------------------------- replay ring -> SGD batch
 def test_replay_gather_and_train_step_match_the_reference(torch_cuda, golden_train):
     """train.py:82-111 with the batch assembled on the device: the fixture's replay buffer is loaded into the engine's

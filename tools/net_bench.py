@@ -20,7 +20,7 @@ def main():
     game = ConnectFour()
     torch.manual_seed(0)
     net = Net(game.obs_shape, game.action_space).eval()
-    dn = DeviceNet(net, game)
+    dn = DeviceNet(net, game, precision="bf16")
     rng = np.random.default_rng(0)
     # random legal-looking boards: random heights, random colours
     boards = np.zeros((leaves, 2), dtype=np.uint64)
