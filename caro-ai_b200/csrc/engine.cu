@@ -61,8 +61,8 @@ struct caro_engine {
   int profiling = 0;  // 0 off, 1 network spans only (cheap: 2 events per minibatch), 2 all four phases
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
-  std::vector<std::pair<size_t, size_t>> spans[4];  // (start, end) event indices per phase
-  size_t open_span[4] = {0, 0, 0, 0};
+  std::vector<std::pair<size_t, size_t>> spans[5];  // (start, end) event indices per phase (4 = Dirichlet noise kernel)
+  size_t open_span[5] = {0, 0, 0, 0, 0};
   unsigned long long launches = 0;
   cudaEvent_t sync_a = nullptr, sync_b = nullptr;  // cross-stream hand-offs (pair pipeline)
   bool lean_tree = false;  // set while the parts pipeline issues launches: prefer tree kernels with few warps
@@ -117,18 +117,10 @@ void build_view(Carver& c, const Dims& dm, char* base, View<Board>* v) {
   CARVE(hist_board, "hist_board", Board, dm.G, dm.max_plies);
   CARVE(hist_player, "hist_player", uint8_t, dm.G, dm.max_plies);
   CARVE(hist_pi, "hist_pi", float, dm.G, dm.max_plies, dm.A);
-  CARVE(d_kind, "desc_kind", uint8_t, dm.G, dm.B);
-  CARVE(d_value, "desc_value", float, dm.G, dm.B);
-  CARVE(d_board, "desc_board", Board, dm.G, dm.B);
-  CARVE(d_player, "desc_player", uint8_t, dm.G, dm.B);
-  CARVE(d_key_lo, "desc_key_lo", uint64_t, dm.G, dm.B);
-  CARVE(d_key_hi, "desc_key_hi", uint64_t, dm.G, dm.B);
-  CARVE(d_path_len, "desc_path_len", int32_t, dm.G, dm.B);
-  CARVE(d_path_node, "desc_path_node", int32_t, dm.G, dm.B, dm.max_depth);
-  CARVE(d_path_action, "desc_path_action", uint8_t, dm.G, dm.B, dm.max_depth);
-  CARVE(d_slot, "desc_slot", int32_t, dm.G, dm.B);
+  CARVE(desc, "desc", DescRec<Board>, dm.G, dm.B);
+  CARVE(d_path, "desc_path", uint32_t, dm.G, dm.B, dm.max_depth);
   CARVE(q_len, "queue_len", int32_t, dm.G);
-  CARVE(q_order, "queue_order", uint8_t, dm.G, dm.B);
+  CARVE(q_entry, "queue", QEntry, dm.G, dm.B);
   CARVE(leaf_board, "leaf_board", Board, GB);
   CARVE(leaf_player, "leaf_player", uint8_t, GB);
   CARVE(leaf_count, "leaf_count", int32_t, 2);
@@ -301,11 +293,11 @@ int caro_engine_profile(caro_engine* e, int enable) {
   return CARO_OK;
 }
 
-int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launches, void* stream) {
+int caro_engine_profile_read(caro_engine* e, double h_ms[5], uint64_t* h_launches, void* stream) {
   if (!e || !h_ms) return caro_fail(CARO_E_ARG, "null argument");
   cudaError_t ce = cudaStreamSynchronize(S(stream));
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
-  for (int ph = 0; ph < 4; ++ph) {
+  for (int ph = 0; ph < 5; ++ph) {
     h_ms[ph] = 0.0;
     for (const auto& sp : e->spans[ph]) {
       float ms = 0.0f;
@@ -410,8 +402,9 @@ int caro_engine_expand_backup(caro_engine* e, int batch, const float* d_probs, c
   } while (0)
   // eight lanes per game inside the parts pipeline (a quarter of the warps: +2.5 % there, where the tree kernels live in
   // the warp slots next to tower CTAs), one warp per game otherwise (20 us instead of 36 us stand-alone at 4,096 games)
-  static const bool group8 = !(getenv("CARO_EXPAND_GROUP8") && atoi(getenv("CARO_EXPAND_GROUP8")) == 0);
-  if (batch <= 8 && e->dm.Apad <= 8 && c4 && group8 && e->lean_tree) {
+  static const int group8 = getenv("CARO_EXPAND_GROUP8") ? atoi(getenv("CARO_EXPAND_GROUP8")) : 1;  // 0 never, 1 auto, 2 always
+  // (and stand-alone from 32 k games per launch: 138 us instead of 194 us at 65,536 games -- a quarter of the warps, one wave less)
+  if (batch <= 8 && e->dm.Apad <= 8 && c4 && group8 && (e->lean_tree || group8 == 2 || e->dm.G >= 32768)) {
     const unsigned g8 = (unsigned)(((long long)e->dm.G * 8 + 127) / 128);
     expand_backup_group8_kernel<C4Rules><<<g8, 128, 0, S(stream)>>>(e->v_c4, e->dm, batch, d_probs, d_values);
   } else if (batch <= 8) LAUNCH_EB(8);
@@ -446,13 +439,14 @@ static int search_step(caro_engine* e, caro_net* net, int i, int batch, int net_
     cudaEventCreateWithFlags(&e->sync_a, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->sync_b, cudaEventDisableTiming);
   }
-  e->span_begin(0, s_tree);
   int rc = CARO_OK;
-  if (prefetch && i > 0) {
-    rc = select_phase(e, batch, i, 2, s_tree);
-  } else {
-    rc = caro_engine_select(e, batch, i, nullptr, nullptr, s_tree);
+  if (!(prefetch && i > 0)) {  // this minibatch's Dirichlet vectors (in the pipeline they were issued under the previous network pass)
+    e->span_begin(4, s_tree);
+    rc = select_phase(e, batch, i, 1, s_tree);
+    e->span_end(4, s_tree);
   }
+  e->span_begin(0, s_tree);
+  if (rc == CARO_OK) rc = select_phase(e, batch, i, 2, s_tree);
   e->span_end(0, s_tree);
   e->span_begin(1, s_tree);
   if (rc == CARO_OK) rc = caro_engine_plan(e, batch, s_tree);

@@ -23,6 +23,34 @@ struct alignas(16) HashSlot {
   uint32_t gen;   // slot is live iff gen == tree_gen[tree] (clear() == ++gen, no memset)
 };
 
+// One descent of the current minibatch (lib/mcts.py:97-148 returns value, leaf state, leaf player, states[], actions[]).
+// ONE record per descent -- 64 bytes for Connect4 (two sectors of one line), 96 for m,n,k -- instead of eight parallel
+// arrays: select writes it with four 16-byte stores, plan and expand+backup read what they need with one or two loads
+// (the parallel arrays cost ~10 sectors per descent for <= 40 useful bytes: 4.8x the algorithmic DRAM traffic).
+struct alignas(16) DescHead {
+  uint8_t kind;      // KIND_*
+  uint8_t player;    // side to move at the leaf
+  uint16_t len;      // path length (edges from the root to the leaf)
+  int32_t slot;      // compact leaf slot of an expand entry (plan), -1 otherwise
+  float value;       // terminal value (-1 / 0), lib/mcts.py:140-146
+  uint32_t pad_;
+  uint64_t key_lo, key_hi;  // transposition key of the leaf
+};
+template <class Board>
+struct alignas(32) DescRec {
+  DescHead h;
+  Board board;       // leaf position
+};
+
+// One entry of a game's back-up queue in back-up order (lib/mcts.py:269-278): everything expand+backup needs to start
+// its loads at once (no order -> kind -> slot -> value chain).  `slot` holds the float bits of the value for a terminal.
+struct alignas(8) QEntry {
+  uint8_t j;         // descent index within the minibatch
+  uint8_t kind;
+  uint16_t len;
+  int32_t slot;
+};
+
 struct Dims {
   int G;          // games
   int tpg;        // trees per game
@@ -73,19 +101,11 @@ struct View {
   uint8_t* hist_player;  // [G][max_plies]
   float* hist_pi;      // [G][max_plies][A]
   // ---- per descent (index = g*B + j) -------------------------------------------------------
-  uint8_t* d_kind;
-  float* d_value;
-  Board* d_board;
-  uint8_t* d_player;
-  uint64_t* d_key_lo;
-  uint64_t* d_key_hi;
-  int32_t* d_path_len;
-  int32_t* d_path_node;    // [G*B][max_depth]
-  uint8_t* d_path_action;  // [G*B][max_depth]
-  int32_t* d_slot;         // compact leaf slot of an expand entry, -1 otherwise
+  DescRec<Board>* desc;    // [G*B]
+  uint32_t* d_path;        // [G*B][max_depth]  (arena-local node index << 8) | action, root first
   // ---- minibatch plan ----------------------------------------------------------------------
   int32_t* q_len;      // [G]
-  uint8_t* q_order;    // [G][B] descent indices in back-up order
+  QEntry* q_entry;     // [G][B] back-up queue
   // ---- compact leaf batch ------------------------------------------------------------------
   Board* leaf_board;   // [G*B]
   uint8_t* leaf_player;  // [G*B]

@@ -69,6 +69,36 @@ __device__ __forceinline__ int ht_lookup1(const HashSlot* __restrict__ ht, int c
   return -1;
 }
 
+// The descent's record (engine.cuh): head = two 16-byte stores, board = 16-byte stores.
+template <class Board>
+__device__ __forceinline__ void store_desc(DescRec<Board>* __restrict__ rec, int kind, int player, int len, float value, Key128 key,
+                                           const Board& board) {
+  DescHead h;
+  h.kind = (uint8_t)kind;
+  h.player = (uint8_t)player;
+  h.len = (uint16_t)len;
+  h.slot = -1;
+  h.value = value;
+  h.pad_ = 0u;
+  h.key_lo = key.lo;
+  h.key_hi = key.hi;
+  rec->h = h;
+  rec->board = board;
+}
+template <class Board>
+__device__ __forceinline__ void store_desc_skip(DescRec<Board>* __restrict__ rec) {
+  DescHead h;
+  h.kind = KIND_SKIP;
+  h.player = 0;
+  h.len = 0;
+  h.slot = -1;
+  h.value = 0.0f;
+  h.pad_ = 0u;
+  h.key_lo = 0ull;
+  h.key_hi = 0ull;
+  rec->h = h;
+}
+
 template <class R>
 struct RulesTraits {
   static constexpr bool kHasKeyHi = true;
@@ -135,10 +165,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   const int g = (int)(grp / batch), j = (int)(grp % batch);
   const size_t di = (size_t)g * dm.B + j;
   if (e.status[g] != ST_ACTIVE) {
-    if (gl == 0) {
-      e.d_kind[di] = KIND_SKIP;
-      e.d_slot[di] = -1;
-    }
+    if (gl == 0) store_desc_skip(e.desc + di);
     return;
   }
   const int A = dm.A;
@@ -157,8 +184,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
   int depth = 0;
   int kind = KIND_EXPAND;
   float term_value = 0.0f;
-  int32_t* path_node = e.d_path_node + di * dm.max_depth;
-  uint8_t* path_action = e.d_path_action + di * dm.max_depth;
+  uint32_t* path = e.d_path + di * dm.max_depth;
 
   while (node >= 0) {
     const size_t row = (nb + (size_t)node) * dm.RS;
@@ -246,10 +272,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
       }
     }
     const int a = best_a;
-    if (gl == 0) {
-      path_node[depth] = node;
-      path_action[depth] = (uint8_t)a;
-    }
+    if (gl == 0) path[depth] = ((uint32_t)node << 8) | (uint32_t)a;
     ++depth;
     const bool won = rules.apply(s, a, who);  // lib/mcts.py:138-139
     who ^= 1;
@@ -277,16 +300,7 @@ select_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int 
       if (node >= 0 && gl == 0) e.C[row + a] = node;
     }
   }
-  if (gl == 0) {
-    e.d_kind[di] = (uint8_t)kind;
-    e.d_value[di] = term_value;
-    e.d_board[di] = s;
-    e.d_player[di] = (uint8_t)who;
-    e.d_key_lo[di] = key.lo;
-    e.d_key_hi[di] = key.hi;
-    e.d_path_len[di] = depth;
-    e.d_slot[di] = -1;
-  }
+  if (gl == 0) store_desc(e.desc + di, kind, who, depth, term_value, key, s);
 }
 
 // Thread-per-descent variant for small action spaces (A <= 16: Connect4, 3x3 / 4x4 boards).  The board update,
@@ -302,8 +316,7 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
   const int g = (int)(grp / batch), j = (int)(grp % batch);
   const size_t di = (size_t)g * dm.B + j;
   if (e.status[g] != ST_ACTIVE) {
-    e.d_kind[di] = KIND_SKIP;
-    e.d_slot[di] = -1;
+    store_desc_skip(e.desc + di);
     return;
   }
   const int A = dm.A;
@@ -320,8 +333,7 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
   int node = ht_lookup1(ht, dm.hash_cap, gen, key, khi);
   int depth = 0, kind = KIND_EXPAND;
   float term_value = 0.0f;
-  int32_t* path_node = e.d_path_node + di * dm.max_depth;
-  uint8_t* path_action = e.d_path_action + di * dm.max_depth;
+  uint32_t* path = e.d_path + di * dm.max_depth;
   while (node >= 0) {
     const size_t row = (nb + (size_t)node) * dm.RS;  // the record [N | W | P | C]: 16 * ROWV consecutive words
     int n_loc[ROWV * 4], c_loc[ROWV * 4];
@@ -386,8 +398,7 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
       }
     }
     const int a = best_a;
-    path_node[depth] = node;
-    path_action[depth] = (uint8_t)a;
+    path[depth] = ((uint32_t)node << 8) | (uint32_t)a;
     ++depth;
     const bool won = rules.apply(s, a, who);
     who ^= 1;
@@ -409,14 +420,7 @@ __device__ __forceinline__ void select_thread_body(const View<typename R::Board>
       if (node >= 0) e.C[row + a] = node;
     }
   }
-  e.d_kind[di] = (uint8_t)kind;
-  e.d_value[di] = term_value;
-  e.d_board[di] = s;
-  e.d_player[di] = (uint8_t)who;
-  e.d_key_lo[di] = key.lo;
-  e.d_key_hi[di] = key.hi;
-  e.d_path_len[di] = depth;
-  e.d_slot[di] = -1;
+  store_desc(e.desc + di, kind, who, depth, term_value, key, s);
 }
 
 template <class R, int ROWV>
@@ -454,12 +458,16 @@ __device__ __forceinline__ void plan_body(const View<Board>& e, const Dims& dm, 
   const bool in_range = g < dm.G;
   const bool live = in_range && e.status[g] == ST_ACTIVE;
   const size_t d0 = (size_t)(in_range ? g : 0) * dm.B;
-  int kind = KIND_SKIP;
+  int kind = KIND_SKIP, len = 0;
   uint64_t lo = 0, hi = 0;
+  float tval = 0.0f;
   if (live && j < batch) {
-    kind = e.d_kind[d0 + j];
-    lo = e.d_key_lo[d0 + j];
-    hi = e.d_key_hi[d0 + j];
+    const DescHead h = e.desc[d0 + j].h;  // one 32-byte sector
+    kind = h.kind;
+    len = h.len;
+    tval = h.value;
+    lo = h.key_lo;
+    hi = h.key_hi;
   }
   const unsigned below = (1u << j) - 1u;
   const unsigned term_m = (__ballot_sync(gmask, kind == KIND_TERMINAL) >> gbase) & ((GP == 32) ? 0xffffffffu : ((1u << GP) - 1u));
@@ -494,14 +502,14 @@ __device__ __forceinline__ void plan_body(const View<Board>& e, const Dims& dm, 
   if (j == 0) e.q_len[g] = live ? n_term + n_new : 0;
   if (!live) return;
   if (kind == KIND_TERMINAL) {
-    e.q_order[d0 + __popc(term_m & below)] = (uint8_t)j;
+    e.q_entry[d0 + __popc(term_m & below)] = QEntry{(uint8_t)j, (uint8_t)KIND_TERMINAL, (uint16_t)len, __float_as_int(tval)};
   } else if (uniq) {
     const int r = __popc(uniq_m & below);
-    e.q_order[d0 + n_term + r] = (uint8_t)j;
     const int slot = base + r;
-    e.d_slot[d0 + j] = slot;
-    e.leaf_board[slot] = e.d_board[d0 + j];
-    e.leaf_player[slot] = e.d_player[d0 + j];
+    e.q_entry[d0 + n_term + r] = QEntry{(uint8_t)j, (uint8_t)KIND_EXPAND, (uint16_t)len, slot};
+    e.desc[d0 + j].h.slot = slot;
+    e.leaf_board[slot] = e.desc[d0 + j].board;
+    e.leaf_player[slot] = e.desc[d0 + j].h.player;
   }
   if (j == 0) {
     if (n_new) atomicAdd(e.ctr + CTR_LEAVES, (unsigned long long)n_new);
@@ -559,15 +567,16 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
   // ---- phase 1 -------------------------------------------------------------------------------------
   int my_di = 0, my_kind = KIND_SKIP, my_slot = -1, my_len = 0;
   float my_val = 0.0f;
-  if (lane < qn) {
-    my_di = (int)e.q_order[d0 + lane];
-    my_kind = e.d_kind[d0 + my_di];
-    my_len = e.d_path_len[d0 + my_di];
+  if (lane < qn) {  // the queue entry carries everything: no order -> kind -> slot chain of dependent loads
+    const QEntry q = e.q_entry[d0 + lane];
+    my_di = q.j;
+    my_kind = q.kind;
+    my_len = q.len;
     if (my_kind == KIND_EXPAND) {
-      my_slot = e.d_slot[d0 + my_di];
+      my_slot = q.slot;
       my_val = values[my_slot];
     } else {
-      my_val = e.d_value[d0 + my_di];
+      my_val = __int_as_float(q.slot);
     }
   }
   const unsigned exp_m = (__ballot_sync(gmask, my_kind == KIND_EXPAND) >> gbase) & (GW == 32 ? 0xffffffffu : ((1u << GW) - 1u));
@@ -576,11 +585,12 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
   const bool creates = my_kind == KIND_EXPAND && my_node < dm.node_cap;
   if (my_kind == KIND_EXPAND && !creates) atomicOr(e.ctr + CTR_ERRORS, ERR_ARENA_FULL);
   if (creates) {  // _create_node, lib/mcts.py:178-190 (scalars + hash slot by the owning lane)
-    const size_t di = d0 + my_di;
-    e.node_board[nb + my_node] = e.d_board[di];
-    e.node_player[nb + my_node] = e.d_player[di];
-    if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + my_node] = e.d_key_hi[di];
-    ht_insert_cas(ht, dm.hash_cap, gen, e.d_key_lo[di], my_node);
+    const DescRec<typename R::Board>* rec = e.desc + d0 + my_di;
+    const DescHead h = rec->h;
+    e.node_board[nb + my_node] = rec->board;
+    e.node_player[nb + my_node] = h.player;
+    if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + my_node] = h.key_hi;
+    ht_insert_cas(ht, dm.hash_cap, gen, h.key_lo, my_node);
   }
   // rows of the new nodes, all lanes cooperating
   for (int q = 0; q < qn; ++q) {
@@ -618,9 +628,9 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
       w_v[q] = 0.0f;
       cur[q] = 0.0f;
       if (q < qn && i < len) {
-        const size_t pi = (d0 + di) * dm.max_depth + i;
-        const int node = e.d_path_node[pi];
-        const int a = e.d_path_action[pi];
+        const uint32_t pe = e.d_path[(d0 + di) * dm.max_depth + i];
+        const int node = (int)(pe >> 8);
+        const int a = (int)(pe & 0xffu);
         idx[q] = (long long)((nb + (size_t)node) * dm.RS + a);
         n_v[q] = e.N[idx[q]];
         w_v[q] = e.W[idx[q]];

@@ -48,8 +48,27 @@ class SelfPlayEngine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # fields of the per-descent record (csrc/engine.cuh DescRec): name -> (byte offset, bytes, dtype); the board follows at 32
+    _DESC_FIELDS = {"desc_kind": (0, 1, torch.uint8), "desc_player": (1, 1, torch.uint8), "desc_path_len": (2, 2, torch.int16),
+                    "desc_slot": (4, 4, torch.int32), "desc_value": (8, 4, torch.int32), "desc_key_lo": (16, 8, torch.int64),
+                    "desc_key_hi": (24, 8, torch.int64)}
+
     def region(self, name: str) -> torch.Tensor:
-        """Zero-copy torch view of a named workspace region (see include/caro_b200.h)."""
+        """Zero-copy torch view of a named workspace region (see include/caro_b200.h).  The per-descent fields
+        ("desc_kind", "desc_slot", "desc_board", "desc_path_node", ...) are COPIES sliced out of the descent records
+        ("desc": one 64 / 96-byte record per descent) and of the packed paths ("desc_path": node << 8 | action)."""
+        if name in self._DESC_FIELDS or name == "desc_board":
+            rec = self.region("desc")  # int64 [G, B, words]
+            raw = rec.view(torch.uint8).view(rec.shape[0], rec.shape[1], rec.shape[2] * 8)
+            if name == "desc_board":
+                words = self.game.board_words
+                return raw[:, :, 32:32 + 8 * words].contiguous().view(torch.int64).view(rec.shape[0], rec.shape[1], words)
+            off, nbytes, dtype = self._DESC_FIELDS[name]
+            out = raw[:, :, off:off + nbytes].contiguous().view(dtype).view(rec.shape[0], rec.shape[1])
+            return out.to(torch.int32) if dtype == torch.int16 else out
+        if name in ("desc_path_node", "desc_path_action"):
+            path = self.region("desc_path")
+            return ((path >> 8) & 0xFFFFFF) if name == "desc_path_node" else (path & 0xFF).to(torch.uint8)
         if name not in self._views:
             off, nbytes, elem = C.c_size_t(), C.c_size_t(), C.c_int32()
             dims = (C.c_int64 * 4)()
@@ -209,10 +228,10 @@ class SelfPlayEngine:
 
     def profile_read(self) -> Dict[str, float]:
         """Summed CUDA-event milliseconds per search phase since the last read (+ kernel launches)."""
-        ms = (C.c_double * 4)()
+        ms = (C.c_double * 5)()
         launches = C.c_uint64()
         _cabi.check(_cabi.lib().caro_engine_profile_read(self.handle, C.byref(ms), C.byref(launches), self._stream()))
-        return {"select_ms": ms[0], "plan_ms": ms[1], "net_ms": ms[2], "expand_backup_ms": ms[3],
+        return {"select_ms": ms[0], "plan_ms": ms[1], "net_ms": ms[2], "expand_backup_ms": ms[3], "noise_ms": ms[4],
                 "launches": int(launches.value)}
 
     def step_host(self, boards_pinned: torch.Tensor, players_pinned: torch.Tensor, net: DeviceNet, count: int, batch: int,

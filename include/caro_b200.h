@@ -153,9 +153,13 @@ void caro_engine_destroy(caro_engine* e);
  * "nodes" (int32 [nodes][4][Apad]: one record per node with rows N | W | P | cached child link; bit 31 of an N word =
  * "W has absorbed a float32 network value"; Q = f32(W / N) is not stored), "node_board","node_count","root_board",
  * "root_player","status","ply",
- * "result","leaf_board","leaf_player","leaf_count","desc_kind","desc_value","desc_board",
- * "desc_player","desc_path_len","desc_path_node","desc_path_action","desc_slot","queue_len",
- * "queue_order","counters","replay_board","replay_player","replay_pi","replay_z","replay_cursor".
+ * "result","leaf_board","leaf_player","leaf_count",
+ * "desc" (one record per descent of the current minibatch, [G][max_batch]: bytes 0 kind, 1 side to move at the leaf,
+ * 2-3 path length, 4-7 compact leaf slot (-1 = none), 8-11 terminal value (float), 16-31 transposition key, 32.. the leaf
+ * board; 64 bytes for Connect4, 96 for m,n,k), "desc_path" (uint32 [G][max_batch][max plies]: (node << 8) | action from
+ * the root down), "queue_len", "queue" (8-byte back-up queue entries {descent u8, kind u8, path length u16, leaf slot or
+ * float bits of a terminal value i32} in the order of lib/mcts.py:269-278), "counters","replay_board","replay_player",
+ * "replay_pi","replay_z","replay_cursor".
  * elem_bytes receives the element size, dims[0..3] the logical shape (unused dims = 0). */
 int caro_engine_region(const caro_engine* e, const char* name, size_t* offset, size_t* bytes,
                        int32_t* elem_bytes, int64_t dims[4]);
@@ -230,11 +234,11 @@ int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, int64_t 
 
 /* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
  * profile_read synchronises `stream` and returns the summed milliseconds of
- * [0] select, [1] plan, [2] network forward, [3] expand+backup kernels since the last read, plus
- * the number of engine kernels launched by search/play in that window. */
+ * [0] select, [1] plan, [2] network forward, [3] expand+backup, [4] Dirichlet-noise kernels since the last read,
+ * plus the number of engine kernels launched by search/play in that window. */
 /* enable: 0 = off, 1 = network kernel only (2 events per minibatch), 2 = all four phases. */
 int caro_engine_profile(caro_engine* e, int enable);
-int caro_engine_profile_read(caro_engine* e, double h_ms[4], uint64_t* h_launches, void* stream);
+int caro_engine_profile_read(caro_engine* e, double h_ms[5], uint64_t* h_launches, void* stream);
 
 /* Host copies of the 64-bit counters (synchronises `stream`): [0] leaf evaluations, [1] finished
  * games, [2] plies played, [3] wins of player 0, [4] wins of player 1, [5] draws, [6] descents,

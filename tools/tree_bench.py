@@ -1,7 +1,7 @@
 """GPU measurement of the tree kernels against the HBM roofline (SURVEY.md section 8d byte model).
 
 For G concurrent Connect4 games with grown trees, times noise+select, plan and expand+backup per minibatch (CUDA events
-around each kernel group, engine profile level 2, single stream, nothing else running) and converts the ALGORITHMIC
+around each kernel, engine profile level 2, single stream, nothing else running) and converts the ALGORITHMIC
 bytes -- select d(12A+20) per descent, backup 20 d per backed-up descent, expand 16A+12 per new node, plan 17 per
 descent + 17 per unique leaf -- into GB/s.  Usage: python tools/tree_bench.py [games ...]"""
 import json
@@ -97,7 +97,9 @@ def main():
         bak_b = depth_sum * 20 + leaves * (16 * A + 12)
         plan_b = desc * 17 + leaves * 17
         out = {"games": G, "descents_per_minibatch": desc / n, "avg_path_len": d, "unique_leaves_per_minibatch": leaves / n}
-        for name, ms, b in (("noise+select", p["select_ms"], sel_b), ("plan", p["plan_ms"], plan_b), ("expand+backup", p["expand_backup_ms"], bak_b)):
+        noise_b = desc * A * 8  # float64 [descents][A] written by noise_kernel (read again by select: not in select's byte model)
+        for name, ms, b in (("noise", p["noise_ms"], noise_b), ("select", p["select_ms"], sel_b), ("plan", p["plan_ms"], plan_b),
+                            ("expand+backup", p["expand_backup_ms"], bak_b)):
             gbs = b / (ms / 1e3) / 1e9
             out[name] = {"us_per_minibatch": 1e3 * ms / n, "algorithmic_MB_per_minibatch": b / n / 1e6, "GB_per_s": gbs,
                          "frac_of_hbm_peak": gbs / HBM_GBS}
