@@ -176,6 +176,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_pol_fc_t = nullptr;
   net->d_trace = nullptr;
   net->d_headfeat = nullptr;
+  net->d_heads_b = nullptr;
   net->headfeat_leaves = 0;
   net->headfeat_seq = 0;
   net->grid_limit = 0;
@@ -188,6 +189,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
     int prc = caro_net_tc_prepare();
     if (prc == CARO_OK) prc = caro_net_rt_prepare();
     if (prc == CARO_OK) prc = caro_net_rx_prepare();
+    if (prc == CARO_OK) prc = caro_net_heads_prepare();
     if (prc != CARO_OK) {
       delete net;
       return prc;
@@ -229,6 +231,7 @@ void caro_net_destroy(caro_net* net) {
   caro_net_tc_free(net);
   caro_net_rt_free(net);
   caro_net_rx_free(net);
+  caro_net_heads_free(net);
   if (net->d_blob) cudaFree(net->d_blob);
   delete net;
 }

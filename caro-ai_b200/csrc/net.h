@@ -57,7 +57,8 @@ struct caro_net {
   alignas(16) float h_rt_consts[6 * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
-  float* d_headfeat;    // large boards: exported 1x1 head-convolution sums [leaf][3][HW] for heads_kernel (net_tc.cu)
+  void* d_headfeat;     // large boards: exported activated head features, bf16 hi + lo images in the A-operand layout of net_heads.cu
+  void* d_heads_b;      // large boards: bf16 hi + lo B-operand image of the FC heads GEMM (net_heads.cu)
   long long headfeat_leaves;  // capacity of ONE slot of d_headfeat in leaves
   unsigned headfeat_seq;      // next slot (round robin per launch)
   void* d_trace;        // optional debug timeline buffer (caro_net_set_trace), normally null
@@ -92,3 +93,12 @@ int caro_net_rx_prepare();
 void caro_net_rx_free(caro_net* net);
 int caro_net_rx_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                         const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);
+
+// net_heads.cu (FC heads of large boards as one split-precision tcgen05 GEMM per 128 leaves)
+int caro_net_heads_kc64(const caro_net* net);
+bool caro_net_heads_supported(const caro_net* net);
+int caro_net_heads_pack(caro_net* net, const float* h_blob);
+int caro_net_heads_prepare();
+void caro_net_heads_free(caro_net* net);
+int caro_net_heads_forward(caro_net* net, const void* a_img, size_t a_lo_off, const int32_t* d_count, int64_t max_count,
+                           float* d_probs, float* d_values, cudaStream_t st);

@@ -38,7 +38,7 @@ constexpr int kTapBytesIn = 2 * 64 * 16;                 // 2,048: one tap of co
 constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
 constexpr int kHeadfeatSlots = 8;                         // scratch slots for exported head features (launches in flight)
-constexpr int kHeadsInTowerMaxHW = 64;                    // larger boards run their FC heads in heads_kernel
+constexpr int kHeadsInTowerMaxHW = 64;                    // larger boards run their FC heads in heads_tc_kernel (net_heads.cu)
 constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
 constexpr int kEpiWarps = 8;                             // warps 0-7: epilogue; TMEM lane quarter = warp & 3, column half = warp >> 2
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -88,120 +88,42 @@ using TcExact = TcCfg<2, true>;
 
 // Large boards (Caro 15x15: 225 actions, 450 x 225 policy FC) do not run their FC heads inside the tower: two head warps
 // re-reading 405 KB of FC weights for every 2-board group made the heads, not the convolutions, the bottleneck (1.9 ms
-// per 4,096 leaves, of which ~0.3 ms tower).  The tower only exports the raw 1x1 head-convolution sums of the group
-// ([leaf][3][HW] floats) and heads_kernel below does the FC layers for 32 leaves per CTA, reading every weight once
-// per CTA from L2 and the features from shared memory.
+// per 4,096 leaves, of which ~0.3 ms tower).  The tower only exports, per leaf, the ACTIVATED outputs of the 1x1 head
+// convolutions (bias + LeakyReLU applied here) as bf16 hi + lo pairs, already in the UMMA A-operand layout of the heads
+// GEMM (net_heads.cu): images [tile of 128 leaves][K / 8][128 rows][8], K = 3 HW padded to 64, one 16-byte store per
+// (leaf, 8 features) and image; heads_tc_kernel then evaluates both FC layers on the tensor cores.
 template <int TEAM, int BAR>
-__device__ __noinline__ void export_heads(const TcGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s,
-                                          float* __restrict__ out) {
-  const int n = nvalid * 3 * gm.H * gm.W;
-  float* dst = out + (size_t)leaf0 * 3 * gm.H * gm.W;
+__device__ __noinline__ void export_heads(const TcGeom& gm, int nvalid, long long leaf0, int ttid, float* headf_s, const float* headw_s,
+                                          uint8_t* __restrict__ out_hi, size_t lo_off, int kc8) {
+  const int HW = gm.H * gm.W, K = 3 * HW;
+  const float hb0 = headw_s[192], hb1 = headw_s[193], hb2 = headw_s[194];
 #pragma unroll 1
-  for (int i = ttid; i < n; i += TEAM) {
-    dst[i] = headf_s[i];
-    headf_s[i] = 0.0f;  // re-arm the accumulation slots
+  for (int item = ttid; item < nvalid * kc8; item += TEAM) {
+    const int b = item / kc8, c8 = item - b * kc8;
+    const long long leaf = leaf0 + b;
+    const float* f = headf_s + (size_t)b * K;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = c8 * 8 + 2 * e + u;
+        v[u] = k < K ? lrelu_tc(f[k] + (k < HW ? hb0 : (k < 2 * HW ? hb1 : hb2))) : 0.0f;
+      }
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - __low2float(h2), v[1] - __high2float(h2));
+      hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    uint8_t* dst = out_hi + (((size_t)(leaf >> 7) * kc8 + c8) * 128 + (size_t)(leaf & 127)) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
-}
-
-constexpr int kHeadsLeaves = 32;   // leaves per CTA of heads_kernel
-constexpr int kHeadsThreads = 512;
-constexpr int kHeadsPitch = 36;    // floats per feature row in shared memory: 32 leaves + 4 (16-byte aligned rows, and the
-                                   // transposing writes of the load phase spread over 8 banks instead of hitting one)
-
-// FC heads for a batch of leaves (lib/model.py:56-72,90-93 + softmax of lib/mcts.py:216) from the exported head features.
-// Shared memory: fs[3 HW][36] activated features (leaf index fastest: the inner loops read 32 leaves of one feature as
-// eight broadcast float4), lg[32][A] logits, hid[32][20].  The FC weights are read once per CTA, 8 rows ahead.
-__global__ void __launch_bounds__(kHeadsThreads)
-heads_kernel(const float* __restrict__ feat, const int32_t* __restrict__ d_count, long long max_count, int HW, int A,
-             const float* __restrict__ blob, BlobLayout L, const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t,
-             float* __restrict__ probs, float* __restrict__ values) {
-  extern __shared__ __align__(16) float hs[];
-  float* fs = hs;                                 // [3 HW][36]
-  float* lg = fs + (size_t)3 * HW * kHeadsPitch;   // [32][A]
-  float* hid = lg + (size_t)kHeadsLeaves * A;      // [32][20]
-  const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
-  const int tid = threadIdx.x;
-  const float hb[3] = {blob[L.val_conv_b], blob[L.pol_conv_b], blob[L.pol_conv_b + 1]};
-  for (long long leaf0 = (long long)blockIdx.x * kHeadsLeaves; leaf0 < count; leaf0 += (long long)gridDim.x * kHeadsLeaves) {
-    const int nvalid = (int)min((long long)kHeadsLeaves, count - leaf0);
-    for (int l = 0; l < kHeadsLeaves; ++l) {  // coalesced reads along the features of one leaf, transposed into fs
-      const float* src = feat + (size_t)(leaf0 + l) * 3 * HW;
-      for (int k = tid; k < 3 * HW; k += kHeadsThreads)
-        fs[k * kHeadsPitch + l] = l < nvalid ? lrelu_tc(src[k] + hb[k / HW]) : 0.0f;
-    }
-    __syncthreads();
-    for (int t = tid; t < 2 * A; t += kHeadsThreads) {  // policy FC: this thread owns action a of 16 of the 32 leaves
-      constexpr int LH = kHeadsLeaves / 2;
-      const int h = t >= A ? 1 : 0, a = t - h * A;
-      float acc[LH];
-#pragma unroll
-      for (int i = 0; i < LH; ++i) acc[i] = 0.0f;
-      const float* fbase = fs + (size_t)HW * kHeadsPitch + h * LH;
-      const int K2 = 2 * HW;
-      int k = 0;
-      for (; k + 8 <= K2; k += 8) {
-        float w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldg(pol_fc_t + (size_t)(k + u) * A + a);  // 8 independent L2 reads in flight
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)(k + u) * kHeadsPitch);
-#pragma unroll
-          for (int q = 0; q < LH / 4; ++q) {
-            const float4 f = f4[q];
-            acc[4 * q] = fmaf(w[u], f.x, acc[4 * q]);
-            acc[4 * q + 1] = fmaf(w[u], f.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(w[u], f.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(w[u], f.w, acc[4 * q + 3]);
-          }
-        }
-      }
-      for (; k < K2; ++k) {
-        const float w = __ldg(pol_fc_t + (size_t)k * A + a);
-        const float4* f4 = reinterpret_cast<const float4*>(fbase + (size_t)k * kHeadsPitch);
-#pragma unroll
-        for (int q = 0; q < LH / 4; ++q) {
-          const float4 f = f4[q];
-          acc[4 * q] = fmaf(w, f.x, acc[4 * q]);
-          acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(w, f.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(w, f.w, acc[4 * q + 3]);
-        }
-      }
-      const float b = blob[L.pol_fc_b + a];
-#pragma unroll
-      for (int i = 0; i < LH; ++i) lg[(h * LH + i) * A + a] = acc[i] + b;
-    }
-    for (int o = tid; o < kHeadsLeaves * 20; o += kHeadsThreads) {  // value FC1
-      const int ll = o & 31, i = o >> 5;
-      float a0 = 0.0f, a1 = 0.0f;
-      int c = 0;
-      for (; c + 1 < HW; c += 2) {
-        a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsPitch + ll], a0);
-        a1 = fmaf(__ldg(val_fc1_t + (size_t)(c + 1) * 20 + i), fs[(c + 1) * kHeadsPitch + ll], a1);
-      }
-      for (; c < HW; ++c) a0 = fmaf(__ldg(val_fc1_t + (size_t)c * 20 + i), fs[c * kHeadsPitch + ll], a0);
-      hid[ll * 20 + i] = lrelu_tc(blob[L.val_fc1_b + i] + (a0 + a1));
-    }
-    __syncthreads();
-    for (int b = tid >> 5; b < nvalid; b += kHeadsThreads / 32) {
-      const int lane = tid & 31;
-      float part = lane < 20 ? blob[L.val_fc2_w + lane] * hid[b * 20 + lane] : 0.0f;
-      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-      if (lane == 0) values[leaf0 + b] = tanhf(blob[L.val_fc2_b] + part);
-      const float* lrow = lg + b * A;
-      float* prow = probs + (size_t)(leaf0 + b) * A;
-      float mx = -INFINITY;
-      for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lrow[a]);
-      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-      float sum = 0.0f;
-      for (int a = lane; a < A; a += 32) sum += expf(lrow[a] - mx);
-      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-      for (int a = lane; a < A; a += 32) prow[a] = expf(lrow[a] - mx) / sum;
-    }
-    __syncthreads();
-  }
+#pragma unroll 1
+  for (int i = ttid; i < nvalid * K; i += TEAM) headf_s[i] = 0.0f;  // re-arm the accumulation slots
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(TEAM) : "memory");
 }
 
 // ------------------------------------------------------------------------------------- kernel
@@ -220,7 +142,8 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const float* __restrict__ bias_g, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
-              float* __restrict__ values, float* __restrict__ headfeat_out, long long* __restrict__ trace) {
+              float* __restrict__ values, uint8_t* __restrict__ headfeat_out, size_t headfeat_lo_off, int headfeat_kc8,
+              long long* __restrict__ trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + K::kAct;
   uint8_t* wgt = smem + K::kWgt;
@@ -291,7 +214,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const int nvalid = (int)min((long long)nb, count - leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
-      if (headfeat_out != nullptr) export_heads<kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, headfeat_out);
+      if (headfeat_out != nullptr) export_heads<kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, headw_s, headfeat_out, headfeat_lo_off, headfeat_kc8);
       else run_heads<kHeadThreads, 2>(gm, nb, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
       mbar_arrive(bar_feat + 1);  // features consumed, slots re-zeroed, scratch free
       if (htid == 0) TC_TRACE(5, gi);  // heads done
@@ -525,7 +448,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         // last group of this CTA: nothing left to overlap with, so all eight epilogue warps do the heads
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int nvalid = (int)min((long long)nb, count - leaf0);
-        if (headfeat_out != nullptr) export_heads<kEpiThreads, 1>(gm, nvalid, leaf0, tid, headf_s, headfeat_out);
+        if (headfeat_out != nullptr) export_heads<kEpiThreads, 1>(gm, nvalid, leaf0, tid, headf_s, headw_s, headfeat_out, headfeat_lo_off, headfeat_kc8);
         else run_heads<kEpiThreads, 1>(gm, nb, nvalid, leaf0, tid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
         if (tid == 0) TC_TRACE(5, gi);
       }
@@ -592,10 +515,16 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
   for (int i = 0; i < 20; ++i)
     for (int c = 0; c < HW; ++c) polt[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
   cudaError_t ce = cudaSuccess;
-  if (HW > kHeadsInTowerMaxHW && !net->d_headfeat) {  // large boards: FC heads run in heads_kernel from exported features
-    net->headfeat_leaves = 32768;  // per slot (708 MB in all for 15x15): larger launches fall back to the FC heads inside the tower
-    ce = cudaMalloc(&net->d_headfeat, (size_t)kHeadfeatSlots * net->headfeat_leaves * 3 * HW * sizeof(float));
-    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  if (HW > kHeadsInTowerMaxHW && caro_net_heads_supported(net)) {  // large boards: FC heads on the tensor cores from exported features
+    if (!net->d_headfeat) {
+      net->headfeat_leaves = 32768;  // per slot; larger launches fall back to the FC heads inside the tower
+      // one slot = hi + lo image of [leaves / 128][K / 8][128][8] bf16 (738 MB in all for 15x15)
+      const size_t image = (size_t)net->headfeat_leaves * caro_net_heads_kc64(net) * 64 * 2;
+      ce = cudaMalloc(&net->d_headfeat, (size_t)kHeadfeatSlots * 2 * image);
+      if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+    }
+    const int hrc = caro_net_heads_pack(net, h);
+    if (hrc != CARO_OK) return hrc;
   }
   if (!net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
   if (ce == cudaSuccess && !net->d_tc_bias) ce = cudaMalloc(&net->d_tc_bias, bias.size() * sizeof(float));
@@ -639,22 +568,17 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   // the exported head features go to one of kHeadfeatSlots scratch slots, round robin per launch: launches of different
   // parts of the self-play pipeline can be in flight at the same time on different streams (and the slot is baked
   // into a captured graph node), so they must not share a buffer
-  float* headfeat = nullptr;
+  uint8_t* headfeat = nullptr;
+  const int kc64 = caro_net_heads_kc64(net);
+  const size_t image = (size_t)net->headfeat_leaves * kc64 * 64 * 2;  // bytes of one (hi or lo) image of a slot
   if (net->d_headfeat != nullptr && max_count <= net->headfeat_leaves)
-    headfeat = net->d_headfeat + (size_t)(net->headfeat_seq++ % kHeadfeatSlots) * net->headfeat_leaves * 3 * HW;
+    headfeat = (uint8_t*)net->d_headfeat + (size_t)(net->headfeat_seq++ % kHeadfeatSlots) * 2 * image;
   kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
                                           (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat,
-                                          (long long*)net->d_trace);
+                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat, image,
+                                          kc64 * 8, (long long*)net->d_trace);
   int rc = caro_check_launch("net_tc_kernel");
-  if (rc == CARO_OK && headfeat != nullptr) {
-    const size_t smem = ((size_t)3 * HW * kHeadsPitch + (size_t)kHeadsLeaves * net->A + kHeadsLeaves * 20) * sizeof(float);
-    const long long tiles = (max_count + kHeadsLeaves - 1) / kHeadsLeaves;
-    const unsigned hgrid = (unsigned)(tiles < 2 * sm_count ? tiles : 2 * sm_count);
-    heads_kernel<<<hgrid, kHeadsThreads, smem, st>>>(headfeat, d_count, (long long)max_count, HW, net->A, net->d_blob, net->layout,
-                                                     net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values);
-    rc = caro_check_launch("heads_kernel");
-  }
+  if (rc == CARO_OK && headfeat != nullptr) rc = caro_net_heads_forward(net, headfeat, image, d_count, max_count, probs, values, st);
   return rc;
 }
 
@@ -665,7 +589,6 @@ int caro_net_tc_prepare() {
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFast::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }

@@ -282,6 +282,59 @@ def test_split_precision_row_tiled_tower(torch_cuda):
         dn.close()
 
 
+def test_caro_heads_on_tensor_cores(torch_cuda):
+    """Boards larger than 8 x 8 (Caro 15 x 15, 9 x 9) evaluate their FC heads as one split-precision tcgen05 GEMM per 128
+    leaves (net_heads.cu) from features the tower exports: priors and values vs PyTorch fp32 at 1e-3 and vs the fp32 SIMT
+    tower at 2e-4 for leaf counts around the 128-leaf tile and 2-board group boundaries, bit-identical from run to run,
+    rows beyond a device-side count untouched."""
+    torch = torch_cuda
+    from test_gpu_parity import _random_net, _reference_outputs
+    from harness import random_position
+    from caro_ai_b200 import _cabi
+    from caro_ai_b200.game import TicTacToe
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(33)
+    for n, k, counts in ((15, 5, (1, 2, 127, 128, 129, 300)), (9, 4, (3, 130))):
+        game = TicTacToe(n, k)
+        og = oracle_for(game)
+        net = _random_net(game, seed=n)
+        dn = DeviceNet(net, game, precision="bf16")
+        base = [random_position(og, rng, int(rng.integers(0, 40 if n == 15 else 14))) for _ in range(48)]  # few enough plies for random play-outs to stay win-free
+        ref_p, ref_v = _reference_outputs(game, net, [p[0] for p in base], [p[1] for p in base])
+        for count in counts:
+            pos = [base[i % len(base)] for i in range(count)]
+            states, players = [p[0] for p in pos], [p[1] for p in pos]
+            p0, v0 = dn.forward_states(states, players, impl=0)
+            p0b, v0b = dn.forward_states(states, players, impl=0)
+            p1, v1 = dn.forward_states(states, players, impl=1)
+            p2, v2 = dn.forward_states(states, players, impl=2)
+            torch.cuda.synchronize()
+            assert torch.equal(p0, p0b) and torch.equal(v0, v0b), (n, count)
+            for i in range(0, count, len(base)):
+                m = min(len(base), count - i)
+                for pp, vv, tol in ((p0, v0, 1e-3), (p2, v2, 3e-4)):
+                    assert np.abs(pp[i:i + m].cpu().numpy() - ref_p[:m]).max() < tol, (n, count, i, tol)
+                    assert np.abs(vv[i:i + m].cpu().numpy() - ref_v[:m]).max() < tol, (n, count, i, tol)
+            assert float((p2 - p1).abs().max()) < 2e-4 and float((v2 - v1).abs().max()) < 2e-4
+            np.testing.assert_allclose(p0.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+        # device-side count
+        count = 200
+        pos = [base[i % len(base)] for i in range(count)]
+        d_boards = torch.from_numpy(game.boards_from_states([p[0] for p in pos]).view(np.int64)).cuda()
+        d_who = torch.tensor([p[1] for p in pos], dtype=torch.uint8, device="cuda")
+        full_p, full_v = dn.forward_boards(d_boards, d_who, count, 0)
+        probs = torch.full((count, n * n), -7.0, dtype=torch.float32, device="cuda")
+        values = torch.full((count,), -7.0, dtype=torch.float32, device="cuda")
+        d_count = torch.tensor([131], dtype=torch.int32, device="cuda")
+        _cabi.check(_cabi.lib().caro_net_forward(dn.handle, game.game_kind, game.n, game.k, d_boards.data_ptr(), d_who.data_ptr(),
+                                                 d_count.data_ptr(), count, probs.data_ptr(), values.data_ptr(), 0,
+                                                 torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(probs[:131], full_p[:131]) and torch.equal(values[:131], full_v[:131])
+        assert bool((probs[131:] == -7.0).all()) and bool((values[131:] == -7.0).all())
+        dn.close()
+
+
 # --------------------------------------------------------------------------- replay ring -> SGD batch
 def test_replay_gather_and_train_step_match_the_reference(torch_cuda, golden_train):
     """train.py:82-111 with the batch assembled on the device: the fixture's replay buffer is loaded into the engine's
