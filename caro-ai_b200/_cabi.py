@@ -17,7 +17,10 @@ class EngineConfig(C.Structure):
     _fields_ = [("game", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("games", C.c_int32),
                 ("trees_per_game", C.c_int32), ("max_batch", C.c_int32), ("node_capacity", C.c_int32),
                 ("replay_capacity", C.c_int32), ("c_puct", C.c_double), ("alpha", C.c_double),
-                ("explore", C.c_double), ("seed", C.c_uint64)]
+                ("explore", C.c_double), ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FLAG_VIRTUAL_LOSS, FLAG_MASK_PRIORS, FLAG_FRESH_TREE = 1, 2, 4
 
 
 _P = C.c_void_p
@@ -30,6 +33,7 @@ _SIGNATURES = {
     "caro_boards_encode_planes": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P, _P]),
     "caro_backup_path": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, _P]),
     "caro_net_blob_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "caro_net_blob_floats_deep": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "caro_net_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
     "caro_net_update": (C.c_int, [_P, _P, C.c_size_t]),
     "caro_net_destroy": (None, [_P]),

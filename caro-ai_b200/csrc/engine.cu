@@ -164,6 +164,8 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
   dm->max_depth = plies;
   dm->max_plies = plies;
   dm->replay_cap = cfg->replay_capacity;
+  dm->flags = cfg->flags;
+  if (cfg->flags & ~7u) return caro_fail(CARO_E_ARG, "unknown engine flags");
   *max_plies = plies;
   return CARO_OK;
 }
@@ -195,6 +197,10 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
     if (phase == 1) return caro_check_launch("noise_kernel");
   } else if (noise_out != nullptr && phase != 2) {
     cudaMemcpyAsync(noise_out, noise, sizeof(double) * (size_t)groups * A, cudaMemcpyDeviceToDevice, st);
+  }
+  if (dm.flags & FLAG_VIRTUAL_LOSS) {  // extension: sequential descents per game with virtual loss (one thread per game)
+    select_vl_kernel<R><<<(unsigned)((dm.G + 63) / 64), 64, 0, st>>>(v, rules, dm, sp, batch, src);
+    return caro_check_launch("select_vl_kernel");
   }
 #define SELECT(GW, APL) select_kernel<R, GW, APL><<<grid(GW), 256, 0, st>>>(v, rules, dm, sp, batch, src)
   // more descents than the GPU holds at once (5 blocks of 90-register threads per SM): the 72-register build keeps 7 blocks

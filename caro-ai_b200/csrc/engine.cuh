@@ -63,7 +63,9 @@ struct Dims {
   int max_depth;  // path stride = max plies of the game
   int max_plies;  // history stride
   int replay_cap;
+  unsigned flags;  // CARO_FLAG_* (include/caro_b200.h): throughput-mode extensions, 0 = the reference's search
 };
+enum : unsigned { FLAG_VIRTUAL_LOSS = 1u, FLAG_MASK_PRIORS = 2u, FLAG_FRESH_TREE = 4u };
 
 struct SearchParams {
   double c_puct, alpha, explore;

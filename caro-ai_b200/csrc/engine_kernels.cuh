@@ -443,6 +443,112 @@ select_thread_dense_kernel(View<typename R::Board> e, R rules, Dims dm, SearchPa
   select_thread_body<R, ROWV>(e, rules, dm, sp, batch, noise_in, grp);
 }
 
+// ------------------------------------------------------------- select with virtual loss (extension)
+// CARO_FLAG_VIRTUAL_LOSS (not in the reference).  The reference's `batch` descents of a minibatch
+// all see the same frozen tree and differ only through the root noise, so ~70 % of them end on a leaf another descent of
+// the same minibatch has already planned and are dropped (lib/mcts.py:273-278).  Here the descents of a game are made ONE
+// AFTER THE OTHER by one thread, and an edge (s, a) that k earlier descents of this minibatch went through is scored as if
+// it had k more visits that all lost: N + k, W - k, sum N + k in the PUCT formula.  The virtual visits are a pure function
+// of the earlier paths (re-read from the path records of this minibatch), the tree itself is not touched, so plan and
+// expand+backup run unchanged and nothing has to be undone.  Same arithmetic as select_thread_body otherwise (float64 at
+// the noisy root, float32 below); works for any action count (the rows are read action by action).
+template <class R>
+__global__ void __launch_bounds__(64)
+select_vl_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch, const double* __restrict__ noise_in) {
+  using Board = typename R::Board;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) *e.leaf_count = 0;
+  if (g >= dm.G) return;
+  const size_t d0 = (size_t)g * dm.B;
+  if (e.status[g] != ST_ACTIVE) {
+    for (int j = 0; j < batch; ++j) store_desc_skip(e.desc + d0 + j);
+    return;
+  }
+  const int A = dm.A;
+  const Board root = e.root_board[g];
+  const int root_who = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? root_who : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  const HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const uint64_t* khi = RulesTraits<R>::kHasKeyHi ? (e.key_hi + nb) : nullptr;
+  const float c_f = (float)sp.c_puct;
+  const float keep_f = (float)(1.0 - sp.explore);
+  const int root_node = ht_lookup1(ht, dm.hash_cap, gen, rules.key(root), khi);
+  int lens[32];  // path lengths of this minibatch's earlier descents (batch <= 32)
+  for (int j = 0; j < batch; ++j) {
+    Board s = root;
+    int who = root_who;
+    Key128 key = rules.key(s);
+    int node = root_node, depth = 0, kind = KIND_EXPAND;
+    float term_value = 0.0f;
+    uint32_t* path = e.d_path + (d0 + j) * dm.max_depth;
+    while (node >= 0) {
+      // virtual visits at this node: the edges earlier descents took from it (a position sits at one depth only)
+      int va[32], nv = 0;
+      for (int i = 0; i < j; ++i)
+        if (lens[i] > depth) {
+          const uint32_t pe = e.d_path[(d0 + i) * dm.max_depth + depth];
+          if ((int)(pe >> 8) == node) va[nv++] = (int)(pe & 0xffu);
+        }
+      const size_t row = (nb + (size_t)node) * dm.RS;
+      int sum_n = nv;
+      for (int a = 0; a < A; ++a) sum_n += e.N[row + a] & kCountMask;
+      double best = -INFINITY;
+      int best_a = 0;
+      const double sq64 = sqrt((double)sum_n);
+      const float sq32 = __fsqrt_rn((float)sum_n);
+      const double* z = noise_in + ((size_t)g * batch + j) * A;
+      for (int a = 0; a < A; ++a) {
+        if (!rules.legal(s, a)) continue;
+        int k = 0;
+        for (int i = 0; i < nv; ++i) k += va[i] == a ? 1 : 0;
+        const int n = (e.N[row + a] & kCountMask) + k;
+        const float w = e.W[row + a] - (float)k;
+        const float p = e.P[row + a];
+        double sc;
+        if (depth == 0) {
+          const double pn = __dadd_rn((double)__fmul_rn(keep_f, p), __dmul_rn(sp.explore, z[a]));
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sq64), (double)(1 + n));
+          sc = __dadd_rn(n > 0 ? (double)__fdiv_rn(w, (float)n) : 0.0, u);
+        } else {
+          const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p), sq32), (float)(1 + n));
+          sc = (double)__fadd_rn(n > 0 ? __fdiv_rn(w, (float)n) : 0.0f, t);
+        }
+        if (sc > best) {
+          best = sc;
+          best_a = a;
+        }
+      }
+      const int a = best_a;
+      path[depth] = ((uint32_t)node << 8) | (uint32_t)a;
+      ++depth;
+      const bool won = rules.apply(s, a, who);
+      who ^= 1;
+      if (won) {
+        kind = KIND_TERMINAL;
+        term_value = -1.0f;
+        break;
+      }
+      if (!rules.any_legal(s)) {
+        kind = KIND_TERMINAL;
+        term_value = 0.0f;
+        break;
+      }
+      key = rules.key(s);
+      const int linked = e.C[row + a];
+      if (linked >= 0) {
+        node = linked;
+      } else {
+        node = ht_lookup1(ht, dm.hash_cap, gen, key, khi);
+        if (node >= 0) e.C[row + a] = node;
+      }
+    }
+    lens[j] = depth;
+    store_desc(e.desc + d0 + j, kind, who, depth, term_value, key, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------ plan
 // Back-up queue = terminal descents in descent order, then the first occurrence of every distinct new leaf
 // (lib/mcts.py:265-278); unique leaves are appended to the compact batch (order across games is arbitrary; results do
@@ -599,10 +705,26 @@ __device__ __forceinline__ void expand_backup_body(const View<typename R::Board>
     const int node = __shfl_sync(gmask, my_node, gbase + q);
     const int slot = __shfl_sync(gmask, my_slot, gbase + q);
     const size_t row = (nb + (size_t)node) * dm.RS;
+    float scale = 1.0f;
+    const bool mask = (dm.flags & FLAG_MASK_PRIORS) != 0u;
+    typename R::Board nboard;
+    if (mask) {  // extension: priors of illegal moves zeroed, the rest renormalised (the reference keeps the raw softmax)
+      const int di = __shfl_sync(gmask, my_di, gbase + q);
+      nboard = e.desc[d0 + di].board;
+      const R legality{};
+      float part = 0.0f;
+      for (int a = lane; a < dm.A; a += GW)
+        if (legality.legal(nboard, a)) part += probs[(size_t)slot * dm.A + a];
+#pragma unroll
+      for (int off = GW / 2; off > 0; off >>= 1) part += __shfl_xor_sync(gmask, part, off);
+      scale = part > 0.0f ? 1.0f / part : 1.0f;
+    }
     for (int a = lane; a < dm.Apad; a += GW) {
       e.N[row + a] = 0;
       e.W[row + a] = 0.0f;
-      e.P[row + a] = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
+      float p = (a < dm.A) ? probs[(size_t)slot * dm.A + a] : 0.0f;
+      if (mask && a < dm.A) p = R{}.legal(nboard, a) ? p * scale : 0.0f;
+      e.P[row + a] = p;
       e.C[row + a] = -1;
     }
   }
@@ -815,6 +937,12 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
     e.root_board[g] = s;
     e.root_player[g] = (uint8_t)(who ^ 1);
     e.ply[g] = ply + 1;
+    if (dm.flags & FLAG_FRESH_TREE) {  // extension: no tree reuse between moves -- arena demand bounded by one move's searches
+      for (int t = 0; t < dm.tpg; ++t) {
+        e.node_count[g * dm.tpg + t] = 0;
+        e.tree_gen[g * dm.tpg + t] += 1u;
+      }
+    }
     return;
   }
   // ---- game over -------------------------------------------------------------------------

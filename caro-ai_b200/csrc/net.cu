@@ -53,7 +53,7 @@ net_simt_kernel(R rules, const typename R::Board* __restrict__ boards, const uin
     __syncthreads();
     float* cur = buf0;
     float* nxt = buf1;
-    for (int layer = 0; layer < kBlocks; ++layer) {
+    for (int layer = 0; layer < L.blocks; ++layer) {
       const float* wgt = blob + L.conv_w[layer];
       const float* bias = blob + L.conv_b[layer];
       for (int o = threadIdx.x; o < kFilters * HW; o += blockDim.x) {
@@ -142,6 +142,11 @@ extern "C" {
 
 size_t caro_net_blob_floats(int rows, int cols, int actions) { return blob_layout(rows, cols, actions).total; }
 
+size_t caro_net_blob_floats_deep(int rows, int cols, int actions, int blocks) {
+  if (blocks < 1 || blocks > kMaxBlocks) return 0;
+  return blob_layout(rows, cols, actions, blocks).total;
+}
+
 int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats) {
   if (!net || !h_blob) return caro_fail(CARO_E_ARG, "null argument");
   if (n_floats != net->layout.total) return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
@@ -167,7 +172,16 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->H = rows;
   net->W = cols;
   net->A = actions;
-  net->layout = blob_layout(rows, cols, actions);
+  {  // the depth of the tower is read off the blob's length: base + blocks x (64 x 64 x 9 + 64) floats
+    const size_t per_block = (size_t)kFilters * kFilters * 9 + kFilters;
+    const size_t base = blob_layout(rows, cols, actions, 1).total - per_block;
+    const size_t blocks = n_floats > base ? (n_floats - base) / per_block : 0;
+    if (blocks < 1 || blocks > (size_t)kMaxBlocks || base + blocks * per_block != n_floats) {
+      delete net;
+      return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
+    }
+    net->layout = blob_layout(rows, cols, actions, (int)blocks);
+  }
   net->d_blob = nullptr;
   net->d_tc_weights = nullptr;
   net->d_rt_weights = nullptr;

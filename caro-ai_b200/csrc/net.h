@@ -8,26 +8,31 @@
 namespace caro {
 
 constexpr int kFilters = 64;      // lib/model.py:7
-constexpr int kBlocks = 5;        // conv_1 .. conv_5
+constexpr int kBlocks = 5;        // conv_1 .. conv_5: the reference's depth (lib/model.py:21-45)
+constexpr int kMaxBlocks = 20;    // deepest tower the kernels accept ("deep residual net" of BASELINE configs[3]): the number of
+                                  // residual blocks is a run-time property of the weight blob, the width (64 filters) is not
 constexpr float kLeaky = 0.01f;   // nn.LeakyReLU default slope
 
 // Offsets (in floats) of the folded-weight blob described in include/caro_b200.h
 struct BlobLayout {
   size_t conv_in_w, conv_in_b;
-  size_t conv_w[kBlocks], conv_b[kBlocks];
+  size_t conv_w[kMaxBlocks], conv_b[kMaxBlocks];
+  int blocks;
   size_t val_conv_w, val_conv_b, val_fc1_w, val_fc1_b, val_fc2_w, val_fc2_b;
   size_t pol_conv_w, pol_conv_b, pol_fc_w, pol_fc_b;
   size_t total;
 };
 
-inline BlobLayout blob_layout(int H, int W, int A) {
+inline BlobLayout blob_layout(int H, int W, int A, int blocks = kBlocks) {
   BlobLayout L;
+  L.blocks = blocks;
+  for (int i = 0; i < kMaxBlocks; ++i) L.conv_w[i] = L.conv_b[i] = 0;
   size_t o = 0;
   const size_t hw = (size_t)H * W;
   auto take = [&](size_t n) { size_t r = o; o += n; return r; };
   L.conv_in_w = take(kFilters * 2 * 9);
   L.conv_in_b = take(kFilters);
-  for (int i = 0; i < kBlocks; ++i) {
+  for (int i = 0; i < blocks; ++i) {
     L.conv_w[i] = take((size_t)kFilters * kFilters * 9);
     L.conv_b[i] = take(kFilters);
   }
@@ -54,7 +59,7 @@ struct caro_net {
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
   void* d_rx_weights;   // fp16 hi / lo UMMA B-operand blocks of the split-precision row-tiled tower -- see net_rx.cu
-  alignas(16) float h_rt_consts[6 * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
+  alignas(16) float h_rt_consts[(caro::kMaxBlocks + 1) * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
   float* d_tc_bias;     // [6][64] folded conv biases
   float* d_pol_fc_t;    // policy FC transposed to [2*HW][A] (+ value FC1 [HW][20]) for coalesced reads in the TC epilogue
   void* d_headfeat;     // large boards: exported activated head features, bf16 hi + lo images in the A-operand layout of net_heads.cu

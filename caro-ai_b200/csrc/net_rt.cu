@@ -242,7 +242,8 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     // ===================== weight producer: the 11 regions of the network, over and over, round-robin into the
     // three resident regions; a region is refilled as soon as the last tile of its layer has released it ==========
     if ((tid & 31) == 0) {
-      const int total = my_groups * kRtRegionsNet;
+      const int regions_net = 2 * gm.layers - 1;  // conv_in (3 blocks + 3 unused) + 2 per residual block
+      const int total = my_groups * regions_net;
       int reg = 0, src = 0;
       uint32_t round = 0;
       for (int n = 0; n < total; ++n) {
@@ -256,7 +257,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * kRtBlockBytes, wimg + (size_t)(src * kRtRegionBlocks + b) * kRtBlockBytes,
                    (uint32_t)kRtBlockBytes, bar);
         if (++reg == kRtRegions) { reg = 0; ++round; }
-        if (++src == kRtRegionsNet) src = 0;
+        if (++src == regions_net) src = 0;
       }
     }
   } else if (warp == K::kMmaWarp) {
@@ -274,7 +275,8 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   do {                                                                          \
     if (tr && (idx) < 1000) trace[(kind) * 1000 + (idx)] = clock64();           \
   } while (0)
-    const int total_layers = my_groups * kRtLayers;
+    const int n_layers = gm.layers;
+    const int total_layers = my_groups * n_layers;
     int reg = 0;
     uint32_t rphase = 0;
     int layer = 0;
@@ -314,7 +316,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const uint32_t full0 = cur.full0, full1 = cur.full1, empty0 = cur.empty0, empty1 = cur.empty1, ph0 = cur.ph0, ph1 = cur.ph1;
       // the next layer's regions are worked out in the middle of tile 1 (H >= 2), not between two layers, and pinned there
       auto mid = [&]() {
-        nxt = take_regions(layer + 1 == kRtLayers);
+        nxt = take_regions(layer + 1 == n_layers);
         asm volatile("" : "+l"(nxt.rb0), "+l"(nxt.rb1), "+r"(nxt.full0), "+r"(nxt.full1), "+r"(nxt.empty0), "+r"(nxt.empty1), "+r"(nxt.ph0),
                      "+r"(nxt.ph1));
       };
@@ -362,7 +364,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         __syncwarp();
       }
       pre_waited = H >= 4 && gl + 1 < total_layers;
-      if (++layer == kRtLayers) layer = 0;
+      if (++layer == n_layers) layer = 0;
     }
 #undef RT_MMA_TRACE
   } else {
@@ -490,7 +492,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         for (int hh = 0; hh < 2; ++hh) {
           uint8_t* arow = act + (size_t)(hh * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
           float2 v[16];
-          load_values(std::true_type{}, kRtLayers - 1, y, hh * 32, v, arow);
+          load_values(std::true_type{}, gm.layers - 1, y, hh * 32, v, arow);
           const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -518,17 +520,17 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const bool more = gi + 1 < my_groups;
       const long long next_leaf0 = (blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb;
-      const int gl0 = gi * kRtLayers;
+      const int gl0 = gi * gm.layers;
 #pragma unroll 1
       for (int y = 0; y < H; ++y) epilogue_tile(std::false_type{}, 0, gl0, y);
 #pragma unroll 1
-      for (int layer = 1; layer < kRtLayers - 1; ++layer) {
+      for (int layer = 1; layer < gm.layers - 1; ++layer) {
 #pragma unroll 1
         for (int y = 0; y < H; ++y) epilogue_tile(std::true_type{}, layer, gl0 + layer, y);
       }
       if (gi > 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // the previous group's features have been consumed
 #pragma unroll 1
-      for (int y = 0; y < H; ++y) last_tile(gi, gl0 + kRtLayers - 1, y, more, next_leaf0);
+      for (int y = 0; y < H; ++y) last_tile(gi, gl0 + gm.layers - 1, y, more, next_leaf0);
       mbar_arrive(bar_feat + 0);  // this thread's head features are in place (release) -> head warps
       if (tid == 0) TC_TRACE(4, gi);
       if (!more) {  // join the head warps for the heads of the last group
@@ -579,7 +581,8 @@ using namespace caro;
 // output tile above / at / below the source tile).
 int caro_net_rt_pack(caro_net* net, const float* h) {
   const BlobLayout& L = net->layout;
-  const size_t img_bytes = (size_t)kRtBlocksNet * kRtBlockBytes;
+  const int blocks = L.blocks;
+  const size_t img_bytes = (size_t)(1 + 2 * blocks) * kRtRegionBlocks * kRtBlockBytes;
   std::vector<uint16_t> img(img_bytes / 2, 0);
   auto put = [&](int block, int j, int co, int c, float w) {
     const size_t off = (size_t)block * kRtBlockBytes + (size_t)(c / 8) * 3072 + (size_t)(j * 64 + co) * 16 + (size_t)(c % 8) * 2;
@@ -589,7 +592,7 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
     for (int j = 0; j < 3; ++j)
       for (int co = 0; co < 64; ++co)
         for (int ci = 0; ci < 2; ++ci) put(kx, j, co, ci, h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + (2 - j) * 3 + kx)]);
-  for (int l = 0; l < kBlocks; ++l)
+  for (int l = 0; l < blocks; ++l)
     for (int kx = 0; kx < 3; ++kx)
       for (int kk = 0; kk < 4; ++kk)
         for (int j = 0; j < 3; ++j)
@@ -600,7 +603,7 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
   static_assert(sizeof(RtConsts) <= sizeof(net->h_rt_consts), "caro_net::h_rt_consts is too small");
   RtConsts* hc = reinterpret_cast<RtConsts*>(net->h_rt_consts);
   for (int co = 0; co < 64; ++co) hc->bias[co] = h[L.conv_in_b + co];
-  for (int l = 0; l < kBlocks; ++l)
+  for (int l = 0; l < blocks; ++l)
     for (int co = 0; co < 64; ++co) hc->bias[(l + 1) * 64 + co] = h[L.conv_b[l] + co];
   for (int c = 0; c < 64; ++c) {
     hc->headw[c] = h[L.val_conv_w + c];
@@ -624,7 +627,7 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
     }
   }
   cudaError_t ce = cudaSuccess;
-  if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);
+  if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);  // the depth of a handle never changes (caro_net_update checks the blob size)
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
@@ -649,6 +652,7 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
   gm.pshift = net->W < 4 ? 2 : 3;
   gm.pitch = 1 << gm.pshift;
   gm.nb = 128 / gm.pitch;
+  gm.layers = 1 + net->layout.blocks;
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;

@@ -43,7 +43,6 @@ namespace caro {
 constexpr int kRxSlots = 3;                                   // weight ring: three 6 KB blocks
 constexpr int kRxLayerBlocks = 24;                            // 12 (dx, k-step) blocks x {hi, lo}
 constexpr int kRxInBlocks = 6;                                // conv_in: 3 dx blocks x {hi, lo}
-constexpr int kRxBlocksNet = kRxInBlocks + kBlocks * kRxLayerBlocks;   // 126 blocks in the global image
 constexpr uint32_t kRxLoUnits = kRtActBytes / 16;             // descriptor offset of the lo activation image
 
 __host__ __device__ constexpr uint32_t rx_idesc(uint32_t n) {  // D = f32, A = B = f16 (format 0), K-major, M = 128
@@ -166,9 +165,10 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
                                                     consts.headb[1], consts.headb[2], fcv, pol_fc_t, val_fc1_t, probs, values, consts);
     }
   } else if (warp == K::kLoadWarp) {
-    // ===================== weight producer: the 126 blocks of the network, over and over, into the ring ==============
+    // ===================== weight producer: the blocks of the whole network, over and over, into the ring ===========
     if ((tid & 31) == 0) {
-      const long long total = (long long)my_groups * kRxBlocksNet;
+      const int blocks_net = kRxInBlocks + (gm.layers - 1) * kRxLayerBlocks;  // 126 blocks for the reference's five residual layers
+      const long long total = (long long)my_groups * blocks_net;
       int slot = 0, src = 0;
       uint32_t round = 0;
       for (long long n = 0; n < total; ++n) {
@@ -176,7 +176,7 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         mbar_expect_tx(bar_full + slot, (uint32_t)kRtBlockBytes);
         bulk_g2s(wgt + slot * kRtBlockBytes, wimg + (size_t)src * kRtBlockBytes, (uint32_t)kRtBlockBytes, bar_full + slot);
         if (++slot == kRxSlots) { slot = 0; ++round; }
-        if (++src == kRxBlocksNet) src = 0;
+        if (++src == blocks_net) src = 0;
       }
     }
   } else if (warp == K::kMmaWarp) {
@@ -186,7 +186,8 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     const uint64_t a_desc0 = make_desc(smem_u32(act) + (uint32_t)kRtHalo * 16u, (uint32_t)kRtChunkBytes, 128u);
     const uint64_t b_desc0 = make_desc(smem_u32(wgt), 192u * 16u, 128u);
     const uint32_t full_a = smem_u32(bar_full), empty_a = smem_u32(bar_empty), acc_a = smem_u32(bar_acc), act_a = smem_u32(bar_act);
-    const int total_layers = my_groups * kRtLayers;
+    const int n_layers = gm.layers;
+    const int total_layers = my_groups * n_layers;
     int slot = 0;
     uint32_t sphase = 0;
     int layer = 0;
@@ -290,7 +291,7 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         for (int k = 0; k < 2; ++k)
           if (++slot == kRxSlots) { slot = 0; sphase ^= 1u; }
       }
-      if (++layer == kRtLayers) layer = 0;
+      if (++layer == n_layers) layer = 0;
     }
 #undef RX_ISSUE
   } else {
@@ -409,7 +410,7 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         for (int hh = 0; hh < 2; ++hh) {
           const uint8_t* arow = act + (size_t)(hh * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
           float2 v[16];
-          load_values(std::true_type{}, kRtLayers - 1, y, hh * 32, v, arow);
+          load_values(std::true_type{}, gm.layers - 1, y, hh * 32, v, arow);
           const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -437,17 +438,17 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
       const bool more = gi + 1 < my_groups;
       const long long next_leaf0 = (blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb;
-      const int gl0 = gi * kRtLayers;
+      const int gl0 = gi * gm.layers;
 #pragma unroll 1
       for (int y = set; y < H; y += 2) epilogue_tile(std::false_type{}, 0, gl0, y);
 #pragma unroll 1
-      for (int layer = 1; layer < kRtLayers - 1; ++layer) {
+      for (int layer = 1; layer < gm.layers - 1; ++layer) {
 #pragma unroll 1
         for (int y = set; y < H; y += 2) epilogue_tile(std::true_type{}, layer, gl0 + layer, y);
       }
       if (gi > 0) mbar_wait(bar_feat + 1, (uint32_t)(gi - 1) & 1u);  // the previous group's features have been consumed
 #pragma unroll 1
-      for (int y = set; y < H; y += 2) last_tile(gl0 + kRtLayers - 1, y, more, next_leaf0);
+      for (int y = set; y < H; y += 2) last_tile(gl0 + gm.layers - 1, y, more, next_leaf0);
       mbar_arrive(bar_feat + 0);
       if (!more) {  // join the head warps for the heads of the last group
         mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
@@ -472,12 +473,13 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
 
 using namespace caro;
 
-// Weight image: 126 blocks of 6,144 B in consumption order -- conv_in: hi(dx=-1), lo(dx=-1), hi(0), lo(0), hi(+1), lo(+1);
+// Weight image: 6 + 24 x blocks (126 for the reference's depth) blocks of 6,144 B in consumption order -- conv_in: hi(dx=-1), lo(dx=-1), hi(0), lo(0), hi(+1), lo(+1);
 // every residual layer: for (dx, k-step) in order: hi block, lo block.  A block is the B operand [2 k-chunks][n = 192][8 in-channels]
 // of net_rt.cu in fp16: n = 64 j + out-channel with j = 0, 1, 2 <-> vertical tap ky = 2, 1, 0.
 int caro_net_rx_pack(caro_net* net, const float* h) {
   const BlobLayout& L = net->layout;
-  const size_t img_bytes = (size_t)kRxBlocksNet * kRtBlockBytes;
+  const int blocks = L.blocks;
+  const size_t img_bytes = (size_t)(kRxInBlocks + blocks * kRxLayerBlocks) * kRtBlockBytes;
   std::vector<uint16_t> img(img_bytes / 2, 0);
   auto put = [&](int block, int j, int co, int c, float w) {  // `block` = index of the hi block; its lo block follows
     const __half hi = __float2half_rn(w);
@@ -490,7 +492,7 @@ int caro_net_rx_pack(caro_net* net, const float* h) {
     for (int j = 0; j < 3; ++j)
       for (int co = 0; co < 64; ++co)
         for (int ci = 0; ci < 2; ++ci) put(2 * kx, j, co, ci, h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + (2 - j) * 3 + kx)]);
-  for (int l = 0; l < kBlocks; ++l)
+  for (int l = 0; l < blocks; ++l)
     for (int kx = 0; kx < 3; ++kx)
       for (int kk = 0; kk < 4; ++kk)
         for (int j = 0; j < 3; ++j)
@@ -520,6 +522,7 @@ static int launch_rx(const R& rules, caro_net* net, const void* boards, const ui
   gm.pshift = net->W < 4 ? 2 : 3;
   gm.pitch = 1 << gm.pshift;
   gm.nb = 128 / gm.pitch;
+  gm.layers = 1 + net->layout.blocks;
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats || 41 + gm.A > 128)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;

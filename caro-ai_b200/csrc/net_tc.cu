@@ -39,7 +39,8 @@ constexpr int kLayerBytes = 9 * kTapBytes;               // 73,728
 constexpr int kLayerBytesIn = 9 * kTapBytesIn;           // 18,432
 constexpr int kHeadfeatSlots = 8;                         // scratch slots for exported head features (launches in flight)
 constexpr int kHeadsInTowerMaxHW = 64;                    // larger boards run their FC heads in heads_tc_kernel (net_heads.cu)
-constexpr int kNumLayers = 1 + kBlocks;                  // conv_in + 5 residual blocks
+constexpr int kSmemBiasLayers = 1 + kBlocks;             // biases of the first six layers sit in shared memory (the budget has 384 bytes to
+                                                         // spare); deeper towers (BlobLayout::blocks > 5) read the others from global memory
 constexpr int kEpiWarps = 8;                             // warps 0-7: epilogue; TMEM lane quarter = warp & 3, column half = warp >> 2
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;                      // warp 8: TMEM owner + MMA issue for tiles 0,2
@@ -73,7 +74,7 @@ struct TcCfg {
   static constexpr int kAct = 0;
   static constexpr int kWgt = kAct + kActBufs * kActBytes;
   static constexpr int kBias = kWgt + kWStages * kWStageBytes;     // float [6][64]
-  static constexpr int kHeadW = kBias + kNumLayers * 64 * 4;       // float [3][64] + [3] biases (+pad)
+  static constexpr int kHeadW = kBias + kSmemBiasLayers * 64 * 4;  // float [3][64] + [3] biases (+pad)
   static constexpr int kHeadF = kHeadW + 4 * 64 * 4;               // float [rows][3] head features
   static constexpr int kFc = kHeadF + kGroupRows * 3 * 4;          // float hidden[nb][20] + logits[nb][A]
   static constexpr int kFcFloats = TILES * 256;
@@ -168,7 +169,8 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < K::kActBufs * K::kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < kNumLayers * 64; i += kThreads) bias_s[i] = bias_g[i];
+  const int n_layers = 1 + L.blocks;
+  for (int i = tid; i < min(n_layers, kSmemBiasLayers) * 64; i += kThreads) bias_s[i] = bias_g[i];
   for (int p = tid; p < K::kGroupRows; p += kThreads) {  // padded position -> (board, cell) once, no divisions in the hot loop
     const int b = p / gm.block, within = p - b * gm.block;
     const int r = within / gm.pitch, c = within - r * gm.pitch;
@@ -227,9 +229,9 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
     const uint32_t act_addr = smem_u32(act);
     const uint32_t wgt_addr = smem_u32(wgt);
-    const int total_layers = my_groups * kNumLayers;
+    const int total_layers = my_groups * n_layers;
     auto load_layer = [&](int gl) {  // global layer index -> weight stage gl % kWStages (hi image, then lo)
-      const int l = gl % kNumLayers;
+      const int l = gl % n_layers;
       uint8_t* dst = wgt + (gl % K::kWStages) * K::kWStageBytes;
       uint64_t* bar = bar_w + (gl % K::kWStages);
       const int tap_bytes = l == 0 ? kTapBytesIn : kTapBytes;
@@ -252,7 +254,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     constexpr uint64_t kBLo = (uint64_t)(kLayerBytes / 16);    // lo weight image
     const int pitch = gm.pitch;
     for (int gl = 0; gl < total_layers; ++gl) {
-      const bool first = (gl % kNumLayers) == 0;
+      const bool first = (gl % n_layers) == 0;
       const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl % K::kWStages) * (K::kWStageBytes / 16));
       mbar_wait(bar_w + (gl % K::kWStages), (uint32_t)(gl / K::kWStages) & 1u);
       if (elected) TC_TRACE(6, gl * 2 + mw);  // weights present
@@ -350,12 +352,14 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       const long long grp = blockIdx.x + (long long)gi * gridDim.x;
       const long long leaf0 = grp * nb;
 #pragma unroll 1
-      for (int layer = 0; layer < kNumLayers; ++layer) {
-        const int gl = gi * kNumLayers + layer;
+      for (int layer = 0; layer < n_layers; ++layer) {
+        const int gl = gi * n_layers + layer;
         const uint32_t acc_par = (uint32_t)gl & 1u;
-        const bool last = layer == kNumLayers - 1;
+        const bool last = layer == n_layers - 1;
         const bool has_res = layer > 0;
-        const float4* bl4 = reinterpret_cast<const float4*>(bias_s + layer * 64 + half * 32);
+        const bool bias_in_smem = layer < kSmemBiasLayers;
+        const float4* bl4 = reinterpret_cast<const float4*>(bias_s + (bias_in_smem ? layer : 0) * 64 + half * 32);
+        const float4* bg4 = reinterpret_cast<const float4*>(bias_g + layer * 64 + half * 32);
 #pragma unroll 1
         for (int t = 0; t < K::kTiles; ++t) {
           // tile t's own accumulator AND tile t+1's (it reads the tail rows of tile t as its halo); the two
@@ -380,7 +384,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bq = bl4[q];
+            const float4 bq = bias_in_smem ? bl4[q] : __ldg(bg4 + q);
             const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -482,7 +486,8 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
   const BlobLayout& L = net->layout;
   // global image: conv_in {hi, lo}, then per residual block {hi, lo}; each part is a stack of 9 tap images in the
   // UMMA B-operand layout [8-channel chunk][n = 64 out channels][8 in channels] (no-swizzle K-major core matrices)
-  const size_t img_bytes = 2 * ((size_t)kLayerBytesIn + (size_t)kBlocks * kLayerBytes);
+  const int blocks = L.blocks;
+  const size_t img_bytes = 2 * ((size_t)kLayerBytesIn + (size_t)blocks * kLayerBytes);
   std::vector<uint16_t> img(img_bytes / 2, 0);
   auto put = [&](size_t part_base, size_t tap_bytes, int tap, int co, int ci, float w) {
     const uint16_t hi = f32_to_bf16(w);
@@ -497,15 +502,15 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
   for (int tap = 0; tap < 9; ++tap)
     for (int co = 0; co < 64; ++co)
       for (int ci = 0; ci < 2; ++ci) put(0, kTapBytesIn, tap, co, ci, h[L.conv_in_w + ((size_t)(co * 2 + ci) * 9 + tap)]);
-  for (int l = 0; l < kBlocks; ++l) {
+  for (int l = 0; l < blocks; ++l) {
     const size_t base = 2 * (size_t)kLayerBytesIn + (size_t)l * 2 * kLayerBytes;
     for (int tap = 0; tap < 9; ++tap)
       for (int co = 0; co < 64; ++co)
         for (int ci = 0; ci < 64; ++ci) put(base, kTapBytes, tap, co, ci, h[L.conv_w[l] + ((size_t)(co * 64 + ci) * 9 + tap)]);
   }
-  std::vector<float> bias((size_t)kNumLayers * 64);
+  std::vector<float> bias((size_t)(1 + blocks) * 64);
   for (int co = 0; co < 64; ++co) bias[co] = h[L.conv_in_b + co];
-  for (int l = 0; l < kBlocks; ++l)
+  for (int l = 0; l < blocks; ++l)
     for (int co = 0; co < 64; ++co) bias[(size_t)(l + 1) * 64 + co] = h[L.conv_b[l] + co];
   const int HW = net->H * net->W, A = net->A;
   // transposed FC weights, policy [2*HW][A] followed by value-FC1 [HW][20]: a warp's outputs read contiguous floats

@@ -28,9 +28,7 @@ constexpr int kRtBlockUnits = kRtBlockBytes / 16;            // in descriptor un
 constexpr int kRtRegionBlocks = 6;                           // a weight region = half a layer
 constexpr int kRtRegions = 3;                                // resident regions: layer L in two, the first half of L+1 in the third
 constexpr int kRtRegionBytes = kRtRegionBlocks * kRtBlockBytes;          // 36,864
-constexpr int kRtRegionsNet = 1 + 2 * kBlocks;               // conv_in (3 blocks + 3 unused) + 2 per residual block
-constexpr int kRtBlocksNet = kRtRegionsNet * kRtRegionBlocks;             // 66 blocks in the global image
-constexpr int kRtLayers = 1 + kBlocks;
+constexpr int kRtMaxLayers = 1 + kMaxBlocks;                 // conv_in + residual blocks (the depth is a run-time value: RtGeom::layers)
 constexpr uint32_t kRtTmemCols = 512;
 constexpr uint32_t kRtLoCol = 384;                           // e5m2 lo residual: tile y at 384 + 16 y
 constexpr int kRtConstFcFloats = 1536;                       // FC weights that travel in the kernel parameters
@@ -43,12 +41,13 @@ __host__ __device__ constexpr uint32_t rt_idesc(uint32_t n) {
 
 struct RtGeom {
   int H, W, A, pitch, pshift, nb;
+  int layers;  // 1 + residual blocks of this network
 };
 
 // Small per-network constants passed BY VALUE as a __grid_constant__ kernel parameter: they are read through the
 // constant cache (LDC), not through the shared-memory pipe, which the tensor cores' operand fetches saturate.
 struct RtConsts {
-  float bias[kRtLayers * 64];   // folded conv biases
+  float bias[kRtMaxLayers * 64];   // folded conv biases
   float headw[3 * 64];          // 1x1 head convolutions: value, policy 0, policy 1
   float headb[4];               // their (folded) biases
   // transposed FC weights, policy [2 HW][A] then value FC1 [HW][20], when they fit (Connect4: 1,428 floats): the FC heads

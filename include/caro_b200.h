@@ -80,13 +80,17 @@ int caro_backup_path(int32_t* d_n, float* d_w, float* d_q, const int64_t* d_edge
  * Policy/value network -- row a17 (lib/model.py:10-94) + the softmax of lib/mcts.py:216.
  * Weights are handed over ALREADY FOLDED (eval-mode BatchNorm merged into the convolutions,
  * done on the host by caro_ai_b200.model.fold_state_dict) as one float32 blob:
- *   conv_in  w[64][2][3][3] b[64] | 5 x ( w[64][64][3][3] b[64] ) |
+ *   conv_in  w[64][2][3][3] b[64] | blocks x ( w[64][64][3][3] b[64] ) |      (blocks = 5 in the reference)
  *   conv_val w[64] b[1] | value.0 w[20][HW] b[20] | value.2 w[20] b[1] |
  *   conv_policy w[2][64] b[2] | policy.0 w[A][2*HW] b[A]
  * ------------------------------------------------------------------------------------------ */
 typedef struct caro_net caro_net;
 
 size_t caro_net_blob_floats(int rows, int cols, int actions);
+/* The same for a tower of `blocks` residual blocks (1..20; the reference has 5, lib/model.py:21-45): the blob then holds
+ * `blocks` x ( w[64][64][3][3] b[64] ) groups, and caro_net_create reads the depth off the blob's length.  The width
+ * (64 filters) is fixed.  Returns 0 for an unsupported depth. */
+size_t caro_net_blob_floats_deep(int rows, int cols, int actions, int blocks);
 /* Copies and re-packs the blob into device memory owned by the handle (bf16 UMMA operand images
  * for the tensor-core tower + fp32 copies for the heads).  Synchronous. */
 int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t n_floats,
@@ -140,7 +144,23 @@ typedef struct {
   double alpha;            /* config.py:27 */
   double explore;          /* config.py:28 */
   uint64_t seed;           /* Philox key */
+  uint32_t flags;          /* CARO_FLAG_*: throughput-mode extensions that are NOT in the reference;
+                              0 = reference behaviour (bit-exact trees) */
+  uint32_t reserved;
 } caro_engine_config;
+
+/* Extensions, all off by default.  With any of them set the search is no longer the reference's (lib/mcts.py:248-287);
+ * they are validated statistically (tests/test_gpu_round2.py), not bit for bit.
+ *   VIRTUAL_LOSS   the batch_size descents of a minibatch are made one after the other per game, and every edge an
+ *                  earlier descent of the same minibatch went through counts as one extra visit that lost
+ *                  (N + 1, W - 1 in the PUCT score; the tree itself is not modified, so the back-up is unchanged): the
+ *                  descents spread out instead of piling onto the same leaf (lib/mcts.py:273-278 drops ~70 % of them).
+ *   MASK_PRIORS    the network's priors are zeroed on illegal moves and renormalised when a node is created
+ *                  (the reference keeps the raw softmax and masks only the PUCT score, lib/mcts.py:86-95).
+ *   FRESH_TREE     a game's tree is cleared after each of its moves instead of being kept for the whole game
+ *                  (lib/utils.py:58-59 keeps it): arena demand is bounded by the searches of ONE move, which is what
+ *                  long 15 x 15 games at 1,600 descents per move need. */
+enum { CARO_FLAG_VIRTUAL_LOSS = 1, CARO_FLAG_MASK_PRIORS = 2, CARO_FLAG_FRESH_TREE = 4 };
 
 /* Bytes of device workspace the engine needs; the caller allocates it (e.g. a torch uint8 CUDA
  * tensor) and keeps it alive for the life of the handle. */

@@ -224,3 +224,19 @@ def test_single_rank_collective_helpers_are_identities():
     out = D.all_gather_rows(t)
     assert out[0] is t[0] and out[1] is t[1]
     assert D.reduce_tallies(1, 2, 3) == (1, 2, 3)
+
+
+def test_deep_tower_blob_sizes():
+    """The number of residual blocks is a property of the weight blob: 5 (the reference) by default, 1..20 accepted."""
+    from caro_ai_b200 import _cabi
+    from caro_ai_b200.model import Net, fold_state_dict
+    lib = _cabi.lib()
+    per_block = 64 * 64 * 9 + 64
+    assert lib.caro_net_blob_floats_deep(6, 7, 7, 5) == lib.caro_net_blob_floats(6, 7, 7)
+    assert lib.caro_net_blob_floats_deep(6, 7, 7, 10) == lib.caro_net_blob_floats(6, 7, 7) + 5 * per_block
+    assert lib.caro_net_blob_floats_deep(6, 7, 7, 0) == 0 and lib.caro_net_blob_floats_deep(6, 7, 7, 21) == 0
+    net = Net((2, 3, 3), 9, blocks=7)
+    assert fold_state_dict(net.state_dict(), 3, 3, 9).size == lib.caro_net_blob_floats_deep(3, 3, 9, 7)
+    x = torch.rand(4, 2, 3, 3)
+    logits, value = net(x)
+    assert tuple(logits.shape) == (4, 9) and tuple(value.shape) == (4, 1)
