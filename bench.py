@@ -500,7 +500,7 @@ def engine_arm(args):
         }
         if extra:
             line["extra"] = extra
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed beside the single-GPU number only
             cores = os.cpu_count() or 1
             r = run_cpu_reference(args.cpu_plies, 1, cores, 1)  # one process per host core, like the reference arm
             line["cpu_baseline"] = {"value": r["leaf_evals_per_s"], "unit": "leaf_evals/s", "cores": cores, "kind": r["kind"],

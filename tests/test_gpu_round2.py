@@ -588,13 +588,16 @@ def test_facade_reports_a_full_arena(torch_cuda):
 
 
 # --------------------------------------------------------------------------- shipped checkpoints
-def test_shipped_checkpoints_load_and_later_generation_is_not_weaker(torch_cuda):
+def test_shipped_checkpoints_load_and_later_generation_wins_its_arena(torch_cuda):
     """All four shipped checkpoints (saves/trained_connect4/best_025|026, saves/trained_tictactoe/best_004|005) load through
-    the reference's `.dat` format; the Connect4 generations play play.py's tournament (1,000 games per ordered pair, 40 x 8
-    searches, tau = 0, fresh trees): generation 026 -- promoted over 025 by the reference's > 0.60 arena gate -- must not
-    lose the match."""
+    the reference's `.dat` format.  Generation 026 was promoted over 025 by the reference's arena (train.py:120-149: games at
+    search_batch(20, 16), tau = 0, promotion above 0.60): replayed here -- 2 x 1,000 games, both colours, fresh trees per game
+    and side, the split-precision tower the precision check selects for these networks -- 026 must win that arena again
+    (measured 0.61; the unmodified reference on the CPU, 160 games at search_batch(20, 8): 0.575 with eval-mode BatchNorm,
+    0.67 with its train-mode BatchNorm).  The ordering is NOT robust to the search budget -- at play.py's 40 x 8 the older
+    net wins 0.61, at 80 x 8 it is even (tools/strength_diag.py) -- so only the arena's own setting is
+    asserted."""
     torch = torch_cuda
-    from caro_ai_b200 import config as cfg
     from caro_ai_b200.game import ConnectFour, TicTacToe
     from caro_ai_b200.model import DeviceNet, load_checkpoint
     from caro_ai_b200.utils import play_games_batched
@@ -610,11 +613,11 @@ def test_shipped_checkpoints_load_and_later_generation_is_not_weaker(torch_cuda)
     old = DeviceNet(load_checkpoint(os.path.join(ck, "connect4_best_025_10600.dat"), game).eval(), game)
     assert new.precision == old.precision == "bf16x3"
     rounds = 1000
-    a = play_games_batched(game, rounds, new, old, 0, cfg.PLAY_MCTS_SEARCHES, cfg.PLAY_MCTS_BATCH_SIZE, trees_per_game=2, seed=1)
-    b = play_games_batched(game, rounds, old, new, 0, cfg.PLAY_MCTS_SEARCHES, cfg.PLAY_MCTS_BATCH_SIZE, trees_per_game=2, seed=2)
+    a = play_games_batched(game, rounds, new, old, 0, 20, 16, trees_per_game=2, seed=1)
+    b = play_games_batched(game, rounds, old, new, 0, 20, 16, trees_per_game=2, seed=2)
     assert a["games"] == b["games"] == rounds
     new_wins, old_wins = a["wins"] + b["losses"], a["losses"] + b["wins"]
-    assert new_wins >= old_wins, (a, b)
+    assert new_wins > 1.15 * old_wins, (a, b)
     new.close()
     old.close()
 

@@ -89,40 +89,59 @@ def config1():
 
 
 def config3():
-    """One outer step of the training loop at train.py's own search setting (10 x 8) plus the 10 SGD rounds."""
+    """One outer step of the training loop at train.py's own search setting (10 x 8) plus the 10 SGD rounds, on this rank's
+    GPU (under torchrun every rank runs it and the collectives of the step are real; rank 0 prints)."""
+    import torch.distributed as dist
     import torch.optim as optim
-    from caro_ai_b200 import train as T
+    from caro_ai_b200 import distributed as D, train as T
+    from caro_ai_b200.utils import SelfPlayWorker
+    if "RANK" in os.environ and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    rank, ws = D.world()
     game = ConnectFour()
     torch.manual_seed(0)
     device = torch.device("cuda", torch.cuda.current_device())
     net = Net(game.obs_shape, game.action_space).to(device)
+    D.broadcast_state_dict(net)
     best = DeviceNet(net, game)
-    replay = collections.deque(maxlen=1 << 20)
 
     class _TB:
         def track(self, *a, **k):
             pass
 
     games = 4096
-    t0 = time.perf_counter()
-    stats, dt = T.self_play(game, replay, best, games, _TB(), 0, seed=1)
+    worker = SelfPlayWorker(game, games, cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.STEPS_BEFORE_TAU_0, replay_steps=2,
+                            min_replay=cfg.REPLAY_BUFFER, seed=1000003 * rank + 17)
+    T.self_play(worker, best, _TB(), 0)  # warm-up step (workspace first touched)
     torch.cuda.synchronize()
-    sp = time.perf_counter() - t0
+    stats, sp = T.self_play(worker, best, _TB(), 1)
     opt = optim.SGD(net.parameters(), lr=cfg.LEARNING_RATE, momentum=0.9)
-    T.train_neural_net(game, net, replay, opt, _TB(), 1, device)  # warm-up (cuDNN autotune)
+    bucket = D.FlatGradients(net.parameters())
+    T.train_neural_net(game, net, worker.engine, opt, _TB(), 1, device, bucket)  # warm-up (cuDNN autotune)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    losses = T.train_neural_net(game, net, replay, opt, _TB(), 2, device)
+    losses = T.train_neural_net(game, net, worker.engine, opt, _TB(), 2, device, bucket)
     torch.cuda.synchronize()
     sgd = time.perf_counter() - t1
     n_param = sum(p.numel() for p in net.parameters())
+    tot = torch.tensor([games / sp, stats["leaf_evals"] / sp], dtype=torch.float64, device=device)
+    if ws > 1:
+        dist.all_reduce(tot)
+    out = {"config": 3, "ranks": ws,
+           "workload": "Connect4 training step: %d self-play games per rank at search_batch(%d,%d) played to the end on ONE persistent engine, "
+                       "then %d SGD rounds of %d rows drawn from the device replay rings (all-gather of %d rows per rank, one flattened "
+                       "NCCL all-reduce of %d fp32 gradients per round)" % (games, cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.TRAIN_ROUNDS,
+                                                                         cfg.BATCH_SIZE, cfg.BATCH_SIZE // ws, n_param),
+           "self_play_games_per_sec": float(tot[0]), "self_play_leaf_evals_per_sec": float(tot[1]), "self_play_precision": best.precision,
+           "replay_positions_per_rank": worker.replay_len(), "replay_capacity_per_rank": worker.replay_capacity,
+           "sgd_ms_per_round": 1e3 * sgd / cfg.TRAIN_ROUNDS, "loss_total": losses[0], "gradient_bytes": 4 * n_param}
+    worker.close()
     best.close()
-    return {"config": 3, "workload": "Connect4 training step on one GPU: %d self-play games at search_batch(%d,%d) + %d SGD rounds of %d "
-                                     "(plain PyTorch autograd); with N ranks: one flattened NCCL all-reduce of %d fp32 gradients per round"
-                                     % (games, cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.TRAIN_ROUNDS, cfg.BATCH_SIZE, n_param),
-            "self_play_games_per_sec": games / sp, "self_play_leaf_evals_per_sec": stats["leaf_evals"] / sp,
-            "replay_positions": len(replay), "sgd_ms_per_round": 1e3 * sgd / cfg.TRAIN_ROUNDS, "loss_total": losses[0],
-            "gradient_bytes": 4 * n_param}
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 def config4(games=128, parts=1):
@@ -166,36 +185,43 @@ def config4(games=128, parts=1):
             "tflops_useful": d["leaf_evals"] * 83760340 / sec / 1e12}
 
 
-def config5():
+def config5(n_ckpt=8, rounds=1000):
+    """BASELINE configs[4] at its stated size: 8 checkpoints through the `.dat` format, 56 ordered pairs x 1,000 games,
+    search_batch(40,8), tau = 0, fresh trees per game and side -- through the play.py CLI twin (caro_ai_b200.play.main)."""
+    import contextlib
+    import io
+    from caro_ai_b200 import play as play_cli
     game = ConnectFour()
     tmp = tempfile.mkdtemp()
     paths = []
-    for i in range(4):
+    for i in range(n_ckpt):
         torch.manual_seed(100 + i)
         p = os.path.join(tmp, "net_%d.dat" % i)
         save_checkpoint(Net(game.obs_shape, game.action_space), p)
         paths.append(p)
-    nets = [DeviceNet(load_checkpoint(p, game).eval(), game) for p in paths]
-    rounds = 512
-    table = {}
     torch.cuda.synchronize()
+    out, err = io.StringIO(), io.StringIO()
     t0 = time.perf_counter()
-    total = 0
-    for i, a in enumerate(nets):
-        for j, b in enumerate(nets):
-            if i == j:
-                continue
-            s = play_games_batched(game, rounds, a, b, steps_before_tau_0=0, mcts_searches=cfg.PLAY_MCTS_SEARCHES,
-                                   mcts_batch_size=cfg.PLAY_MCTS_BATCH_SIZE, trees_per_game=2, seed=i * 1000 + j)
-            table["%d-%d" % (i, j)] = [s["wins"], s["losses"], s["draws"]]
-            total += s["games"]
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        play_cli.main(["-g", "0", "-r", str(rounds)] + paths)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    for n in nets:
-        n.close()
-    return {"config": 5, "workload": "tournament: 4 random-init Connect4 checkpoints saved/loaded as .dat, 12 ordered pairs x %d games, "
-                                     "search_batch(40,8), tau=0, two trees per game (play.py semantics), wall clock incl. engine set-up" % rounds,
-            "games_per_sec": total / dt, "games": total, "w_l_d": table}
+    lines = [l for l in out.getvalue().splitlines() if " vs " in l]
+    table, total = {}, 0
+    for l in lines:
+        names, res = l.split(" -> ")
+        a, b = [os.path.basename(x).replace("net_", "").replace(".dat", "") for x in names.split(" vs ")]
+        w, lo, d = [int(x.split("=")[1].rstrip(",")) for x in res.split()]
+        table["%s-%s" % (a, b)] = [w, lo, d]
+        total += w + lo + d
+    assert len(lines) == n_ckpt * (n_ckpt - 1) and total == len(lines) * rounds
+    speeds = [float(l.split()[1]) for l in err.getvalue().splitlines() if l.startswith("Speed")]
+    return {"config": 5, "workload": "tournament: %d random-init Connect4 checkpoints saved/loaded as .dat, %d ordered pairs x %d games, "
+                                     "search_batch(40,8), tau=0, two trees per game (play.py semantics), through caro_ai_b200.play.main; "
+                                     "wall clock incl. checkpoint loading, precision calibration and engine set-up per pair"
+                                     % (n_ckpt, len(lines), rounds),
+            "games_per_sec": total / dt, "games": total, "seconds": dt, "pair_games_per_sec_median": sorted(speeds)[len(speeds) // 2],
+            "leaderboard": out.getvalue().split("Leaderboard:")[1].strip().splitlines(), "w_l_d": table}
 
 
 def main():
@@ -205,7 +231,9 @@ def main():
         if k == 4 and len(sys.argv) > 2:
             print(json.dumps(config4(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 1)), flush=True)
         else:
-            print(json.dumps(fns[k]()), flush=True)
+            res = fns[k]()
+            if res is not None:
+                print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
