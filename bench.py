@@ -7,7 +7,7 @@
 One "step" = one ply of lock-step self-play for every game of the batch: MCTS.search_batch(100, 8)
 (= 800 descents, lib/mcts.py:162-176) on each of the G games, then the policy / sampling / move of
 lib/utils.py:76-99, finished games re-seated immediately.  Workload = BASELINE.json configs[1]:
-Connect4 6x7, 800 sims/move, >= 4096 concurrent games per B200 (default 2 x 4096: two half-batches pipelined
+Connect4 6x7, 800 sims/move, >= 4096 concurrent games per B200 (default 2 x 8192: two half-batches pipelined
 against each other), random-init 5x64 residual network,
 tau = 1 for 10 plies, c_puct 1.0, Dirichlet(0.3) eps 0.25.  Synthetic: no dataset, seeded weights.
 
@@ -28,7 +28,8 @@ if ROOT not in sys.path:
 
 FLOP_PER_LEAF_C4 = 15598672  # conv_in 96,768*... + 5 x 3,096,576*... + heads (2 x MAC)
 SIMS_COUNT, SIMS_BATCH, TAU_PLIES = 100, 8, 10
-GAMES_PER_GPU = 8192  # two software-pipelined half-batches of 4096 (north_star: >= 4096 concurrent games per GPU)
+GAMES_PER_GPU = 16384  # two software-pipelined half-batches of 8192 (north_star: >= 4096 concurrent games per GPU; the line at
+                       # exactly 4096 games is extra.configs.connect4_4096_games)
 NODE_CAPACITY = 24576
 
 
@@ -269,10 +270,10 @@ def extra_configs(torch, rank, seed, small=False):
     from caro_ai_b200.model import DeviceNet, Net
     out = {}
 
-    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note):
+    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, **flags):
         torch.manual_seed(0)
         dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
-        engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h) for h in range(parts)]
+        engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h, **flags) for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=warm, count=count, batch=batch, tau_plies=TAU_PLIES, auto_restart=True)
         torch.cuda.synchronize()
         c0 = [e.counters() for e in engs]
@@ -289,10 +290,16 @@ def extra_configs(torch, rank, seed, small=False):
 
     if small:  # the contract test: the same code on toy sizes
         run("connect4_4096_games", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)")
+        run("connect4_4096_games_virtual_loss", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)",
+            virtual_loss=True, mask_priors=True)
         run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)")
         return out
     run("connect4_4096_games", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 12288, 3, 12,
         "BASELINE configs[1] at exactly 4,096 concurrent games (2 pipeline parts of 2,048), search_batch(100,8)")
+    run("connect4_4096_games_virtual_loss", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 24576, 2, 8,
+        "EXTENSION, not the reference's search (CARO_FLAG_VIRTUAL_LOSS + MASK_PRIORS): 4,096 games, search_batch(100,8); nearly every "
+        "descent reaches the network, so a ply costs ~3x the leaf evaluations of the reference-compatible search",
+        virtual_loss=True, mask_priors=True)
     run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 4,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
         "1,024 concurrent games (2 pipeline parts of 512)")

@@ -57,7 +57,7 @@ _SIGNATURES = {
     "caro_engine_profile": (C.c_int, [_P, C.c_int]),
     "caro_engine_profile_read": (C.c_int, [_P, C.POINTER(C.c_double * 5), C.POINTER(C.c_uint64), _P]),
     "caro_engine_play_multi": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "caro_engine_replay_gather": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
+    "caro_engine_replay_gather": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "caro_engine_counters": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8), _P]),
 }
 

@@ -701,16 +701,16 @@ int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int mov
   return CARO_OK;
 }
 
-int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, int64_t count, float* d_planes, float* d_pi, float* d_z,
-                              void* stream) {
+int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, const int32_t* d_symmetry, int64_t count, float* d_planes,
+                              float* d_pi, float* d_z, void* stream) {
   if (!e || !d_entries || !d_planes || !d_pi || !d_z) return caro_fail(CARO_E_ARG, "null argument");
   if (e->dm.replay_cap <= 0) return caro_fail(CARO_E_STATE, "the engine was created without a replay ring");
   if (count <= 0) return CARO_OK;
   const long long* ent = reinterpret_cast<const long long*>(d_entries);
   if (e->cfg.game == CARO_GAME_CONNECT4)
-    replay_gather_kernel<C4Rules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_c4, C4Rules(), e->dm, ent, (long long)count, d_planes, d_pi, d_z);
+    replay_gather_kernel<C4Rules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_c4, C4Rules(), e->dm, ent, d_symmetry, (long long)count, d_planes, d_pi, d_z);
   else
-    replay_gather_kernel<MnkRules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, ent, (long long)count, d_planes, d_pi, d_z);
+    replay_gather_kernel<MnkRules><<<(unsigned)count, 64, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, ent, d_symmetry, (long long)count, d_planes, d_pi, d_z);
   return caro_check_launch("replay_gather_kernel");
 }
 

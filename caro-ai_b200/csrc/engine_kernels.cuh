@@ -993,21 +993,42 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
 // planes (game.states_to_training_batch of the stored position, from the side to move's point of view), the MCTS
 // policy target and the outcome z.  `entry[i]` = absolute number of the sampled ring entry (slot = entry % capacity;
 // the host draws the numbers with random.sample, like the reference).  One block per sample.
+// `sym` (extension, nullptr = off; not in the reference): symmetry augmentation -- sample i is written through the board
+// symmetry sym[i]: bit 0 mirrors the columns (the only symmetry of Connect4), bit 1 mirrors the rows, bit 2 transposes
+// (square boards: the eight dihedral symmetries); planes and policy target are transformed together, z is invariant.
 template <class R>
 __global__ void __launch_bounds__(64)
-replay_gather_kernel(View<typename R::Board> e, R rules, Dims dm, const long long* __restrict__ entry, long long count,
-                     float* __restrict__ planes, float* __restrict__ pi, float* __restrict__ z) {
+replay_gather_kernel(View<typename R::Board> e, R rules, Dims dm, const long long* __restrict__ entry, const int32_t* __restrict__ sym,
+                     long long count, float* __restrict__ planes, float* __restrict__ pi, float* __restrict__ z) {
   const long long i = blockIdx.x;
   if (i >= count) return;
   const size_t slot = (size_t)(entry[i] % (long long)dm.replay_cap);
   const typename R::Board s = e.rp_board[slot];
   const int who = e.rp_player[slot];
   const int H = rules.rows(), W = rules.cols(), HW = H * W;
-  for (int t = threadIdx.x; t < 2 * HW; t += blockDim.x) {
-    const int plane = t / HW, cell = t - plane * HW;
-    planes[(size_t)i * 2 * HW + t] = (float)rules.plane_value(s, who, plane, cell / W, cell % W);
+  const int t = sym ? sym[i] : 0;
+  auto source_cell = [&](int r, int c, int* sr, int* sc) {  // output cell (r, c) shows source cell (sr, sc)
+    if (t & 4) { const int x = r; r = c; c = x; }
+    *sr = (t & 2) ? H - 1 - r : r;
+    *sc = (t & 1) ? W - 1 - c : c;
+  };
+  for (int o = threadIdx.x; o < 2 * HW; o += blockDim.x) {
+    const int plane = o / HW, cell = o - plane * HW;
+    int sr, sc;
+    source_cell(cell / W, cell % W, &sr, &sc);
+    planes[(size_t)i * 2 * HW + o] = (float)rules.plane_value(s, who, plane, sr, sc);
   }
-  for (int a = threadIdx.x; a < dm.A; a += blockDim.x) pi[(size_t)i * dm.A + a] = e.rp_pi[slot * dm.A + a];
+  for (int a = threadIdx.x; a < dm.A; a += blockDim.x) {
+    int src = a;
+    if (dm.A == W) {  // column actions (Connect4)
+      src = (t & 1) ? W - 1 - a : a;
+    } else {          // cell actions, row-major (m,n,k)
+      int sr, sc;
+      source_cell(a / W, a % W, &sr, &sc);
+      src = sr * W + sc;
+    }
+    pi[(size_t)i * dm.A + a] = e.rp_pi[slot * dm.A + src];
+  }
   if (threadIdx.x == 0) z[i] = e.rp_z[slot];
 }
 

@@ -302,10 +302,12 @@ class SelfPlayEngine:
         """Entries currently held by the ring = ``len(replay_buffer)`` of train.py:199."""
         return min(self.replay_cursor(), max(0, self.cfg.replay_capacity))
 
-    def replay_sample(self, count: int, rng=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def replay_sample(self, count: int, rng=None, augment: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """train.py:85-94 without the host round trip: ``random.sample`` draws ``count`` of the live ring entries (the
         reference's sampler, on the entry NUMBERS only), the CUDA gather kernel turns them into the SGD tensors
-        (planes float32 [count,2,H,W], pi float32 [count,A], z float32 [count]) straight from the ring."""
+        (planes float32 [count,2,H,W], pi float32 [count,A], z float32 [count]) straight from the ring.
+        ``augment`` (extension, the reference has none): every row goes through a random board symmetry (Connect4: column
+        mirror; square m,n,k boards: the eight dihedral symmetries), planes and policy target together."""
         import random as _random
         rng = rng or _random
         cursor = self.replay_cursor()
@@ -313,12 +315,17 @@ class SelfPlayEngine:
         assert count <= live, "sample larger than the replay ring's content"
         picks = rng.sample(range(live), count)
         entries = torch.tensor([cursor - live + i for i in picks], dtype=torch.int64).to(self.device, non_blocking=True)
+        sym = None
+        if augment:
+            n_sym = 2 if self.game.game_kind == _cabi.GAME_CONNECT4 else 8
+            sym = torch.tensor([rng.randrange(n_sym) for _ in range(count)], dtype=torch.int32).to(self.device, non_blocking=True)
         _, h, w = self.game.obs_shape
         planes = torch.empty((count, 2, h, w), dtype=torch.float32, device=self.device)
         pi = torch.empty((count, self.A), dtype=torch.float32, device=self.device)
         z = torch.empty((count,), dtype=torch.float32, device=self.device)
-        _cabi.check(_cabi.lib().caro_engine_replay_gather(self.handle, entries.data_ptr(), count, planes.data_ptr(),
-                                                          pi.data_ptr(), z.data_ptr(), self._stream()))
+        _cabi.check(_cabi.lib().caro_engine_replay_gather(self.handle, entries.data_ptr(), sym.data_ptr() if sym is not None else None,
+                                                          count, planes.data_ptr(), pi.data_ptr(), z.data_ptr(), self._stream()))
+        self._last_symmetry = sym
         return planes, pi, z
 
     def replay_load(self, entries) -> None:

@@ -70,12 +70,12 @@ def sgd_losses(net: Net, planes: torch.Tensor, probs: torch.Tensor, values: torc
     return loss_policy + loss_value, loss_value, loss_policy
 
 
-def sample_batch(game, source, count: int, device):
+def sample_batch(game, source, count: int, device, augment: bool = False):
     """train.py:85-94: ``count`` random replay rows as (planes, probs, values) tensors on ``device``.
     ``source`` is a ``SelfPlayEngine`` (device ring: the rows never visit the host) or a reference-style deque of
     (state, player, probs, z) tuples (host path: states -> device boards -> CUDA plane encoder)."""
     if hasattr(source, "replay_sample"):
-        return source.replay_sample(count, random)
+        return source.replay_sample(count, random, augment=augment)
     batch = random.sample(source, count)
     states, who, probs, values = zip(*batch)
     d_boards = torch.from_numpy(game.boards_from_states(states).view("int64")).to(device)
@@ -84,22 +84,24 @@ def sample_batch(game, source, count: int, device):
             torch.tensor(values, dtype=torch.float32, device=device))
 
 
-def train_neural_net(game, net: Net, source, optimizer, tb, step_idx: int, device, bucket=None, exchange: str = "gather"):
+def train_neural_net(game, net: Net, source, optimizer, tb, step_idx: int, device, bucket=None, exchange: str = "gather",
+                     augment: bool = False):
     """train.py:62-117.  ``source``: the self-play engine (device replay ring) or a deque of reference tuples.
     ``bucket``: a ``distributed.FlatGradients`` over the net's parameters (one all-reduce per round, no flatten /
     scatter); without it the gradients are flattened per round (``allreduce_gradients``).
     ``exchange`` (several ranks): "gather" = every rank draws BATCH_SIZE / world rows and the step's batch is their
     all-gather (the reference's batch size, BatchNorm statistics over all 256 rows); "local" = every rank trains on
-    BATCH_SIZE rows of its own ring and only the gradients are exchanged (data parallel, world x the batch)."""
+    BATCH_SIZE rows of its own ring and only the gradients are exchanged (data parallel, world x the batch).
+    ``augment`` (extension, default off): random board symmetries on the sampled rows (device ring only)."""
     _, ws = D.world()
     sums = torch.zeros(3, dtype=torch.float64, device=device)
     net.train()
     gather = exchange == "gather" and ws > 1 and cfg.BATCH_SIZE % ws == 0
     for _ in range(cfg.TRAIN_ROUNDS):
         if gather:
-            planes, probs, values = D.all_gather_rows(sample_batch(game, source, cfg.BATCH_SIZE // ws, device))
+            planes, probs, values = D.all_gather_rows(sample_batch(game, source, cfg.BATCH_SIZE // ws, device, augment))
         else:
-            planes, probs, values = sample_batch(game, source, cfg.BATCH_SIZE, device)
+            planes, probs, values = sample_batch(game, source, cfg.BATCH_SIZE, device, augment)
         if bucket is not None:
             bucket.zero()
         else:
@@ -146,6 +148,7 @@ def parse_args(argv=None):
     p.add_argument("--replay-steps", type=int, default=4, help="device replay ring = this many steps of --games games (>= REPLAY_BUFFER)")
     p.add_argument("--replay-exchange", default="gather", choices=["gather", "local"],
                    help="several ranks: all-gather BATCH_SIZE/world rows per rank (default) or train on local rows only")
+    p.add_argument("--augment", action="store_true", help="extension: random board symmetries on the sampled replay rows")
     p.add_argument("--evaluate-every", type=int, default=cfg.EVALUATE_EVERY_STEP, help="arena evaluation period in steps")
     return p.parse_args(argv)
 
@@ -188,7 +191,8 @@ def main(argv=None):
             need = max(cfg.MIN_REPLAY_TO_TRAIN, cfg.BATCH_SIZE)
             if D.all_min(replay_len, device=device) < need:
                 continue
-            train_neural_net(game, net, worker.engine, optimizer, tb, step_idx, device, bucket, exchange=args.replay_exchange)
+            train_neural_net(game, net, worker.engine, optimizer, tb, step_idx, device, bucket, exchange=args.replay_exchange,
+                             augment=args.augment)
             if step_idx % args.evaluate_every == 0:
                 D.broadcast_state_dict(net)  # every rank's arena games are played by the same challenger (BN buffers included)
                 win_ratio = evaluate(game, net, best_dev, cfg.EVALUATION_ROUNDS, seed=step_idx, device=device)

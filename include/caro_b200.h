@@ -248,9 +248,12 @@ int caro_engine_play_multi(caro_engine** engines, int n, caro_net* net, int move
  * device: `d_entries` int64 [count] are absolute entry numbers of the replay ring (entry k lives in slot k % replay_capacity;
  * valid numbers are [cursor - min(cursor, capacity), cursor), "replay_cursor" region); the rows are written as
  * d_planes float32 [count][2][H][W] (from the stored side to move's point of view), d_pi float32 [count][A] and
- * d_z float32 [count] (lib/utils.py:101-106) without a host round trip. */
-int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, int64_t count, float* d_planes, float* d_pi,
-                              float* d_z, void* stream);
+ * d_z float32 [count] (lib/utils.py:101-106) without a host round trip.
+ * d_symmetry (extension, NULL = off; the reference has no augmentation): int32 [count], sample i is written through the
+ * board symmetry d_symmetry[i] -- bit 0 mirrors the columns (Connect4: 0..1), bit 1 the rows, bit 2 transposes (square
+ * m,n,k boards: 0..7); planes and policy target are transformed together. */
+int caro_engine_replay_gather(caro_engine* e, const int64_t* d_entries, const int32_t* d_symmetry, int64_t count,
+                              float* d_planes, float* d_pi, float* d_z, void* stream);
 
 /* Optional per-phase timing of caro_engine_search with CUDA events on the launching stream.
  * profile_read synchronises `stream` and returns the summed milliseconds of

@@ -451,6 +451,47 @@ def test_replay_gather_and_train_step_match_the_reference(torch_cuda, golden_tra
         eng.close()
 
 
+def test_replay_symmetry_augmentation(torch_cuda, golden_train):
+    """`replay_sample(augment=True)` (extension; the reference has no augmentation): every sampled row is written through a
+    random board symmetry -- Connect4: column mirror; 3 x 3: the eight dihedral symmetries -- planes AND policy target
+    transformed together, z untouched; checked against the same transforms applied on the host to the un-augmented rows."""
+    torch = torch_cuda
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    for case in golden_train:
+        game = ConnectFour() if case["game"] == "connect4" else TicTacToe(3, 3)
+        _, H, W = game.obs_shape
+        A = game.action_space
+        eng = SelfPlayEngine(game, 4, max_batch=8, node_capacity=64, replay_capacity=1024, seed=1)
+        eng.replay_load([(s, p, pi, z) for s, p, pi, z in case["replay"]])
+        random.seed(5)
+        p0, pi0, z0 = (t.cpu().numpy() for t in eng.replay_sample(200, random))
+        random.seed(5)
+        p1, pi1, z1 = (t.cpu().numpy() for t in eng.replay_sample(200, random, augment=True))
+        sym = eng._last_symmetry.cpu().numpy()
+        assert set(sym.tolist()) == set(range(2 if A == W else 8))
+        np.testing.assert_array_equal(z0, z1)
+
+        def src(t, r, c):
+            if t & 4:
+                r, c = c, r
+            return (H - 1 - r if t & 2 else r), (W - 1 - c if t & 1 else c)
+        for i in range(200):
+            t = int(sym[i])
+            want = np.zeros_like(p0[i])
+            for r in range(H):
+                for c in range(W):
+                    sr, sc = src(t, r, c)
+                    want[:, r, c] = p0[i][:, sr, sc]
+            np.testing.assert_array_equal(p1[i], want)
+            if A == W:
+                want_pi = pi0[i][::-1] if t & 1 else pi0[i]
+            else:
+                want_pi = np.array([pi0[i][src(t, a // W, a % W)[0] * W + src(t, a // W, a % W)[1]] for a in range(A)], dtype=np.float32)
+            np.testing.assert_array_equal(pi1[i], want_pi)
+        eng.close()
+
+
 def test_selfplay_worker_keeps_one_engine_and_a_ring_of_several_steps(torch_cuda):
     """The trainer's self-play side: the same engine (same workspace pointer) serves every step, every step plays
     `games` fresh games to the end, the ring keeps the positions of the last `replay_steps` steps (nothing of the current
