@@ -262,28 +262,40 @@ def extra_train(torch, dist, game, ring_engine, world, rank, rounds=20):
     return out
 
 
-def extra_configs(torch, rank, seed, small=False):
-    """Short, honestly sized runs of the other BASELINE.json configurations on THIS rank's GPU (every number below is
-    measured by CUDA events around the plies named in `plies`; nothing is scaled or extrapolated)."""
+def extra_configs(torch, dist, world, rank, seed, small=False):
+    """Short, honestly sized runs of the other BASELINE.json configurations.  EVERY rank runs them on its own GPU (games
+    shard by rank, no collective on the data path) and the per-rank rates are summed: at N GPUs the entries are the
+    aggregate of N x the stated per-GPU workload (weak scaling).  Every number is measured by CUDA events around the plies
+    named in `plies` (max over ranks); nothing is scaled or extrapolated."""
     from caro_ai_b200.engine import SelfPlayEngine
     from caro_ai_b200.game import ConnectFour, TicTacToe
     from caro_ai_b200.model import DeviceNet, Net
     out = {}
 
-    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, **flags):
+    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, blocks=5, **flags):
         torch.manual_seed(0)
-        dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
-        engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h, **flags) for h in range(parts)]
+        dn = DeviceNet(Net(game.obs_shape, game.action_space, blocks=blocks).eval(), game)
+        engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h + 101 * rank, **flags)
+                for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=warm, count=count, batch=batch, tau_plies=TAU_PLIES, auto_restart=True)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         c0 = [e.counters() for e in engs]
         ms = _cuda_ms(torch, lambda: SelfPlayEngine.play_multi(engs, dn, moves=plies, count=count, batch=batch, tau_plies=TAU_PLIES,
                                                                 auto_restart=True))
         c1 = [e.counters() for e in engs]
         d = {k: sum(b[k] - a[k] for a, b in zip(c0, c1)) for k in c1[0]}
-        out[tag] = {"workload": note, "games": parts * games_per_part, "parts": parts, "plies": plies, "warmup_plies": warm,
-                    "ms_per_ply": ms / plies, "leaf_evals_per_sec": d["leaf_evals"] / (ms / 1e3), "descents_per_sec": d["descents"] / (ms / 1e3),
-                    "plies_per_sec": d["plies"] / (ms / 1e3), "precision": dn.precision, "errors": sum(c["errors"] for c in c1)}
+        tot = torch.tensor([d["leaf_evals"], d["descents"], d["plies"], sum(c["errors"] for c in c1)], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sec = float(tmax[0]) / 1e3
+        out[tag] = {"workload": note, "gpus": world, "games_per_gpu": parts * games_per_part, "parts": parts, "plies": plies,
+                    "warmup_plies": warm, "ms_per_ply": 1e3 * sec / plies, "leaf_evals_per_sec": float(tot[0]) / sec,
+                    "descents_per_sec": float(tot[1]) / sec, "plies_per_sec": float(tot[2]) / sec, "precision": dn.precision,
+                    "residual_blocks": blocks, "errors": int(tot[3])}
         for e in engs:
             e.close()
         dn.close()
@@ -293,16 +305,20 @@ def extra_configs(torch, rank, seed, small=False):
         run("connect4_4096_games_virtual_loss", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)",
             virtual_loss=True, mask_priors=True)
         run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)")
+        run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)", blocks=10)
         return out
     run("connect4_4096_games", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 12288, 3, 12,
-        "BASELINE configs[1] at exactly 4,096 concurrent games (2 pipeline parts of 2,048), search_batch(100,8)")
+        "BASELINE configs[1] at exactly 4,096 concurrent games per GPU (2 pipeline parts of 2,048), search_batch(100,8)")
     run("connect4_4096_games_virtual_loss", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 24576, 2, 8,
-        "EXTENSION, not the reference's search (CARO_FLAG_VIRTUAL_LOSS + MASK_PRIORS): 4,096 games, search_batch(100,8); nearly every "
-        "descent reaches the network, so a ply costs ~3x the leaf evaluations of the reference-compatible search",
+        "EXTENSION, not the reference's search (CARO_FLAG_VIRTUAL_LOSS + MASK_PRIORS): 4,096 games per GPU, search_batch(100,8); nearly "
+        "every descent reaches the network, so a ply costs ~3x the leaf evaluations of the reference-compatible search",
         virtual_loss=True, mask_priors=True)
     run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 4,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
-        "1,024 concurrent games (2 pipeline parts of 512)")
+        "1,024 concurrent games per GPU (2 pipeline parts of 512)")
+    run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 3,
+        "the same with the 'deep residual net' BASELINE configs[3] names and the reference does not define: here 10 residual blocks "
+        "of 64 filters (Net(blocks=10); 166.7 MFLOP per leaf)", blocks=10)
     return out
 
 
@@ -429,15 +445,11 @@ def engine_arm(args):
     extra = {}
     if not args.no_extra:
         extra["train"] = extra_train(torch, dist, game, engs[0], world, rank)
-        for e in engs[1:]:
+        for e in engs:
             e.close()
-        if rank == 0:  # the other configurations are per-GPU workloads: one rank measures them
-            del engs[1:]
-            engs[0].close()
-            torch.cuda.empty_cache()
-            extra["configs"] = extra_configs(torch, rank, 4321, small=args.extra_small)
-        if world > 1:
-            dist.barrier()
+        del engs[:]
+        torch.cuda.empty_cache()
+        extra["configs"] = extra_configs(torch, dist, world, rank, 4321, small=args.extra_small)
 
     def allmax(x):
         if world == 1:

@@ -199,7 +199,9 @@ int launch_select(const View<Board>& v, const R& rules, const Dims& dm, const Se
     cudaMemcpyAsync(noise_out, noise, sizeof(double) * (size_t)groups * A, cudaMemcpyDeviceToDevice, st);
   }
   if (dm.flags & FLAG_VIRTUAL_LOSS) {  // extension: sequential descents per game with virtual loss (one thread per game)
-    select_vl_kernel<R><<<(unsigned)((dm.G + 63) / 64), 64, 0, st>>>(v, rules, dm, sp, batch, src);
+    static const bool vl_group = !(getenv("CARO_VL_GROUP") && atoi(getenv("CARO_VL_GROUP")) == 0);
+    if (A <= 8 && vl_group) select_vl_group_kernel<R><<<(unsigned)(((long long)dm.G * 8 + 255) / 256), 256, 0, st>>>(v, rules, dm, sp, batch, src);
+    else select_vl_kernel<R><<<(unsigned)((dm.G + 63) / 64), 64, 0, st>>>(v, rules, dm, sp, batch, src);
     return caro_check_launch("select_vl_kernel");
   }
 #define SELECT(GW, APL) select_kernel<R, GW, APL><<<grid(GW), 256, 0, st>>>(v, rules, dm, sp, batch, src)

@@ -549,6 +549,122 @@ select_vl_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, i
   }
 }
 
+// The same search with eight lanes per game (A <= 8: Connect4), lane = action: the descents of a game are still made one after
+// the other (that is what virtual loss means), but every level of a descent is one coalesced 128-byte record load and a
+// three-step shuffle argmax instead of a serial loop over the actions, and eight times as many warps are in flight -- the
+// one-thread-per-game kernel left 64 warps per 8,192 games, and IT, not the tower, set the pace of the extension mode.
+// Identical choices to select_vl_kernel (same arithmetic per action, first maximum = lowest action).
+template <class R>
+__global__ void __launch_bounds__(256)
+select_vl_group_kernel(View<typename R::Board> e, R rules, Dims dm, SearchParams sp, int batch, const double* __restrict__ noise_in) {
+  using Board = typename R::Board;
+  constexpr int GW = 8;
+  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gthread == 0) *e.leaf_count = 0;
+  const int g = gthread / GW;
+  if (g >= dm.G) return;  // whole groups leave together (blockDim is a multiple of GW)
+  const int gl = threadIdx.x & (GW - 1);
+  const unsigned gmask = group_mask<GW>();
+  const int gbase = (threadIdx.x & 31) & ~(GW - 1);
+  const size_t d0 = (size_t)g * dm.B;
+  if (e.status[g] != ST_ACTIVE) {
+    for (int j = gl; j < batch; j += GW) store_desc_skip(e.desc + d0 + j);
+    return;
+  }
+  const int A = dm.A;
+  const Board root = e.root_board[g];
+  const int root_who = e.root_player[g];
+  const int tree = g * dm.tpg + (dm.tpg == 2 ? root_who : 0);
+  const uint32_t gen = e.tree_gen[tree];
+  const HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const uint64_t* khi = RulesTraits<R>::kHasKeyHi ? (e.key_hi + nb) : nullptr;
+  const float c_f = (float)sp.c_puct;
+  const float keep_f = (float)(1.0 - sp.explore);
+  const int root_node = ht_lookup<GW>(ht, dm.hash_cap, gen, rules.key(root), khi, gl, gmask);
+  const bool mine = gl < A;
+  int len_reg = 0;  // lane i keeps the path length of descent i (batch <= 8) -- descents 8.. are looked up in the records
+  for (int j = 0; j < batch; ++j) {
+    Board s = root;
+    int who = root_who;
+    Key128 key = rules.key(s);
+    int node = root_node, depth = 0, kind = KIND_EXPAND;
+    float term_value = 0.0f;
+    uint32_t* path = e.d_path + (d0 + j) * dm.max_depth;
+    while (node >= 0) {
+      const size_t row = (nb + (size_t)node) * dm.RS;
+      // virtual visits of MY edge: earlier descents of this minibatch that went through (node, action = lane)
+      int k = 0;
+      for (int i = 0; i < j; ++i) {
+        const int len_i = i < GW ? __shfl_sync(gmask, len_reg, gbase + i) : (int)e.desc[d0 + i].h.len;
+        if (len_i > depth) {
+          const uint32_t pe = e.d_path[(d0 + i) * dm.max_depth + depth];
+          if ((int)(pe >> 8) == node) k += ((int)(pe & 0xffu) == gl) ? 1 : 0;
+        }
+      }
+      int n = 0, c_link = -1;
+      float w = 0.0f, p = 0.0f;
+      if (mine) {
+        n = (e.N[row + gl] & kCountMask) + k;
+        w = e.W[row + gl] - (float)k;
+        p = e.P[row + gl];
+        c_link = e.C[row + gl];
+      }
+      int sum_n = mine ? n : 0;
+#pragma unroll
+      for (int off = GW / 2; off > 0; off >>= 1) sum_n += __shfl_xor_sync(gmask, sum_n, off);
+      double sc = -INFINITY;
+      if (mine && rules.legal(s, gl)) {
+        if (depth == 0) {
+          const double z = noise_in[((size_t)g * batch + j) * A + gl];
+          const double pn = __dadd_rn((double)__fmul_rn(keep_f, p), __dmul_rn(sp.explore, z));
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(sp.c_puct, pn), sqrt((double)sum_n)), (double)(1 + n));
+          sc = __dadd_rn(n > 0 ? (double)__fdiv_rn(w, (float)n) : 0.0, u);
+        } else {
+          const float t = __fdiv_rn(__fmul_rn(__fmul_rn(c_f, p), __fsqrt_rn((float)sum_n)), (float)(1 + n));
+          sc = (double)__fadd_rn(n > 0 ? __fdiv_rn(w, (float)n) : 0.0f, t);
+        }
+      }
+      int best_a = gl;
+#pragma unroll
+      for (int off = GW / 2; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(gmask, sc, off);
+        const int oa = __shfl_xor_sync(gmask, best_a, off);
+        if (ob > sc || (ob == sc && oa < best_a)) {
+          sc = ob;
+          best_a = oa;
+        }
+      }
+      const int a = best_a;
+      if (gl == 0) path[depth] = ((uint32_t)node << 8) | (uint32_t)a;
+      ++depth;
+      const bool won = rules.apply(s, a, who);
+      who ^= 1;
+      if (won) {
+        kind = KIND_TERMINAL;
+        term_value = -1.0f;
+        break;
+      }
+      if (!rules.any_legal(s)) {
+        kind = KIND_TERMINAL;
+        term_value = 0.0f;
+        break;
+      }
+      key = rules.key(s);
+      const int linked = __shfl_sync(gmask, c_link, gbase + a);
+      if (linked >= 0) {
+        node = linked;
+      } else {
+        node = ht_lookup<GW>(ht, dm.hash_cap, gen, key, khi, gl, gmask);
+        if (node >= 0 && gl == 0) e.C[row + a] = node;
+      }
+    }
+    if (gl == (j & (GW - 1)) && j < GW) len_reg = depth;
+    if (gl == 0) store_desc(e.desc + d0 + j, kind, who, depth, term_value, key, s);
+    __syncwarp(gmask);  // the path and the record of this descent are read by the whole group from the next descent on
+  }
+}
+
 // ------------------------------------------------------------------------------------ plan
 // Back-up queue = terminal descents in descent order, then the first occurrence of every distinct new leaf
 // (lib/mcts.py:265-278); unique leaves are appended to the compact batch (order across games is arbitrary; results do

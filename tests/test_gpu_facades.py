@@ -348,7 +348,7 @@ def test_bench_engine_arm_prints_the_contract_line():
     assert d["net_precision"]["selected"] == "bf16" and d["net_precision"]["calibration"]["max_abs_prior_diff"] < 1e-3
     tr = d["extra"]["train"]
     assert tr["rounds"] == 20 and tr["sgd_ms_per_round"] > 0 and tr["gradient_bytes"] == 188301 * 4 and tr["allreduce_us"] is None
-    for tag in ("connect4_4096_games", "caro_15x15_1600_sims"):
+    for tag in ("connect4_4096_games", "connect4_4096_games_virtual_loss", "caro_15x15_1600_sims", "caro_15x15_1600_sims_deep10"):
         assert d["extra"]["configs"][tag]["leaf_evals_per_sec"] > 0 and d["extra"]["configs"][tag]["errors"] == 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and 0 < r["frac"] < 1.5 and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9

@@ -724,6 +724,17 @@ def test_virtual_loss_spreads_descents_and_keeps_strength(torch_cuda):
         eng.close()
     assert frac[False] < 0.7 and frac[True] >= 0.9 and frac[True] > 1.4 * frac[False], frac
     dn.close()
+    # the eight-lanes-per-game kernel (default for A <= 8) makes exactly the choices of the one-thread-per-game kernel
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for mode in ("1", "0"):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "vl_digest.py")], capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, CARO_VL_GROUP=mode), cwd=root)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0].replace("hash", ""))
+    assert digests[0] == digests[1], digests
     trained = DeviceNet(load_checkpoint(os.path.join(GOLDEN, "checkpoints", "connect4_best_026_12000.dat"), game).eval(), game)
     vl_mode, ref_mode = {"virtual_loss": True, "count": 10}, {"virtual_loss": False, "count": 40}
     p1, g1, ev_vl1, ev_ref1 = _match(torch, game, trained, vl_mode, ref_mode, 1024, True, 100)
