@@ -165,7 +165,7 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
   dm->max_plies = plies;
   dm->replay_cap = cfg->replay_capacity;
   dm->flags = cfg->flags;
-  if (cfg->flags & ~7u) return caro_fail(CARO_E_ARG, "unknown engine flags");
+  if (cfg->flags & ~15u) return caro_fail(CARO_E_ARG, "unknown engine flags");
   *max_plies = plies;
   return CARO_OK;
 }

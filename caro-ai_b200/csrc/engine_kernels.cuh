@@ -1053,8 +1053,13 @@ __global__ void advance_kernel(View<typename R::Board> e, R rules, Dims dm, Sear
     e.root_board[g] = s;
     e.root_player[g] = (uint8_t)(who ^ 1);
     e.ply[g] = ply + 1;
-    if (dm.flags & FLAG_FRESH_TREE) {  // extension: no tree reuse between moves -- arena demand bounded by one move's searches
-      for (int t = 0; t < dm.tpg; ++t) {
+    // extensions: FRESH_TREE = no tree reuse between moves (arena demand bounded by one move's searches); RECYCLE_TREE = the tree
+    // is kept from move to move, like the reference's, until it fills more than half of its arena, then cleared (never overflows
+    // while one move's searches fit half an arena; most moves still start from the previous move's subtree)
+    for (int t = 0; t < dm.tpg; ++t) {
+      const bool clear = (dm.flags & FLAG_FRESH_TREE) ||
+                         ((dm.flags & FLAG_RECYCLE_TREE) && e.node_count[g * dm.tpg + t] > dm.node_cap / 2);
+      if (clear) {
         e.node_count[g * dm.tpg + t] = 0;
         e.tree_gen[g * dm.tpg + t] += 1u;
       }

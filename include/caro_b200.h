@@ -159,8 +159,11 @@ typedef struct {
  *                  (the reference keeps the raw softmax and masks only the PUCT score, lib/mcts.py:86-95).
  *   FRESH_TREE     a game's tree is cleared after each of its moves instead of being kept for the whole game
  *                  (lib/utils.py:58-59 keeps it): arena demand is bounded by the searches of ONE move, which is what
- *                  long 15 x 15 games at 1,600 descents per move need. */
-enum { CARO_FLAG_VIRTUAL_LOSS = 1, CARO_FLAG_MASK_PRIORS = 2, CARO_FLAG_FRESH_TREE = 4 };
+ *                  long 15 x 15 games at 1,600 descents per move need.
+ *   RECYCLE_TREE   the tree is kept from move to move until it fills more than half of its arena and is cleared then: no
+ *                  overflow while one move's searches fit half an arena, and most moves still reuse the previous subtree
+ *                  (stands in for re-rooting / compaction, which is not built). */
+enum { CARO_FLAG_VIRTUAL_LOSS = 1, CARO_FLAG_MASK_PRIORS = 2, CARO_FLAG_FRESH_TREE = 4, CARO_FLAG_RECYCLE_TREE = 8 };
 
 /* Bytes of device workspace the engine needs; the caller allocates it (e.g. a torch uint8 CUDA
  * tensor) and keeps it alive for the life of the handle. */

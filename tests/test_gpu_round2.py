@@ -750,7 +750,9 @@ def test_virtual_loss_spreads_descents_and_keeps_strength(torch_cuda):
 def test_masked_priors_and_fresh_tree_flags(torch_cuda):
     """CARO_FLAG_MASK_PRIORS: every node's priors vanish on illegal moves and sum to one (the reference keeps the raw
     softmax).  CARO_FLAG_FRESH_TREE: a game's arena is emptied after each of its moves, so a capacity of ONE move's searches
-    carries a game of any length (here 15 x 15 with a 2,048-node arena over 12 plies of 200 descents: no arena-full bit)."""
+    carries a game of any length (here 15 x 15 with a 2,048-node arena over 12 plies of 200 descents: no arena-full bit);
+    CARO_FLAG_RECYCLE_TREE keeps the tree until it fills half the arena (reuse on most moves, still no overflow); with neither
+    the persistent tree overflows this arena."""
     torch = torch_cuda
     from caro_ai_b200.engine import SelfPlayEngine
     from caro_ai_b200.game import ConnectFour, TicTacToe
@@ -774,12 +776,17 @@ def test_masked_priors_and_fresh_tree_flags(torch_cuda):
     caro = TicTacToe(15, 5)
     torch.manual_seed(0)
     dc = DeviceNet(Net(caro.obs_shape, caro.action_space).eval(), caro, precision="bf16")
-    for fresh in (True, False):
-        eng = SelfPlayEngine(caro, 32, max_batch=8, node_capacity=2048, seed=3, fresh_tree=fresh)
-        eng.play(dc, dc, moves=12, count=25, batch=8, tau_plies=10, auto_restart=True)
+    for mode in ("fresh", "recycle", "keep"):
+        eng = SelfPlayEngine(caro, 32, max_batch=8, node_capacity=2048, seed=3, fresh_tree=mode == "fresh", recycle_tree=mode == "recycle")
+        reused = 0
+        for ply in range(12):
+            eng.play(dc, dc, moves=1, count=25, batch=8, tau_plies=10, auto_restart=True)
+            reused += int((eng.region("node_count") > 0).sum().item())
         c = eng.counters()
-        assert bool(c["errors"] & 1) == (not fresh), (fresh, c)
-        if fresh:
-            assert int(eng.region("node_count").max().item()) == 0  # emptied by the last advance
+        assert bool(c["errors"] & 1) == (mode == "keep"), (mode, c)
+        if mode == "fresh":
+            assert reused == 0  # emptied by every advance
+        if mode == "recycle":  # kept most of the time, never more than half an arena + one move's searches
+            assert reused > 32 * 6 and int(eng.region("node_count").max().item()) <= 1024
         eng.close()
     dc.close()
