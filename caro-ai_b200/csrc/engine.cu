@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -252,7 +253,7 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
   if (rc != CARO_OK) return rc;
   const size_t need = caro_engine_workspace_bytes(cfg);
   if (bytes < need) return caro_fail(CARO_E_ARG, "workspace too small");
-  static unsigned long long next_serial = 0;
+  static std::atomic<unsigned long long> next_serial{0};
   caro_engine* e = new caro_engine();
   e->serial = ++next_serial;
   e->cfg = *cfg;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <atomic>
+
 #include "../../include/caro_b200.h"
 #include "common_host.h"
 #include "net.h"
@@ -152,6 +154,9 @@ int caro_net_update(caro_net* net, const float* h_blob, size_t n_floats) {
   if (n_floats != net->layout.total) return caro_fail(CARO_E_ARG, "weight blob has the wrong size");
   caro_pipeline_forget(0, net->serial);  // a captured ply holds the previous constants by value
   net->version += 1;
+  // the weight images are rewritten in place: searches that are still running on the pipeline's non-blocking streams must
+  // have finished with the old ones (an update is rare: NetWrapper.sync after a promotion)
+  if (cudaDeviceSynchronize() != cudaSuccess) return caro_fail(CARO_E_CUDA, "device error before the weight update");
   cudaError_t ce = cudaMemcpy(net->d_blob, h_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   const int rc = caro_net_tc_pack(net, h_blob);
@@ -165,7 +170,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   if (!out || !h_blob) return caro_fail(CARO_E_ARG, "null argument");
   if (rows < 2 || cols < 2 || rows > 15 || cols > 15 || actions < 1 || actions > 255) return caro_fail(CARO_E_ARG, "bad net shape");
   if (caro_device_count() <= 0) return caro_fail(CARO_E_CUDA, "no CUDA device: the network has no CPU fallback");
-  static unsigned long long next_serial = 0;
+  static std::atomic<unsigned long long> next_serial{0};
   caro_net* net = new caro_net();
   net->serial = ++next_serial;
   net->version = 0;
