@@ -313,10 +313,10 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
         "EXTENSION, not the reference's search (CARO_FLAG_VIRTUAL_LOSS + MASK_PRIORS): 4,096 games per GPU, search_batch(100,8); nearly "
         "every descent reaches the network, so a ply costs ~3x the leaf evaluations of the reference-compatible search",
         virtual_loss=True, mask_priors=True)
-    run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 4,
+    run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 3,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
-        "1,024 concurrent games per GPU (2 pipeline parts of 512)")
-    run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 512, 200, 8, 8192, 1, 3,
+        "2,048 concurrent games per GPU (2 pipeline parts of 1,024)")
+    run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 2,
         "the same with the 'deep residual net' BASELINE configs[3] names and the reference does not define: here 10 residual blocks "
         "of 64 filters (Net(blocks=10); 166.7 MFLOP per leaf)", blocks=10)
     return out
