@@ -522,6 +522,33 @@ def test_selfplay_worker_keeps_one_engine_and_a_ring_of_several_steps(torch_cuda
     dn.close()
 
 
+def test_train_main_trains_evaluates_and_checkpoints(torch_cuda, tmp_path, capsys):
+    """`python -m caro_ai_b200.train -g 1` end to end on one GPU (train.py:165-217): two steps of 512 TicTacToe games fill the
+    device ring past MIN_REPLAY_TO_TRAIN, so both steps run the ten SGD rounds, the arena is played after the second step, the
+    reference's progress line is printed, and a promotion (if the arena grants one) writes `saves/<name>/best_001_00002.dat`
+    in the reference's format."""
+    torch = torch_cuda
+    from caro_ai_b200 import train as train_cli
+    from caro_ai_b200.game import TicTacToe
+    from caro_ai_b200.model import load_checkpoint
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        random.seed(0)
+        torch.manual_seed(0)
+        assert train_cli.main(["-g", "1", "-n", "r2test", "--games", "512", "--max-steps", "2", "--evaluate-every", "2", "--augment"]) == 0
+    finally:
+        os.chdir(cwd)
+    out = capsys.readouterr().out
+    assert "Step 2, steps" in out and "replay " in out and "Net evaluated, win ratio = " in out
+    ratio = float(out.split("Net evaluated, win ratio = ")[1].split()[0])
+    saved = os.path.join(tmp_path, "saves", "r2test", "best_001_00002.dat")
+    assert os.path.isdir(os.path.join(tmp_path, "saves", "r2test"))
+    assert os.path.exists(saved) == (ratio > 0.60)
+    if os.path.exists(saved):
+        load_checkpoint(saved, TicTacToe(3, 3))
+
+
 # --------------------------------------------------------------------------- cached ply graph life cycle
 def test_ply_graph_is_not_replayed_for_other_engines_or_new_weights(torch_cuda):
     """`caro_engine_play_multi` replays one captured CUDA graph per ply.  The graph bakes in workspace pointers,
