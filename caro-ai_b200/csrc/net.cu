@@ -190,6 +190,9 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_blob = nullptr;
   net->d_tc_weights = nullptr;
   net->d_rt_weights = nullptr;
+  net->d_rt_pair_weights = nullptr;
+  net->d_rt_scratch = nullptr;
+  net->rt_scratch_seq = 0;
   net->d_rx_weights = nullptr;
   net->d_tc_bias = nullptr;
   net->d_pol_fc_t = nullptr;

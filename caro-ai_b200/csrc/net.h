@@ -58,6 +58,9 @@ struct caro_net {
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
+  void* d_rt_pair_weights;  // the same for the CTA-pair form: one image per cluster rank, 7 KB blocks
+  void* d_rt_scratch;       // CTA-pair form: head features + FC scratch of every CTA, kRtScratchSlots launches in flight
+  unsigned rt_scratch_seq;  // next slot (round robin per launch)
   void* d_rx_weights;   // fp16 hi / lo UMMA B-operand blocks of the split-precision row-tiled tower -- see net_rx.cu
   alignas(16) float h_rt_consts[(caro::kMaxBlocks + 1) * 64 + 3 * 64 + 4 + 1536 + 4];  // host copy of the row-tiled tower's by-value constants (RtConsts)
   float* d_tc_bias;     // [6][64] folded conv biases

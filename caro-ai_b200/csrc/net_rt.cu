@@ -57,8 +57,16 @@
 namespace caro {
 
 // CP = channel parts of the epilogue (2 -> 8 epilogue warps x 32 channels, 4 -> 16 warps x 16 channels)
-template <int CP>
+// PAIR: two CTAs of a cluster (one TPC) run the tower as ONE cta_group::2 MMA stream of M = 256: each CTA keeps its own 16
+// boards (activations, accumulators, epilogue, heads) but stores and fetches only HALF of every B operand, 4 + 3 KB per
+// N = 192 MMA instead of 4 + 6.  The blocks grow from 6 to 7 KB (three windows, rt_common.cuh), which the head features and
+// the FC scratch pay for by moving to global memory.
+template <int CP, bool PAIR_ = false>
 struct RtCfg {
+  static constexpr bool kPair = PAIR_;
+  static constexpr int kBlockBytes = PAIR_ ? kRtPairBlockBytes : kRtBlockBytes;
+  static constexpr int kBlockUnits = kBlockBytes / 16;
+  static constexpr int kRegionBytes = kRtRegionBlocks * kBlockBytes;
   static constexpr int kCP = CP;
   static constexpr int kCH = 64 / CP;
   static constexpr int kEpiWarps = 4 * CP;
@@ -72,17 +80,23 @@ struct RtCfg {
   static_assert(CP == 2, "the last layer's even/odd tile split assumes two channel parts");
   static constexpr int kAct = 0;
   static constexpr int kWgt = kAct + kRtActBytes;
-  static constexpr int kHeadF = kWgt + kRtRegions * kRtRegionBytes;  // float [nb][3][HW] head features
-  static constexpr int kFc = kHeadF + kRtHeadFloats * 4;
-  static constexpr int kFcW = kFc + kRtFcFloats * 4;               // transposed FC weights (policy, value FC1) when they fit
+  static constexpr int kHeadF = kWgt + kRtRegions * kRegionBytes;  // float [nb][3][HW] head features (PAIR: in global memory)
+  static constexpr int kFc = kHeadF + (PAIR_ ? 0 : kRtHeadFloats * 4);
+  static constexpr int kFcW = kFc + (PAIR_ ? 0 : kRtFcFloats * 4);  // transposed FC weights (policy, value FC1) when they fit
   static constexpr int kBars0 = kFcW;
-  static constexpr int kNumBars = kRtRegions * kRtRegionBlocks + kRtRegions + 2 * kRtMaxH + 2;
+  static constexpr int kNumBars = kRtRegions * kRtRegionBlocks + 2 * kRtRegions + 2 * kRtMaxH + 2;
   static constexpr int kFixed = kBars0 + kNumBars * 8 + 32;         // everything but the FC weights
   static constexpr int kFcWFloats = (CARO_RT_SMEM_LIMIT - kFixed) / 4;  // what is left of the budget
   static constexpr int kBars = kFcW + kFcWFloats * 4;
   static constexpr int kTotal = kBars + kNumBars * 8 + 32;
   static_assert(kFixed <= CARO_RT_SMEM_LIMIT && kTotal <= CARO_RT_SMEM_LIMIT, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
+
+template <int V>
+struct RtInt {};
+template <int V>
+__device__ __forceinline__ constexpr int rt_value(RtInt<V>) { return V; }
+__device__ __forceinline__ constexpr int rt_value(int v) { return v; }
 
 // The MMAs of one source tile.  POS: 0 = first board row (no out[-1]: B slot 0 is skipped, the accumulators of
 // out[0], out[1] are overwritten by the first MMA; it is also the tile that waits for the weight blocks to land),
@@ -91,32 +105,54 @@ struct RtCfg {
 // tile base and the TMEM addresses is a compile-time constant, so that the MMAs issue back to back.
 // `mid` (run when do_mid, in the middle of the tile): work of the issuing warp that would otherwise sit between two layers; in the
 // middle of an N = 192 tile the MMAs already queued hide ~265 cycles of it, next to a commit only ~95 (tools/cta2_probe.cu).
-template <int POS, bool FIRST, class Mid>
+// PAIR (cta_group::2, issued by the leader CTA for both): every MMA accumulates -- the epilogues leave the accumulators they
+// have read zeroed --, B comes from the window of the tile's position, `fullp` = the barriers the peer's weights are reported on.
+template <int POS, bool FIRST, bool PAIR, class Mid>
 __device__ __forceinline__ void rt_issue_tile(bool do_mid, Mid&& mid, uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
                                               uint32_t d_new, uint32_t full0, uint32_t full1, uint32_t ph0, uint32_t ph1,
-                                              uint32_t empty0, uint32_t empty1, uint32_t next_bar, uint32_t next_bar2, uint32_t next_par) {
+                                              uint32_t empty0, uint32_t empty1, uint32_t next_bar, uint32_t next_bar2, uint32_t next_par,
+                                              uint32_t fullp0, uint32_t fullp1, long long* tstamp = nullptr) {
   // all barriers are shared-memory addresses; next_bar / next_bar2 == 0: nothing to poll
   constexpr int NB = FIRST ? 3 : 12;
+  constexpr int kUnits = PAIR ? kRtPairBlockBytes / 16 : kRtBlockUnits;
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int dx = FIRST ? i - 1 : i / 4 - 1, kk = FIRST ? 0 : i % 4;
-    if (POS == 0 && (i == 0 || i == 6)) mbar_wait_a(i < 6 ? full0 : full1, i < 6 ? ph0 : ph1);  // first use of the region in this layer
+    if (POS == 0 && (i == 0 || i == 6)) {  // first use of the region in this layer
+      if (tstamp && elected) tstamp[i < 6 ? 0 : 3] = clock64();
+      mbar_wait_a(i < 6 ? full0 : full1, i < 6 ? ph0 : ph1);
+      if (tstamp && elected) tstamp[i < 6 ? 1 : 4] = clock64();
+      if (PAIR) mbar_wait_cluster_a(i < 6 ? fullp0 : fullp1, i < 6 ? ph0 : ph1);
+      if (tstamp && elected) tstamp[i < 6 ? 2 : 5] = clock64();
+    }
     // the barrier the NEXT tile needs is polled while this tile's MMAs are still queued in the tensor pipe
     if (i == (FIRST ? 1 : 4) && do_mid) mid();
     if (i == (FIRST ? 1 : 8) && next_bar != 0u) {
-      mbar_wait_a(next_bar, next_par);
-      if (next_bar2 != 0u) mbar_wait_a(next_bar2, next_par);
+      if (PAIR) {
+        mbar_wait_cluster_a(next_bar, next_par);
+        if (next_bar2 != 0u) mbar_wait_cluster_a(next_bar2, next_par);
+      } else {
+        mbar_wait_a(next_bar, next_par);
+        if (next_bar2 != 0u) mbar_wait_a(next_bar2, next_par);
+      }
     }
     if (elected) {
       const uint64_t ad = a_tile + (uint64_t)(int64_t)(dx + kk * 2 * kRtActRows);
-      const uint64_t bd = (i < 6 ? rb0 + (uint64_t)(i * kRtBlockUnits) : rb1 + (uint64_t)((i - 6) * kRtBlockUnits)) + (POS == 0 ? 64ull : 0ull);
-      if (POS == 1 && i == 0) {
-        umma_bf16(d_main, ad, bd, rt_idesc(128), 1u);
-        umma_bf16(d_new, ad, bd + 128ull, rt_idesc(64), 0u);
+      if (PAIR) {
+        const uint64_t bd = (i < 6 ? rb0 + (uint64_t)(i * kUnits) : rb1 + (uint64_t)((i - 6) * kUnits)) +
+                            (POS == 0 ? (uint64_t)kRtPairTop : POS == 2 ? (uint64_t)kRtPairBottom : 0ull);
+        umma_bf16_pair(d_main, ad, bd, POS == 1 ? rt_idesc_pair(192) : rt_idesc_pair(128), 1u);
+        if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit_pair_a(i < 6 ? empty0 : empty1);
       } else {
-        umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc(192) : rt_idesc(128), (POS == 0 && i == 0) ? 0u : 1u);
+        const uint64_t bd = (i < 6 ? rb0 + (uint64_t)(i * kUnits) : rb1 + (uint64_t)((i - 6) * kUnits)) + (POS == 0 ? 64ull : 0ull);
+        if (POS == 1 && i == 0) {
+          umma_bf16(d_main, ad, bd, rt_idesc(128), 1u);
+          umma_bf16(d_new, ad, bd + 128ull, rt_idesc(64), 0u);
+        } else {
+          umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc(192) : rt_idesc(128), (POS == 0 && i == 0) ? 0u : 1u);
+        }
+        if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit_a(i < 6 ? empty0 : empty1);
       }
-      if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit_a(i < 6 ? empty0 : empty1);
     }
   }
 }
@@ -130,21 +166,26 @@ __device__ __forceinline__ void rt_issue_tile(bool do_mid, Mid&& mid, uint32_t e
 //               AND the accumulators out[y-1..y+1] drained by the previous layer's epilogues;
 //   EPI(gl, y)  waits the commit after source tile min(y+1, H-1): out[y] has received all of its contributions;
 //               it rewrites act[y] in place (source tile y has been consumed by then).
-template <class R, class K>
+// HC: the number of board rows as a compile-time constant (0 = run-time gm.H): the MMA warp's tile loop is then unrolled
+// with every position test, barrier choice and TMEM address folded -- the issuing thread is the tower's critical resource.
+template <class R, class K, int HC>
 __global__ void __maxnreg__(CARO_RT_MAXREG)
 net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const __grid_constant__ RtConsts consts, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
-              float* __restrict__ values, long long* __restrict__ trace) {
+              float* __restrict__ values, long long* __restrict__ trace, float* __restrict__ scratch) {
+  constexpr bool PAIR = K::kPair;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + K::kAct;
   uint8_t* wgt = smem + K::kWgt;
-  float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
-  float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
+  // PAIR: head features and FC scratch of this CTA live in global memory (`scratch`, one slot per launch in flight)
+  float* headf_s = PAIR ? scratch + (size_t)blockIdx.x * (kRtHeadFloats + kRtFcFloats) : reinterpret_cast<float*>(smem + K::kHeadF);
+  float* fc_s = PAIR ? headf_s + kRtHeadFloats : reinterpret_cast<float*>(smem + K::kFc);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [regions][6], slot 0 used: the region's weight blocks landed
   uint64_t* bar_empty = bar_full + kRtRegions * kRtRegionBlocks;          // [regions] region consumed by the last tile
-  uint64_t* bar_acc = bar_empty + kRtRegions;                             // [H] MMAs of source tile y complete
+  uint64_t* bar_fullp = bar_empty + kRtRegions;                           // [regions] PAIR, leader: the peer's blocks landed too
+  uint64_t* bar_acc = bar_fullp + kRtRegions;                             // [H] MMAs of source tile y complete
   uint64_t* bar_act = bar_acc + kRtMaxH;                                  // [H] activation tile rewritten + accumulator drained
   uint64_t* bar_feat = bar_act + kRtMaxH;                                 // [0] head features complete, [1] consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_feat + 2);
@@ -168,19 +209,28 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   }
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int nb = gm.nb;
-  const int H = gm.H;
+  const int H = HC > 0 ? HC : gm.H;
   const long long n_groups = (count + nb - 1) / nb;
-  if ((long long)blockIdx.x >= n_groups) return;  // uniform per CTA, before any barrier / TMEM use
-  const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // PAIR: the unit of work is a PAIR of groups, the CTA of rank r takes the r-th; an odd last group leaves the peer an empty one
+  // (all of its leaves >= count: it feeds zeros through the same protocol and writes nothing)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const long long unit = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long n_units = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const long long work = PAIR ? (n_groups + 1) / 2 : n_groups;
+  if (unit >= work) return;  // uniform per CTA (pair), before any barrier / TMEM use
+  const int my_groups = (int)((work - unit + n_units - 1) / n_units);
+  auto group_leaf0 = [&](int gi) { return ((unit + (long long)gi * n_units) * (PAIR ? 2 : 1) + rank) * nb; };
+  auto group_valid = [&](long long leaf0) { return (int)max(0ll, min((long long)nb, count - leaf0)); };
 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < kRtActBytes / 16; i += K::kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < kRtRegions * kRtRegionBlocks; ++s) mbar_init(bar_full + s, 1);
     for (int s = 0; s < kRtRegions; ++s) mbar_init(bar_empty + s, 1);
+    for (int s = 0; s < kRtRegions; ++s) mbar_init(bar_fullp + s, 1);
     for (int t = 0; t < kRtMaxH; ++t) {
       mbar_init(bar_acc + t, 1);
-      mbar_init(bar_act + t, K::kEpiThreads);
+      mbar_init(bar_act + t, PAIR ? 2 * K::kEpiWarps : K::kEpiThreads);  // PAIR: one arrival per epilogue warp of either CTA
     }
     mbar_init(bar_feat + 0, K::kEpiThreads);
     mbar_init(bar_feat + 1, K::kHeadThreads);
@@ -188,13 +238,20 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   }
   if (warp == K::kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kRtTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kRtTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kRtTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything reaches across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) TC_TRACE(7, 1);  // setup done
@@ -221,8 +278,8 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     }
     asm volatile("bar.sync 2, %0;" ::"n"(K::kHeadThreads) : "memory");
     for (int gi = 0; gi + 1 < my_groups; ++gi) {
-      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
-      const int nvalid = (int)min((long long)nb, count - leaf0);
+      const long long leaf0 = group_leaf0(gi);
+      const int nvalid = group_valid(leaf0);
       mbar_wait_relaxed(bar_feat + 0, (uint32_t)gi & 1u);
       rt_heads<K::kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, fc_s, consts.headb[0], consts.headb[1], consts.headb[2], fcv, polw,
                                    valw, probs, values, consts);
@@ -231,8 +288,8 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     }
     {  // the last group of this CTA: nothing is left to overlap with, the (idle) epilogue warps join in
       const int gi = my_groups - 1;
-      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
-      const int nvalid = (int)min((long long)nb, count - leaf0);
+      const long long leaf0 = group_leaf0(gi);
+      const int nvalid = group_valid(leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
       rt_heads<K::kEpiThreads + K::kHeadThreads, 3>(gm, nvalid, leaf0, K::kEpiThreads + htid, headf_s, fc_s, consts.headb[0],
                                                     consts.headb[1], consts.headb[2], fcv, polw, valw, probs, values, consts);
@@ -244,6 +301,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     if ((tid & 31) == 0) {
       const int regions_net = 2 * gm.layers - 1;  // conv_in (3 blocks + 3 unused) + 2 per residual block
       const int total = my_groups * regions_net;
+      const uint8_t* wrank = wimg + (size_t)rank * regions_net * K::kRegionBytes;  // PAIR: one image per rank
       int reg = 0, src = 0;
       uint32_t round = 0;
       for (int n = 0; n < total; ++n) {
@@ -252,12 +310,26 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         // ONE barrier per region (slot 0 of its six): the first tile of a layer polls two barriers instead of twelve -- its
         // N = 128 MMAs issue at the tensor pipe's own rate, so every poll between two of them is exposed (tools/cta2_probe.cu)
         uint64_t* bar = bar_full + reg * kRtRegionBlocks;
-        mbar_expect_tx(bar, (uint32_t)(nblk * kRtBlockBytes));
+        mbar_expect_tx(bar, (uint32_t)(nblk * K::kBlockBytes));
         for (int b = 0; b < nblk; ++b)
-          bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * kRtBlockBytes, wimg + (size_t)(src * kRtRegionBlocks + b) * kRtBlockBytes,
-                   (uint32_t)kRtBlockBytes, bar);
+          bulk_g2s(wgt + (reg * kRtRegionBlocks + b) * K::kBlockBytes, wrank + (size_t)(src * kRtRegionBlocks + b) * K::kBlockBytes,
+                   (uint32_t)K::kBlockBytes, bar);
         if (++reg == kRtRegions) { reg = 0; ++round; }
         if (++src == regions_net) src = 0;
+      }
+    }
+  } else if (warp == K::kMmaWarp && PAIR && rank != 0) {
+    // ===================== PAIR, peer CTA: the leader issues the MMAs of both; this warp only reports the arrival of this
+    // CTA's weight regions to the leader (a local wait, then one remote arrive per region) ==============================
+    if ((tid & 31) == 0) {
+      const int total = my_groups * (2 * gm.layers - 1);
+      const uint32_t fullp_leader = mapa_a(smem_u32(bar_fullp), 0u);
+      int reg = 0;
+      uint32_t ph = 0;
+      for (int n = 0; n < total; ++n) {
+        mbar_wait(bar_full + reg * kRtRegionBlocks, ph);  // spinning: the leader's first tile of a layer waits for this report
+        mbar_arrive_cluster_a(fullp_leader + 8u * (uint32_t)reg);
+        if (++reg == kRtRegions) { reg = 0; ph ^= 1u; }
       }
     }
   } else if (warp == K::kMmaWarp) {
@@ -266,9 +338,10 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     uint32_t elected;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
     const uint64_t a_desc0 = make_desc(smem_u32(act) + (uint32_t)kRtHalo * 16u, (uint32_t)kRtChunkBytes, 128u);
-    const uint64_t b_desc0 = make_desc(smem_u32(wgt), 192u * 16u, 128u);
+    const uint64_t b_desc0 = make_desc(smem_u32(wgt), (PAIR ? (uint32_t)kRtPairRows : 192u) * 16u, 128u);
     uint32_t full_a = smem_u32(bar_full), empty_a = smem_u32(bar_empty), acc_a = smem_u32(bar_acc), act_a = smem_u32(bar_act);
-    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(acc_a), "+r"(act_a));  // opaque: not re-derived from the CTA's shared window per tile
+    uint32_t fullp_a = smem_u32(bar_fullp);
+    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(acc_a), "+r"(act_a), "+r"(fullp_a));  // opaque: not re-derived from the CTA's shared window per tile
     // the timeline's condition is evaluated once: between two tiles every instruction of this warp is exposed
     const bool tr = elected && trace != nullptr && blockIdx.x == 0;
 #define RT_MMA_TRACE(kind, idx)                                                 \
@@ -284,23 +357,26 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     // weight regions of a layer: descriptor bases, "landed" / "consumed" barriers and the phases to wait for
     struct LayerW {
       uint64_t rb0, rb1;
-      uint32_t full0, full1, empty0, empty1, ph0, ph1;
+      uint32_t full0, full1, empty0, empty1, ph0, ph1, fullp0, fullp1;
     };
     auto take_regions = [&](bool first_l) {
       LayerW w;
-      w.rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+      w.rb0 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * K::kBlockUnits);
       w.full0 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
       w.empty0 = empty_a + 8u * (uint32_t)reg;
+      w.fullp0 = fullp_a + 8u * (uint32_t)reg;
       w.ph0 = rphase;
       if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
       w.rb1 = w.rb0;
       w.full1 = w.full0;
       w.empty1 = w.empty0;
+      w.fullp1 = w.fullp0;
       w.ph1 = w.ph0;
       if (!first_l) {
-        w.rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * kRtBlockUnits);
+        w.rb1 = b_desc0 + (uint64_t)(uint32_t)(reg * kRtRegionBlocks * K::kBlockUnits);
         w.full1 = full_a + 8u * (uint32_t)(reg * kRtRegionBlocks);
         w.empty1 = empty_a + 8u * (uint32_t)reg;
+        w.fullp1 = fullp_a + 8u * (uint32_t)reg;
         w.ph1 = rphase;
         if (++reg == kRtRegions) { reg = 0; rphase ^= 1u; }
       }
@@ -314,19 +390,26 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const LayerW cur = nxt;
       const uint64_t rb0 = cur.rb0, rb1 = cur.rb1;
       const uint32_t full0 = cur.full0, full1 = cur.full1, empty0 = cur.empty0, empty1 = cur.empty1, ph0 = cur.ph0, ph1 = cur.ph1;
+      const uint32_t fullp0 = cur.fullp0, fullp1 = cur.fullp1;
       // the next layer's regions are worked out in the middle of tile 1 (H >= 2), not between two layers, and pinned there
       auto mid = [&]() {
         nxt = take_regions(layer + 1 == n_layers);
         asm volatile("" : "+l"(nxt.rb0), "+l"(nxt.rb1), "+r"(nxt.full0), "+r"(nxt.full1), "+r"(nxt.empty0), "+r"(nxt.empty1), "+r"(nxt.ph0),
                      "+r"(nxt.ph1));
+        if (PAIR) asm volatile("" : "+r"(nxt.fullp0), "+r"(nxt.fullp1));
       };
-#pragma unroll 1
-      for (int y = 0; y < H; ++y) {
+      auto tile = [&](auto yv) {
+        const int y = rt_value(yv);
         // tile y reads act[y] and writes out[y-1..y+1]: it needs the barriers of tiles y-1, y, y+1 at this stage.
         // All but the first tile's were already polled while the previous tile's MMAs were being issued.
         if (y == 0 && !pre_waited) {
-          mbar_wait_a(act_a, par);
-          mbar_wait_a(act_a + 8u, par);
+          if (PAIR) {
+            mbar_wait_cluster_a(act_a, par);
+            mbar_wait_cluster_a(act_a + 8u, par);
+          } else {
+            mbar_wait_a(act_a, par);
+            mbar_wait_a(act_a + 8u, par);
+          }
         }
         if (y == 0) RT_MMA_TRACE(6, gl * 2 + 1);  // first tile: barriers passed
         tc_fence_after();  // orders this tile's MMAs after the barrier observations (also the early ones)
@@ -351,17 +434,31 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           npar = par ^ 1u;
         }
         if (first) {
-          if (y == 0) rt_issue_tile<0, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, true>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else if (y == H - 1) rt_issue_tile<2, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else rt_issue_tile<1, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
         } else {
-          if (y == 0) rt_issue_tile<0, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else if (y == H - 1) rt_issue_tile<2, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
-          else rt_issue_tile<1, false>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar);
+          if (y == 0) rt_issue_tile<0, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1, tr && gl < 100 ? trace + 5000 + gl * 6 : nullptr);
+          else if (y == H - 1) rt_issue_tile<2, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else rt_issue_tile<1, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
         }
-        if (elected) umma_commit_a(acc_a + 8u * (uint32_t)y);
+        if (elected) {
+          if (PAIR) umma_commit_pair_a(acc_a + 8u * (uint32_t)y);
+          else umma_commit_a(acc_a + 8u * (uint32_t)y);
+        }
         RT_MMA_TRACE(1, gl * 8 + y);
         __syncwarp();
+      };
+      if constexpr (HC == 6) {
+        tile(RtInt<0>{});
+        tile(RtInt<1>{});
+        tile(RtInt<2>{});
+        tile(RtInt<3>{});
+        tile(RtInt<4>{});
+        tile(RtInt<5>{});
+      } else {
+#pragma unroll 1
+        for (int y = 0; y < H; ++y) tile(y);
       }
       pre_waited = H >= 4 && gl + 1 < total_layers;
       if (++layer == n_layers) layer = 0;
@@ -376,6 +473,25 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int HW = gm.H * gm.W;
     const bool dbg_skip_epilogue = trace != nullptr && trace[7999] == 1;
+    // "activation tile y rewritten, accumulator drained".  PAIR: the barrier lives in the leader CTA and counts WARPS of both
+    // CTAs (every lane has fenced its own writes; the warp barrier orders them before lane 0's cluster-scope release)
+    const uint32_t act_leader = PAIR ? mapa_a(smem_u32(bar_act), 0u) : 0u;
+    auto act_arrive = [&](int y) {
+      if (PAIR) {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_cluster_a(act_leader + 8u * (uint32_t)y);
+      } else {
+        mbar_arrive(bar_act + y);
+      }
+    };
+    // PAIR: every MMA accumulates, so whoever reads an accumulator leaves it zeroed for the next layer
+    const bool dbg_no_zero = trace != nullptr && (trace[7996] & 1);
+    auto zero_acc = [&](int y, int c0) {
+      if (dbg_no_zero) return;
+      const uint32_t a = tmem_base + lane_base + (uint32_t)(y * 64 + c0);
+      TMEM_ST16Z(a, 0u);
+      TMEM_ST16Z(a + 16u, 0u);
+    };
 
     // `writer`: the warp set that stores the planes (the one that last read this tile's activations)
     auto write_inputs = [&](int y, long long leaf0, int writer) {
@@ -394,7 +510,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         *reinterpret_cast<uint4*>(dst + kRtChunkBytes) = make_uint4(0u, 0u, 0u, 0u);  // K is padded to 16
         fence_async_smem();
       }
-      mbar_arrive(bar_act + y);
+      act_arrive(y);
     };
 
     // Loads the accumulator, bias, LeakyReLU and (HAS_RES) the residual hi (bf16, shared memory) + lo (e5m2, TMEM)
@@ -445,12 +561,13 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       if (tid == 0) TC_TRACE(2, gl * 8 + y);
       if (dbg_skip_epilogue) {  // debug (tools/net_trace.py): measure the MMA stream without the epilogue's traffic
         tc_fence_before();
-        mbar_arrive(bar_act + y);
+        act_arrive(y);
         return;
       }
       uint8_t* arow = act + (size_t)(cp * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
       float2 v[16];
       load_values(has_res_c, layer, y, cp * 32, v, arow);
+      if (PAIR) zero_acc(y, cp * 32);
       const float2 minus1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
@@ -473,7 +590,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_act + y);
+      act_arrive(y);
       if (tid == 0) TC_TRACE(3, gl * 8 + y);
     };
 
@@ -493,6 +610,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           uint8_t* arow = act + (size_t)(hh * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
           float2 v[16];
           load_values(std::true_type{}, gm.layers - 1, y, hh * 32, v, arow);
+          if (PAIR) zero_acc(y, hh * 32);
           const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -509,17 +627,23 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           headf_s[(bidx * 3 + 1) * HW + cell] = ap0;
           headf_s[(bidx * 3 + 2) * HW + cell] = ap1;
         }
+        if (PAIR) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
       if (more) write_inputs(y, next_leaf0, y & 1);  // by the set that just read this tile's residual
       if (tid == 0) TC_TRACE(3, gl * 8 + y);
     };
 
-    for (int y = 0; y < H; ++y) write_inputs(y, (long long)blockIdx.x * nb, 0);
+    if (PAIR) {  // all accumulators start out zero (the first MMA of a layer accumulates like every other)
+      for (int c = cp * 192; c < cp * 192 + 192; c += 32) zero_acc(0, c);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+    }
+    for (int y = 0; y < H; ++y) write_inputs(y, group_leaf0(0), 0);
     for (int gi = 0; gi < my_groups; ++gi) {
-      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
+      const long long leaf0 = group_leaf0(gi);
       const bool more = gi + 1 < my_groups;
-      const long long next_leaf0 = (blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb;
+      const long long next_leaf0 = group_leaf0(gi + 1);
       const int gl0 = gi * gm.layers;
 #pragma unroll 1
       for (int y = 0; y < H; ++y) epilogue_tile(std::false_type{}, 0, gl0, y);
@@ -535,7 +659,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       if (tid == 0) TC_TRACE(4, gi);
       if (!more) {  // join the head warps for the heads of the last group
         mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
-        const int nvalid = (int)min((long long)nb, count - leaf0);
+        const int nvalid = group_valid(leaf0);
         const float* fcv = reinterpret_cast<const float*>(smem + K::kFcW);  // staged by the head warps (same rule as there)
         const int fcv_floats = (41 + gm.A + 3) & ~3;
         const bool staged = fcv_floats + HW * (2 * gm.A + 20) <= K::kFcWFloats;
@@ -551,6 +675,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   if (tid == 0) TC_TRACE(7, 2);  // epilogue warp 0 finished (incl. the last group's heads)
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA of a pair leaves (or frees TMEM) while the other may still be signalled or read
   if (tid == 0) TC_TRACE(7, 3);  // all roles finished
   if (gt_slot != nullptr) {
     long long t;
@@ -559,7 +684,8 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   }
   if (warp == K::kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kRtTmemCols) : "memory");
   }
 }
 
@@ -626,21 +752,49 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
         for (int c = 0; c < HW; ++c) hc->fcw[(size_t)2 * HW * A + (size_t)c * 20 + i] = h[L.val_fc1_w + (size_t)i * HW + c];
     }
   }
+  // CTA-pair form: one image per cluster rank, 7 KB blocks of three windows cut out of the same 192 stacked columns
+  const size_t n_blocks = (size_t)(1 + 2 * blocks) * kRtRegionBlocks;
+  const size_t pair_bytes = n_blocks * kRtPairBlockBytes;
+  std::vector<uint16_t> pimg(2 * pair_bytes / 2, 0);
+  for (int r = 0; r < 2; ++r)
+    for (size_t b = 0; b < n_blocks; ++b)
+      for (int chunk = 0; chunk < 2; ++chunk)
+        for (int row = 0; row < kRtPairRows; ++row) {
+          const int n = row < 96 ? r * 96 + row : row < 160 ? 64 + r * 64 + (row - 96) : r * 64 + (row - 160);
+          const uint16_t* src = &img[(b * kRtBlockBytes + (size_t)chunk * 3072 + (size_t)n * 16) / 2];
+          uint16_t* dst = &pimg[((size_t)r * pair_bytes + b * kRtPairBlockBytes + (size_t)chunk * kRtPairRows * 16 + (size_t)row * 16) / 2];
+          for (int e = 0; e < 8; ++e) dst[e] = src[e];
+        }
   cudaError_t ce = cudaSuccess;
   if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);  // the depth of a handle never changes (caro_net_update checks the blob size)
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && !net->d_rt_pair_weights) ce = cudaMalloc(&net->d_rt_pair_weights, 2 * pair_bytes);
+  if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_pair_weights, pimg.data(), 2 * pair_bytes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && !net->d_rt_scratch)
+    ce = cudaMalloc(&net->d_rt_scratch, (size_t)kRtScratchSlots * net->sm_count * (kRtHeadFloats + kRtFcFloats) * sizeof(float));
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }
 
 void caro_net_rt_free(caro_net* net) {
   if (net->d_rt_weights) cudaFree(net->d_rt_weights);
+  if (net->d_rt_pair_weights) cudaFree(net->d_rt_pair_weights);
+  if (net->d_rt_scratch) cudaFree(net->d_rt_scratch);
   net->d_rt_weights = nullptr;
+  net->d_rt_pair_weights = nullptr;
+  net->d_rt_scratch = nullptr;
 }
 
 bool caro_net_rt_supports(const caro_net* net) { return net->H >= 2 && net->H <= kRtMaxH && net->W >= 2 && net->W <= kRtMaxW; }
 
 using RtK = RtCfg<CARO_RT_CP>;
+using RtKPair = RtCfg<CARO_RT_CP, true>;
+
+// CARO_RT_PAIR=1/0 switches the CTA-pair form of the tower on / off (read once)
+static bool rt_pair_enabled() {
+  static const bool on = getenv("CARO_RT_PAIR") ? atoi(getenv("CARO_RT_PAIR")) != 0 : false;
+  return on;
+}
 
 template <class R>
 static int launch_rt(const R& rules, caro_net* net, const void* boards, const uint8_t* who, const int32_t* d_count,
@@ -656,22 +810,62 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;
+  static const int generic_env = getenv("CARO_RT_GENERIC") ? atoi(getenv("CARO_RT_GENERIC")) : 0;  // A/B: 1 = run-time H
   // SMs for the persistent tower: the user's limit, else (inside the parts pipeline) all but a ninth of the SMs, which stay
   // with the other parts' tree kernels -- their dependent chain expand -> select -> plan, not the tower, sets the
   // pipeline's period once they only get the leftover warp slots next to tower CTAs (tools/pipeline_trace.py)
   const int lim = net->grid_limit > 0 ? net->grid_limit : net->pipeline_limit;
   const int ctas = lim > 0 && lim < net->sm_count ? lim : net->sm_count;
+  if (rt_pair_enabled() && max_groups >= 2 && ctas >= 2) {
+    // clusters of two CTAs (one TPC each); every launch in flight gets its own slot of the global head scratch -- launches of
+    // different pipeline parts overlap on the GPU, and the slot is baked into a captured graph node
+    const long long max_units = (max_groups + 1) / 2;
+    const unsigned pairs = (unsigned)(max_units < ctas / 2 ? max_units : ctas / 2);
+    float* scratch = (float*)net->d_rt_scratch +
+                     (size_t)(net->rt_scratch_seq++ % kRtScratchSlots) * net->sm_count * (kRtHeadFloats + kRtFcFloats);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(RtKPair::kThreads);
+    cfg.dynamicSmemBytes = RtKPair::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    auto pkern = gm.H == 6 && !generic_env ? net_rt_kernel<R, RtKPair, 6> : net_rt_kernel<R, RtKPair, 0>;
+    const cudaError_t ce = cudaLaunchKernelEx(
+        &cfg, pkern, rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
+        (const uint8_t*)net->d_rt_pair_weights, *reinterpret_cast<const RtConsts*>(net->h_rt_consts), (const float*)net->d_blob, net->layout,
+        (const float*)net->d_pol_fc_t, (const float*)(net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A), probs, values,
+        (long long*)net->d_trace, scratch);
+    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+    return caro_check_launch("net_rt_kernel (pair)");
+  }
   const unsigned grid = (unsigned)(max_groups < ctas ? max_groups : ctas);
-  net_rt_kernel<R, RtK><<<grid, RtK::kThreads, RtK::kTotal, st>>>(
+  auto kern = gm.H == 6 && !generic_env ? net_rt_kernel<R, RtK, 6> : net_rt_kernel<R, RtK, 0>;
+  kern<<<grid, RtK::kThreads, RtK::kTotal, st>>>(
       rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_weights,
       *reinterpret_cast<const RtConsts*>(net->h_rt_consts), net->d_blob, net->layout, net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs,
-      values, (long long*)net->d_trace);
+      values, (long long*)net->d_trace, nullptr);
   return caro_check_launch("net_rt_kernel");
 }
 
 int caro_net_rt_prepare() {
-  cudaError_t ce = cudaFuncSetAttribute(net_rt_kernel<C4Rules, RtK>, cudaFuncAttributeMaxDynamicSharedMemorySize, RtK::kTotal);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rt_kernel<MnkRules, RtK>, cudaFuncAttributeMaxDynamicSharedMemorySize, RtK::kTotal);
+  cudaError_t ce = cudaSuccess;
+  auto set = [&](auto kern, int bytes) {
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  };
+  set(net_rt_kernel<C4Rules, RtK, 0>, RtK::kTotal);
+  set(net_rt_kernel<C4Rules, RtK, 6>, RtK::kTotal);
+  set(net_rt_kernel<MnkRules, RtK, 0>, RtK::kTotal);
+  set(net_rt_kernel<MnkRules, RtK, 6>, RtK::kTotal);
+  set(net_rt_kernel<C4Rules, RtKPair, 0>, RtKPair::kTotal);
+  set(net_rt_kernel<C4Rules, RtKPair, 6>, RtKPair::kTotal);
+  set(net_rt_kernel<MnkRules, RtKPair, 0>, RtKPair::kTotal);
+  set(net_rt_kernel<MnkRules, RtKPair, 6>, RtKPair::kTotal);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }

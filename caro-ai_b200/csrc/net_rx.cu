@@ -40,7 +40,10 @@
 
 namespace caro {
 
-constexpr int kRxSlots = 3;                                   // weight ring: three 6 KB blocks
+#ifndef CARO_RX_SLOTS
+#define CARO_RX_SLOTS 5
+#endif
+constexpr int kRxSlots = CARO_RX_SLOTS;                                   // weight ring: three 6 KB blocks
 constexpr int kRxLayerBlocks = 24;                            // 12 (dx, k-step) blocks x {hi, lo}
 constexpr int kRxInBlocks = 6;                                // conv_in: 3 dx blocks x {hi, lo}
 constexpr uint32_t kRxLoUnits = kRtActBytes / 16;             // descriptor offset of the lo activation image
@@ -62,9 +65,9 @@ struct RxCfg {
   static constexpr int kActHi = 0;
   static constexpr int kActLo = kRtActBytes;
   static constexpr int kWgt = 2 * kRtActBytes;
-  static constexpr int kHeadF = kWgt + kRxSlots * kRtBlockBytes;   // float [nb][3][HW] head features
-  static constexpr int kFc = kHeadF + kRtHeadFloats * 4;
-  static constexpr int kFcV = kFc + kRtFcFloats * 4;               // small head vectors (FC1 bias, FC2, policy bias)
+  // the head features and the FC scratch live in global memory (caro_net::d_rt_scratch, one slot per launch in flight):
+  // their 11.5 KB buy two more ring slots -- with three the MMA warp waited for weights ~8 % of the time
+  static constexpr int kFcV = kWgt + kRxSlots * kRtBlockBytes;     // small head vectors (FC1 bias, FC2, policy bias)
   static constexpr int kBars = kFcV + 512;
   static constexpr int kNumBars = 2 * kRxSlots + 2 * kRtMaxH + 2;
   static constexpr int kTotal = kBars + kNumBars * 8 + 32;
@@ -85,19 +88,22 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*
 // Warp roles: 0..15 epilogue -- set = warp >> 3 owns the tiles with y % 2 == set, TMEM lane quarter = warp & 3, channel
 // half = (warp >> 2) & 1, so two tiles are rewritten at the same time in the window between two layers where nothing
 // else runs --, 16 = TMEM owner + MMA issue (one elected lane), 17 = weight producer, 18..19 = FC heads of the previous group.
-template <class R>
+// HC: the number of board rows as a compile-time constant (0 = run-time gm.H).  The MMA warp's loop is issue-bound: with H
+// known every tile's position test folds away (one UTCHMMA per MMA instead of a predicated pair, no per-tile branch)
+// -- 0.385 -> 0.31 ms per 9,472 Connect4 leaves.
+template <class R, int HC>
 __global__ void __launch_bounds__(RxCfg::kThreads, 1)
 net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, const uint8_t* __restrict__ who,
               const int32_t* __restrict__ d_count, long long max_count, const uint8_t* __restrict__ wimg,
               const __grid_constant__ RtConsts consts, const float* __restrict__ blob, BlobLayout L,
               const float* __restrict__ pol_fc_t, const float* __restrict__ val_fc1_t, float* __restrict__ probs,
-              float* __restrict__ values, long long* __restrict__ trace) {
+              float* __restrict__ values, long long* __restrict__ trace, float* __restrict__ scratch) {
   using K = RxCfg;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act = smem + K::kActHi;
   uint8_t* wgt = smem + K::kWgt;
-  float* headf_s = reinterpret_cast<float*>(smem + K::kHeadF);
-  float* fc_s = reinterpret_cast<float*>(smem + K::kFc);
+  float* headf_s = scratch + (size_t)blockIdx.x * (kRtHeadFloats + kRtFcFloats);
+  float* fc_s = headf_s + kRtHeadFloats;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + K::kBars);  // [slots] weight block landed
   uint64_t* bar_empty = bar_full + kRxSlots;                            // [slots] block consumed by every tile
   uint64_t* bar_acc = bar_empty + kRxSlots;                             // [H] all MMAs of source tiles <= y complete (last block)
@@ -109,7 +115,7 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   const int warp = tid >> 5;
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int nb = gm.nb;
-  const int H = gm.H;
+  const int H = HC > 0 ? HC : gm.H;
   const long long n_groups = (count + nb - 1) / nb;
   if ((long long)blockIdx.x >= n_groups) return;  // uniform per CTA, before any barrier / TMEM use
   const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -523,22 +529,29 @@ static int launch_rx(const R& rules, caro_net* net, const void* boards, const ui
   gm.pitch = 1 << gm.pshift;
   gm.nb = 128 / gm.pitch;
   gm.layers = 1 + net->layout.blocks;
+  static const int generic_env = getenv("CARO_RX_GENERIC") ? atoi(getenv("CARO_RX_GENERIC")) : 0;  // A/B: 1 = run-time H
   if (gm.nb * 3 * gm.H * gm.W > kRtHeadFloats || gm.nb * (20 + gm.A) > kRtFcFloats || 41 + gm.A > 128)
     return caro_fail(CARO_E_ARG, "board does not fit the row-tiled tensor-core geometry");
   const long long max_groups = (max_count + gm.nb - 1) / gm.nb;
   const int lim = net->grid_limit > 0 ? net->grid_limit : net->pipeline_limit;
   const int ctas = lim > 0 && lim < net->sm_count ? lim : net->sm_count;
   const unsigned grid = (unsigned)(max_groups < ctas ? max_groups : ctas);
-  net_rx_kernel<R><<<grid, RxCfg::kThreads, RxCfg::kTotal, st>>>(
+  // every launch in flight has its own slot of the global head scratch (launches of different pipeline parts overlap)
+  float* scratch = (float*)net->d_rt_scratch +
+                   (size_t)(net->rt_scratch_seq++ % kRtScratchSlots) * net->sm_count * (kRtHeadFloats + kRtFcFloats);
+  auto kern = gm.H == 6 && !generic_env ? net_rx_kernel<R, 6> : net_rx_kernel<R, 0>;
+  kern<<<grid, RxCfg::kThreads, RxCfg::kTotal, st>>>(
       rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rx_weights,
       *reinterpret_cast<const RtConsts*>(net->h_rt_consts), net->d_blob, net->layout, net->d_pol_fc_t,
-      net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values, (long long*)net->d_trace);
+      net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values, (long long*)net->d_trace, scratch);
   return caro_check_launch("net_rx_kernel");
 }
 
 int caro_net_rx_prepare() {
-  cudaError_t ce = cudaFuncSetAttribute(net_rx_kernel<C4Rules>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rx_kernel<MnkRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
+  cudaError_t ce = cudaFuncSetAttribute(net_rx_kernel<C4Rules, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rx_kernel<C4Rules, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rx_kernel<MnkRules, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_rx_kernel<MnkRules, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RxCfg::kTotal);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }

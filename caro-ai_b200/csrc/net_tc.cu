@@ -565,7 +565,8 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   if (gm.boards_per_group < 1 || gm.boards_per_group > 32 || gm.pitch + 1 > kHalo ||
       gm.boards_per_group * (20 + gm.A) > K::kFcFloats)
     return caro_fail(CARO_E_ARG, "board does not fit the tensor-core tile geometry");
-  const int sm_count = net->sm_count;
+  const int lim = net->grid_limit > 0 ? net->grid_limit : net->pipeline_limit;
+  const int sm_count = lim > 0 && lim < net->sm_count ? lim : net->sm_count;
   auto kern = net_tc_kernel<R, K>;
   const long long max_groups = (max_count + gm.boards_per_group - 1) / gm.boards_per_group;
   const unsigned grid = (unsigned)(max_groups < sm_count ? max_groups : sm_count);

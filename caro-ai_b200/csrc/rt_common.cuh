@@ -39,6 +39,18 @@ __host__ __device__ constexpr uint32_t rt_idesc(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// CTA-pair form (cta_group::2, net_rt.cu with PAIR): M = 256 = the 128 lanes of both CTAs, each CTA supplies half of B
+__host__ __device__ constexpr uint32_t rt_idesc_pair(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+// B block of the pair form, per CTA: rows 0..95 = its half of the 192 stacked columns (interior tiles), 96..159 = its half of
+// columns 64..191 (first board row: no out[-1]), 160..223 = its half of columns 0..127 (last board row: no out[H]).  One
+// descriptor addresses BOTH CTAs' copies, so each window has to start at the same offset in both.
+constexpr int kRtPairRows = 224;
+constexpr int kRtPairBlockBytes = 2 * kRtPairRows * 16;       // 7,168
+constexpr uint32_t kRtPairTop = 96, kRtPairBottom = 160;      // window starts in rows (= descriptor units)
+constexpr int kRtScratchSlots = 8;                            // launches of the pair form that may be in flight at once
+
 struct RtGeom {
   int H, W, A, pitch, pshift, nb;
   int layers;  // 1 + residual blocks of this network
@@ -208,5 +220,57 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+
+// ---- CTA pair (cluster of two, cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the address of this CTA's shared-memory location `addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_a(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Remote arrive in the form CUTLASS' ClusterBarrier::arrive(cta_id) uses (default .release.cta): a cluster-scope release
+// compiles to a MEMBAR that waits for every outstanding memory operation of the thread -- ncu showed the epilogue warps
+// stalled on it for as long as on all other reasons together (profiles/r2_net_rt_pair_ncu.txt)
+__device__ __forceinline__ void mbar_arrive_cluster_a(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar, uint32_t parity) {  // arrivals come from the peer CTA too
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_a(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+#define TMEM_ST16Z(addr, z)                                                                                      \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" \
+               ::"r"(addr), "r"(z) : "memory")
 
 }  // namespace caro

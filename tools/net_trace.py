@@ -26,6 +26,7 @@ def main():
     trace = torch.zeros(8000, dtype=torch.int64, device="cuda")
     if len(sys.argv) > 4 and sys.argv[4] == "mma-only":
         trace[7999] = 1  # row-tiled kernel: epilogue warps only pass the barriers on
+    trace[7996] = int(os.environ.get("TRACE_FLAGS", "0"))  # CTA-pair tower experiments (bit 0: accumulators are not zeroed)
     _cabi.check(_cabi.lib().caro_net_set_trace(dn.handle, trace.data_ptr()))
     dn.forward_boards(boards, who, leaves, impl)
     torch.cuda.synchronize()
@@ -33,13 +34,18 @@ def main():
     t = trace.cpu().numpy()
     names = ["mma_start", "mma_issued", "epi_start", "epi_done", "lastepi+inputs", "heads_done", "weights_ok"]
     ev = []
-    for kind in range(8):
+    for kind in (0, 1, 2, 3, 4, 6, 7):
         for idx in range(1000):
             v = int(t[kind * 1000 + idx])
-            if v and not (kind == 7 and idx >= 4):  # trace[7998], trace[7999] are mode flags, not stamps
+            if v and not (kind == 7 and idx >= 4) and not (kind * 1000 + idx >= 7990):  # trace[7998], trace[7999] are mode flags, not stamps
                 ev.append((v, kind, idx))
     ev.sort()
     t0 = ev[0][0]
+    for gl in range(1, 8):  # first tile of a layer: before / after the waits for the two weight regions (local, peer)
+        w = [int(x) - t0 for x in t[5000 + gl * 6:5006 + gl * 6]]
+        if w[0] > 0:
+            print("weights gl=%d: region0 at %d local +%d peer +%d | region1 at %d local +%d peer +%d" %
+                  (gl, w[0], w[1] - w[0], w[2] - w[1], w[3], w[4] - w[3], w[5] - w[4]))
     limit = int(sys.argv[2]) if len(sys.argv) > 2 else 140
     for clk, kind, idx in ev[:limit]:
         if kind == 6:
