@@ -274,8 +274,8 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
     if (game == CARO_GAME_CONNECT4) return launch_simt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
     return launch_simt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   }
-  if (impl == 0 && caro_net_rt_supports(net))
-    return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if ((impl == 0 || impl == 5) && caro_net_rt_supports(net))
+    return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 5, st);
   if (impl == 2 && caro_net_rt_supports(net))
     return caro_net_rx_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   if (impl == 0 || impl == 2 || impl == 3 || impl == 4)

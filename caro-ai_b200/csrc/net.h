@@ -93,7 +93,7 @@ int caro_net_rt_prepare();
 void caro_net_rt_free(caro_net* net);
 bool caro_net_rt_supports(const caro_net* net);
 int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int pair, cudaStream_t st);
 
 // net_rx.cu (split-precision row-tiled tower, fp16 hi + lo, boards up to 6 x 7)
 int caro_net_rx_pack(caro_net* net, const float* h_blob);

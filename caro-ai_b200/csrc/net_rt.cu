@@ -798,7 +798,7 @@ static bool rt_pair_enabled() {
 
 template <class R>
 static int launch_rt(const R& rules, caro_net* net, const void* boards, const uint8_t* who, const int32_t* d_count,
-                     int64_t max_count, float* probs, float* values, cudaStream_t st) {
+                     int64_t max_count, float* probs, float* values, bool pair, cudaStream_t st) {
   RtGeom gm;
   gm.H = net->H;
   gm.W = net->W;
@@ -816,7 +816,7 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
   // pipeline's period once they only get the leftover warp slots next to tower CTAs (tools/pipeline_trace.py)
   const int lim = net->grid_limit > 0 ? net->grid_limit : net->pipeline_limit;
   const int ctas = lim > 0 && lim < net->sm_count ? lim : net->sm_count;
-  if (rt_pair_enabled() && max_groups >= 2 && ctas >= 2) {
+  if ((pair || rt_pair_enabled()) && max_groups >= 2 && ctas >= 2) {
     // clusters of two CTAs (one TPC each); every launch in flight gets its own slot of the global head scratch -- launches of
     // different pipeline parts overlap on the GPU, and the slot is baked into a captured graph node
     const long long max_units = (max_groups + 1) / 2;
@@ -871,7 +871,7 @@ int caro_net_rt_prepare() {
 }
 
 int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, cudaStream_t st) {
-  if (game == CARO_GAME_CONNECT4) return launch_rt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
-  return launch_rt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int pair, cudaStream_t st) {
+  if (game == CARO_GAME_CONNECT4) return launch_rt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, pair != 0, st);
+  return launch_rt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, pair != 0, st);
 }

@@ -230,6 +230,65 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       for (int b = 0; b < nblk; ++b) {
         const int dx = first ? b - 1 : (b >> 2) - 1, kk = first ? 0 : (b & 3);
         const uint64_t a_blk = a_desc0 + (uint64_t)(int64_t)(dx + kk * 2 * kRtActRows);
+        if (kRxSlots >= 5 && !first && (b == 0 || b == nblk - 2)) {
+          // ---- TWO blocks tile-major (four ring slots): at the head of a layer tile y issues the MMAs of blocks 0 and 1 as soon
+          // as the previous layer's epilogues of tiles y-1 .. y+1 are done, at the tail blocks n-2 and n-1 finish tile by tile with a
+          // commit each -- twice the MMA work that can run underneath the epilogue chain between two layers
+          const bool head = b == 0;
+          const int b1 = b + 1;
+          const uint64_t a_blk1 = a_desc0 + (uint64_t)(int64_t)(((b1 >> 2) - 1) + (b1 & 3) * 2 * kRtActRows);
+          int sl[4];
+          uint32_t sp[4];
+          uint64_t bd[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sl[k] = slot + k;
+            sp[k] = sphase;
+            if (sl[k] >= kRxSlots) { sl[k] -= kRxSlots; sp[k] ^= 1u; }
+            bd[k] = b_desc0 + (uint64_t)(uint32_t)(sl[k] * kRtBlockUnits);
+          }
+          mbar_wait_a(full_a + 8u * (uint32_t)sl[0], sp[0]);
+          if (tr && gl * 32 + b * 2 < 1000) trace[gl * 32 + b * 2] = clock64();
+#pragma unroll
+          for (int y = 0; y < kRtMaxH; ++y) {
+            if (y < H) {
+              if (head) {
+                if (y == 0) mbar_wait_a(act_a, par);
+                if (y + 1 < H) mbar_wait_a(act_a + 8u * (uint32_t)(y + 1), par);
+              }
+              if (y == 0) mbar_wait_a(full_a + 8u * (uint32_t)sl[1], sp[1]);  // the later slots are waited for at their first use
+              tc_fence_after();
+              const uint64_t ad0 = a_blk + (uint64_t)(uint32_t)(y * 128), ad1 = a_blk1 + (uint64_t)(uint32_t)(y * 128);
+              if (elected && !dbg_skip_mma) {
+                RX_ISSUE(y, ad0, bd[0], head);
+                RX_ISSUE(y, ad0 + (uint64_t)kRxLoUnits, bd[0], false);
+                RX_ISSUE(y, ad0, bd[1], false);
+              }
+              if (y == 0) {
+                mbar_wait_a(full_a + 8u * (uint32_t)sl[2], sp[2]);
+                mbar_wait_a(full_a + 8u * (uint32_t)sl[3], sp[3]);
+                tc_fence_after();
+              }
+              if (elected) {
+                if (!dbg_skip_mma) {
+                  RX_ISSUE(y, ad1, bd[2], false);
+                  RX_ISSUE(y, ad1 + (uint64_t)kRxLoUnits, bd[2], false);
+                  RX_ISSUE(y, ad1, bd[3], false);
+                }
+                if (!head) umma_commit_a(acc_a + 8u * (uint32_t)y);
+              }
+            }
+          }
+          if (elected) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_commit_a(empty_a + 8u * (uint32_t)sl[k]);
+          }
+          __syncwarp();
+          for (int k = 0; k < 4; ++k)
+            if (++slot == kRxSlots) { slot = 0; sphase ^= 1u; }
+          ++b;
+          continue;
+        }
         const int slot_lo = slot + 1 == kRxSlots ? 0 : slot + 1;
         const uint32_t sphase_lo = slot + 1 == kRxSlots ? sphase ^ 1u : sphase;
         const uint64_t bd_hi = b_desc0 + (uint64_t)(uint32_t)(slot * kRtBlockUnits);

@@ -117,9 +117,12 @@ int caro_net_set_grid_limit(caro_net* net, int ctas);
  *             3 = tcgen05 bf16 tower, tap-per-MMA kernel for every board size (A/B comparisons),
  *             2 = split-precision tcgen05 tower (hi / lo pairs of activations and weights, 3 MMAs per product:
  *                 fp32-class accuracy for trained checkpoints with large logits).  Boards up to 6 x 7 run the
- *                 row-tiled fp16 hi + lo kernel (net_rx.cu, ~2.2x the one-pass time), larger ones the
+ *                 row-tiled fp16 hi + lo kernel (net_rx.cu, ~2.3x the one-pass time), larger ones the
  *                 tap-per-MMA bf16 hi + lo kernel (net_tc.cu, ~3.5x),
  *             4 = the tap-per-MMA split-precision kernel for every board size (A/B comparisons),
+ *             5 = the row-tiled bf16 tower as CTA pairs (tcgen05 cta_group::2: clusters of two CTAs, each fetching half of
+ *                 every B operand; bit-identical to impl 0, boards up to 6 x 7 only; measured slower than impl 0, kept for
+ *                 A/B runs -- CARO_RT_PAIR=1 in the environment makes impl 0 use it),
  *             1 = fp32 SIMT tower (numerics reference kernel used by the tests). */
 int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards,
                      const uint8_t* d_who, const int32_t* d_count, int64_t max_count,

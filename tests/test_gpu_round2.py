@@ -282,6 +282,42 @@ def test_split_precision_row_tiled_tower(torch_cuda):
         dn.close()
 
 
+def test_cta_pair_tower_is_bit_identical(torch_cuda):
+    """impl 5 = the row-tiled bf16 tower run by clusters of two CTAs (tcgen05 cta_group::2: one MMA stream of M = 256, each
+    CTA stores and fetches half of every B operand, accumulators zeroed by the epilogues instead of overwritten by the first
+    MMA): the same products summed in the same order as impl 0, so priors and values must be BIT-identical -- for every
+    geometry class (Connect4, pitch-4 3x3, 4x3-in-a-row, 6x6), odd and ragged group counts (a peer CTA with an empty group),
+    several passes per pair, and with an SM limit (an odd one leaves one SM out of the pairs)."""
+    torch = torch_cuda
+    from test_gpu_parity import _random_net
+    from harness import random_position
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(33)
+    cases = [(ConnectFour(), (2, 17, 33, 47, 2400, 9473)), (TicTacToe(3, 3), (33, 65, 4800)), (TicTacToe(4, 3), (40,)),
+             (TicTacToe(6, 4), (37, 700))]
+    for game, counts in cases:
+        og = oracle_for(game)
+        cells = game.obs_shape[1] * game.obs_shape[2]
+        dn = DeviceNet(_random_net(game), game, precision="bf16")
+        base = [random_position(og, rng, int(rng.integers(0, max(1, cells - 3)))) for _ in range(200)]
+        for count in counts:
+            pos = [base[i % len(base)] for i in range(count)]
+            states, players = [p[0] for p in pos], [p[1] for p in pos]
+            p0, v0 = dn.forward_states(states, players, impl=0)
+            p5, v5 = dn.forward_states(states, players, impl=5)
+            torch.cuda.synchronize()
+            assert torch.equal(p0, p5) and torch.equal(v0, v5), (game.obs_shape, count)
+        for limit in (6, 7, 0):
+            dn.set_grid_limit(limit)
+            pos = [base[i % len(base)] for i in range(1500)]
+            p0, v0 = dn.forward_states([p[0] for p in pos], [p[1] for p in pos], impl=0)
+            p5, v5 = dn.forward_states([p[0] for p in pos], [p[1] for p in pos], impl=5)
+            torch.cuda.synchronize()
+            assert torch.equal(p0, p5) and torch.equal(v0, v5), (game.obs_shape, "limit", limit)
+        dn.close()
+
+
 def test_caro_heads_on_tensor_cores(torch_cuda):
     """Boards larger than 8 x 8 (Caro 15 x 15, 9 x 9) evaluate their FC heads as one split-precision tcgen05 GEMM per 128
     leaves (net_heads.cu) from features the tower exports: priors and values vs PyTorch fp32 at 1e-3 and vs the fp32 SIMT
