@@ -9,19 +9,21 @@
 // three MMAs per product on the same operand layout, tile mapping and stacked-tap trick as net_rt.cu (M-tile = one
 // board row of 16 boards, B = [w(dy=+1) | w(dy=0) | w(dy=-1)], 128 x 192 x 16 MMAs into three adjacent accumulators).
 // The residual stream v <- v + lrelu(conv(v)) IS the hi + lo pair in shared memory (no TMEM copy, no e5m2 tail).
-// Measured against PyTorch fp32 on the shipped Connect4 checkpoint: priors 4e-5, values 2e-5 (CPU emulation 3.9e-5).
+// Measured against PyTorch fp32 on the shipped Connect4 checkpoint: priors 1.9e-4, values 1.7e-4 (tools/net_check.py).
 //
 // What differs from net_rt.cu is the schedule.  Two activation images (hi, lo: 2 x 98,816 B) leave 33 KB of the SM's
 // shared memory, so a layer's weights (12 blocks x {hi, lo} x 6 KB = 144 KB) cannot be resident: they STREAM through a
-// ring of three 6 KB slots, and the MMA order is block-major -- for every (horizontal tap, k-step) block all H tiles
-// issue their MMAs while the block is in the ring (hi block: a_hi w_hi and a_lo w_hi for every tile, then lo block:
-// a_hi w_lo), so every weight byte is fetched from L2 once per group and layer.  All H accumulators are live for the
-// whole layer; the epilogue of tile y starts when the last block has passed tile y + 1, the next layer's first block
-// chases the epilogues through the tiles (the first and the last block of a layer are issued tile-major for that reason).
-// The tensor pipe has 3 x the work of the bf16 tower and the epilogue only overlaps with the first and last block of a
-// layer.  Measured (tools/net_bench.py, tools/rx_probe.py, 9,472 leaves): 0.385 ms = 3.0 x the bf16 tower (0.128 ms) and
-// 0.59 x the tap-per-MMA split kernel (0.648 ms); MMA stream alone 0.334 ms (0.306 ms with the ring preloaded): a block
-// of 18 MMAs takes ~2,300 cycles against a tensor floor of 1,536 whatever the issue order or the number of commits.
+// ring of five 6 KB slots (the head features and the FC scratch live in global memory to make room), and the MMA order
+// is block-major -- for every (horizontal tap, k-step) block all H tiles issue their MMAs while the block is in the ring
+// (hi block: a_hi w_hi and a_lo w_hi for every tile, then lo block: a_hi w_lo), so every weight byte is fetched from L2
+// once per group and layer.  All H accumulators are live for the whole layer; the epilogue of tile y starts when the last
+// block has passed tile y + 1, the next layer's first blocks chase the epilogues through the tiles: the first two and the
+// last two blocks of a layer are issued tile-major for that reason (one and one with fewer than five slots or in conv_in).
+// The kernel is templated on the board height: with run-time H the issuing thread, not the tensor pipe, set the pace
+// (a block of 18 MMAs took ~2,300 cycles against a tensor floor of 1,536 whatever the issue order, the ring depth or the
+// number of commits; with H = 6 folded into the code it takes 1,544).  Measured (tools/net_bench.py, tools/rx_probe.py,
+// 9,472 leaves): 0.300 ms = 2.3 x the bf16 tower (0.130 ms) and 0.46 x the tap-per-MMA split kernel (0.648 ms); 0.385 ms
+// before the specialisation.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -43,7 +45,7 @@ namespace caro {
 #ifndef CARO_RX_SLOTS
 #define CARO_RX_SLOTS 5
 #endif
-constexpr int kRxSlots = CARO_RX_SLOTS;                                   // weight ring: three 6 KB blocks
+constexpr int kRxSlots = CARO_RX_SLOTS;                                   // weight ring: 6 KB blocks
 constexpr int kRxLayerBlocks = 24;                            // 12 (dx, k-step) blocks x {hi, lo}
 constexpr int kRxInBlocks = 6;                                // conv_in: 3 dx blocks x {hi, lo}
 constexpr uint32_t kRxLoUnits = kRtActBytes / 16;             // descriptor offset of the lo activation image
@@ -217,11 +219,12 @@ net_rx_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
     }                                                                                                                    \
   } while (0)
     // Schedule of a layer (nblk = 12 weight blocks, 3 for conv_in; block b = {hi, lo} in two ring slots):
-    //   block 0        tile-major: tile y issues all its MMAs as soon as the previous layer's epilogues of tiles y-1 .. y+1 are
-    //                  done (rows rewritten, accumulators drained) -- it chases the epilogues through the tiles;
-    //   blocks 1..n-2  block-major: the hi part (a_hi w_hi, a_lo w_hi for every tile) releases the hi slot before the lo
-    //                  part (a_hi w_lo) runs, so that the ring (3 slots) always has the next block in flight;
-    //   block n-1      tile-major again, with a commit per tile: the epilogue of tile y starts while tiles y+2 .. are issued.
+    //   blocks 0, 1      tile-major (block 0 only in conv_in / with a short ring): tile y issues all its MMAs as soon as the previous
+    //                    layer's epilogues of tiles y-1 .. y+1 are done (rows rewritten, accumulators drained) -- it chases the
+    //                    epilogues through the tiles;
+    //   middle blocks    block-major: the hi part (a_hi w_hi, a_lo w_hi for every tile) releases the hi slot before the lo
+    //                    part (a_hi w_lo) runs, so that the ring always has the next blocks in flight;
+    //   blocks n-2, n-1  tile-major again, with a commit per tile: the epilogue of tile y starts while tiles y+2 .. are issued.
     for (int gl = 0; gl < total_layers; ++gl) {
       const uint32_t par = (uint32_t)gl & 1u;
       const bool first = layer == 0;
