@@ -27,6 +27,14 @@
 //   * biases and 1x1 head weights come through the constant cache (__grid_constant__ struct), the last layer
 //     stores every head feature exactly once (tiles split by parity between the two channel halves): no
 //     shared-memory atomics, bit-identical results from run to run.
+//
+// What bounds it (round 2): the EPILOGUE CHAIN -- the same eight warps rewrite the six tiles of a layer
+// back to back, ~1,050 cycles of work (344 SASS instructions per thread) + ~230 cycles of barrier / fence / loop per tile =
+// ~7,660 cycles per layer against a tensor floor of 6,144, with the MMA warp far ahead.  Two template switches:
+//   HC    the board height as a compile-time constant (6): the MMA warp's tile loop unrolled, every position test folded;
+//   PAIR  two CTAs of a cluster run ONE cta_group::2 MMA stream (M = 256, each CTA stores and fetches half of every B
+//         operand: 30 % fewer operand wavefronts, half the bank conflicts, bit-identical results) -- 7 % slower, because the
+//         pair couples two epilogue chains and shared memory was not the limit; kept as impl 5 / CARO_RT_PAIR=1 for A/B runs.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>

@@ -49,7 +49,8 @@ __host__ __device__ constexpr uint32_t rt_idesc_pair(uint32_t n) {
 constexpr int kRtPairRows = 224;
 constexpr int kRtPairBlockBytes = 2 * kRtPairRows * 16;       // 7,168
 constexpr uint32_t kRtPairTop = 96, kRtPairBottom = 160;      // window starts in rows (= descriptor units)
-constexpr int kRtScratchSlots = 8;                            // launches of the pair form that may be in flight at once
+constexpr int kRtScratchSlots = 16;                           // launches of one network that may be in flight at once (net_rx.cu, pair form):
+                                                              // their head features / FC scratch live in global memory, one slot per launch, round robin
 
 struct RtGeom {
   int H, W, A, pitch, pshift, nb;
