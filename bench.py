@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+TRAINED_C4 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "checkpoints", "connect4_best_026_12000.dat")
 FLOP_PER_LEAF_C4 = 15598672  # conv_in 96,768*... + 5 x 3,096,576*... + heads (2 x MAC)
 SIMS_COUNT, SIMS_BATCH, TAU_PLIES = 100, 8, 10
 GAMES_PER_GPU = 16384  # two software-pipelined half-batches of 8192 (north_star: >= 4096 concurrent games per GPU; the line at
@@ -272,9 +273,13 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
     from caro_ai_b200.model import DeviceNet, Net
     out = {}
 
-    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, blocks=5, **flags):
+    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, blocks=5, checkpoint=None, **flags):
         torch.manual_seed(0)
-        dn = DeviceNet(Net(game.obs_shape, game.action_space, blocks=blocks).eval(), game)
+        if checkpoint is not None:  # a TRAINED network: precision "auto" has to pick the split-precision tower for it
+            from caro_ai_b200.model import load_checkpoint
+            dn = DeviceNet(load_checkpoint(checkpoint, game).eval(), game)
+        else:
+            dn = DeviceNet(Net(game.obs_shape, game.action_space, blocks=blocks).eval(), game)
         engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h + 101 * rank, **flags)
                 for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=warm, count=count, batch=batch, tau_plies=TAU_PLIES, auto_restart=True)
@@ -304,6 +309,9 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
         run("connect4_4096_games", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)")
         run("connect4_4096_games_virtual_loss", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)",
             virtual_loss=True, mask_priors=True)
+        if os.path.exists(TRAINED_C4):
+            run("connect4_trained_checkpoint", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)",
+                checkpoint=TRAINED_C4)
         run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)")
         run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)", blocks=10)
         return out
@@ -313,6 +321,12 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
         "EXTENSION, not the reference's search (CARO_FLAG_VIRTUAL_LOSS + MASK_PRIORS): 4,096 games per GPU, search_batch(100,8); nearly "
         "every descent reaches the network, so a ply costs ~3x the leaf evaluations of the reference-compatible search",
         virtual_loss=True, mask_priors=True)
+    if os.path.exists(TRAINED_C4):
+        run("connect4_trained_checkpoint", ConnectFour(), 2, 8192, SIMS_COUNT, SIMS_BATCH, 8192, 2, 6,
+            "the headline workload (2 x 8,192 games, search_batch(100,8)) with the reference's TRAINED Connect4 checkpoint "
+            "best_026_12000.dat instead of a random-init network: DeviceNet(precision='auto') measures the one-pass bf16 tower at "
+            "0.24 off fp32 on it and selects the split-precision tower (fp16 hi + lo, 3 MMAs per product, net_rx.cu)",
+            checkpoint=TRAINED_C4)
     run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 3,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
         "2,048 concurrent games per GPU (2 pipeline parts of 1,024)")
