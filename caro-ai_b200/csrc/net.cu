@@ -191,6 +191,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_tc_weights = nullptr;
   net->d_rt_weights = nullptr;
   net->d_rt_pair_weights = nullptr;
+  net->d_tc_pair_weights = nullptr;
   net->d_rt_scratch = nullptr;
   net->rt_scratch_seq = 0;
   net->d_rx_weights = nullptr;
@@ -278,8 +279,9 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
     return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 5, st);
   if (impl == 2 && caro_net_rt_supports(net))
     return caro_net_rx_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
-  if (impl == 0 || impl == 2 || impl == 3 || impl == 4)
-    return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, (impl == 2 || impl == 4) ? 1 : 0, st);
+  if (impl == 0 || impl == 2 || impl == 3 || impl == 4 || impl == 6)
+    return caro_net_tc_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values,
+                               (impl == 2 || impl == 4) ? 1 : impl == 6 ? 2 : 0, st);
   return caro_fail(CARO_E_ARG, "unknown net impl");
 }
 

@@ -58,6 +58,7 @@ struct caro_net {
   float* d_blob;        // fp32 folded weights (SIMT tower + heads of both towers)
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
+  void* d_tc_pair_weights;  // tap-per-MMA tower as CTA pairs: one compact bf16 image per cluster rank
   void* d_rt_pair_weights;  // the same for the CTA-pair form: one image per cluster rank, 7 KB blocks
   void* d_rt_scratch;       // CTA-pair form: head features + FC scratch of every CTA, kRtScratchSlots launches in flight
   unsigned rt_scratch_seq;  // next slot (round robin per launch)

@@ -28,6 +28,7 @@
 #include "rules.cuh"
 
 #include "tc_common.cuh"
+#include "rt_common.cuh"
 
 namespace caro {
 
@@ -57,10 +58,19 @@ constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kHeadThreads;
 //           evaluated as hi*hi + lo*hi + hi*lo (fp32 accumulate), ~16 mantissa bits instead of 8.  Needed for
 //           trained checkpoints whose policy logits span +-100; 3x the tensor work and twice
 //           the shared memory per row, hence 2 tiles per pass and a single (hi+lo) weight buffer.
-template <int TILES, bool SPLIT>
+//   PAIR  = two CTAs of a cluster run ONE cta_group::2 MMA stream of M = 256 (each CTA its own boards, accumulators, epilogue
+//           and heads); each CTA stores and fetches only its 32 of the 64 output channels of every tap, 4 + 1 KB per MMA instead
+//           of 4 + 2 -- this kernel IS bound by the shared-memory pipe (operand fetch 48 cycles per 32-cycle MMA).
+template <int TILES, bool SPLIT, bool PAIR_ = false>
 struct TcCfg {
   static constexpr int kTiles = TILES;
   static constexpr bool kSplit = SPLIT;
+  static constexpr bool kPair = PAIR_;
+  static_assert(!(SPLIT && PAIR_), "the pair form exists for the one-pass mode only");
+  static constexpr int kBRows = PAIR_ ? 32 : 64;                    // B rows (output channels) a CTA stores per tap
+  static constexpr int kTapB = 8 * kBRows * 16;                     // bytes of one tap of a 64 -> 64 layer
+  static constexpr int kTapBIn = 2 * kBRows * 16;                   // conv_in (K padded to 16)
+  static constexpr int kLayerB = 9 * kTapB;
   static constexpr int kGroupRows = TILES * kTileRows;
   static constexpr int kActRows = kGroupRows + 2 * kHalo;
   static constexpr int kChunkBytes = kActRows * 16;      // one 8-channel chunk of all positions
@@ -68,7 +78,7 @@ struct TcCfg {
   static constexpr int kActBufs = SPLIT ? 2 : 1;
   static constexpr int kWStages = SPLIT ? 1 : 2;         // weight buffers in flight
   static constexpr int kWParts = SPLIT ? 2 : 1;          // hi (+ lo) images per layer
-  static constexpr int kWStageBytes = kWParts * kLayerBytes;
+  static constexpr int kWStageBytes = kWParts * kLayerB;
   static constexpr uint32_t kTmemCols = 2 * TILES * 64;  // accumulators + fp32 residual stream
   // dynamic shared memory carve-up (byte offsets from a 128-aligned base)
   static constexpr int kAct = 0;
@@ -85,6 +95,7 @@ struct TcCfg {
 };
 using TcFast = TcCfg<4, false>;
 using TcExact = TcCfg<2, true>;
+using TcPair = TcCfg<4, false, true>;
 
 
 // Large boards (Caro 15x15: 225 actions, 450 x 225 policy FC) do not run their FC heads inside the tower: two head warps
@@ -157,15 +168,24 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   uint64_t* bar_act = bar_w + 6;                                        // [4] activation tile rewritten / accumulator drained
   uint64_t* bar_feat = bar_w + 10;                                      // [0] head features complete, [1] consumed + re-zeroed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 12);
+  uint64_t* bar_wp = bar_w + 13;                                        // [2] PAIR, leader: the peer's weights buffer filled
   uint16_t* cell_tab = reinterpret_cast<uint16_t*>(smem + K::kCellTab);
+  constexpr bool PAIR = K::kPair;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const long long count = d_count ? min((long long)*d_count, max_count) : max_count;
   const int nb = gm.boards_per_group;
   const long long n_groups = (count + nb - 1) / nb;
-  if ((long long)blockIdx.x >= n_groups) return;  // uniform per CTA, before any barrier / TMEM use
-  const int my_groups = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // PAIR: the unit of work is a PAIR of groups, the CTA of rank r takes the r-th; an odd tail leaves the peer an empty group
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const long long unit = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long n_units = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const long long work = PAIR ? (n_groups + 1) / 2 : n_groups;
+  if (unit >= work) return;  // uniform per CTA (pair), before any barrier / TMEM use
+  const int my_groups = (int)((work - unit + n_units - 1) / n_units);
+  auto group_leaf0 = [&](int gi) { return ((unit + (long long)gi * n_units) * (PAIR ? 2 : 1) + rank) * nb; };
+  auto group_valid = [&](long long leaf0) { return (int)max(0ll, min((long long)nb, count - leaf0)); };
 
   // ---- one-time setup ---------------------------------------------------------------------
   for (int i = tid; i < K::kActBufs * K::kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
@@ -188,9 +208,11 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     headw_s[194] = blob[L.pol_conv_b + 1];
     mbar_init(bar_w + 0, 1);
     mbar_init(bar_w + 1, 1);
+    mbar_init(bar_wp + 0, 1);
+    mbar_init(bar_wp + 1, 1);
     for (int t = 0; t < 4; ++t) {
       mbar_init(bar_acc + t, 1);
-      mbar_init(bar_act + t, kEpiThreads);
+      mbar_init(bar_act + t, PAIR ? 2 * kEpiWarps : kEpiThreads);  // PAIR: one arrival per epilogue warp of either CTA
     }
     mbar_init(bar_feat + 0, kEpiThreads);
     mbar_init(bar_feat + 1, kHeadThreads);
@@ -198,13 +220,20 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   }
   if (warp == kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything reaches across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -213,8 +242,8 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     // group of a CTA is left to the epilogue warps (4x the threads, and they are idle by then) ==================
     const int htid = tid - kHeadWarp * 32;
     for (int gi = 0; gi + 1 < my_groups; ++gi) {
-      const long long leaf0 = (blockIdx.x + (long long)gi * gridDim.x) * nb;
-      const int nvalid = (int)min((long long)nb, count - leaf0);
+      const long long leaf0 = group_leaf0(gi);
+      const int nvalid = group_valid(leaf0);
       mbar_wait(bar_feat + 0, (uint32_t)gi & 1u);
       if (headfeat_out != nullptr) export_heads<kHeadThreads, 2>(gm, nvalid, leaf0, htid, headf_s, headw_s, headfeat_out, headfeat_lo_off, headfeat_kc8);
       else run_heads<kHeadThreads, 2>(gm, nb, nvalid, leaf0, htid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
@@ -234,29 +263,56 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       const int l = gl % n_layers;
       uint8_t* dst = wgt + (gl % K::kWStages) * K::kWStageBytes;
       uint64_t* bar = bar_w + (gl % K::kWStages);
-      const int tap_bytes = l == 0 ? kTapBytesIn : kTapBytes;
+      const int tap_bytes = l == 0 ? K::kTapBIn : K::kTapB;
       const int layer_bytes = 9 * tap_bytes;
-      // global image: conv_in {hi, lo}, then per block {hi, lo}
-      const uint8_t* src = l == 0 ? wimg : wimg + 2 * kLayerBytesIn + (size_t)(l - 1) * 2 * kLayerBytes;
+      // global image: conv_in {hi, lo}, then per block {hi, lo}; PAIR: one compact image per rank, hi only, half the rows per tap
+      const uint8_t* src = PAIR ? wimg + (size_t)rank * (9 * K::kTapBIn + (size_t)(n_layers - 1) * K::kLayerB) +
+                                      (l == 0 ? 0 : 9 * K::kTapBIn + (size_t)(l - 1) * K::kLayerB)
+                                : (l == 0 ? wimg : wimg + 2 * kLayerBytesIn + (size_t)(l - 1) * 2 * kLayerBytes);
       mbar_expect_tx(bar, (uint32_t)(K::kWParts * layer_bytes));
       for (int part = 0; part < K::kWParts; ++part)
         for (int tap = 0; tap < 9; ++tap)
-          bulk_g2s(dst + part * kLayerBytes + tap * tap_bytes, src + (size_t)part * layer_bytes + tap * tap_bytes, tap_bytes, bar);
+          bulk_g2s(dst + part * K::kLayerB + tap * tap_bytes, src + (size_t)part * layer_bytes + tap * tap_bytes, tap_bytes, bar);
     };
     if (mw == 1 && elected) {
       load_layer(0);
       if (K::kWStages > 1 && total_layers > 1) load_layer(1);
     }
+    if (PAIR && rank != 0) {
+      // PAIR, peer CTA: the leader issues the MMAs of both.  Warp 9 keeps streaming this CTA's half of the weights -- layer gl+1
+      // as soon as every tile of layer gl-1 has committed (the multicast commits arrive here too): its buffer is free then --,
+      // warp 8 reports "weights landed" to the leader (a local wait, then one remote arrive per layer).
+      if (mw == 1 && elected) {
+        for (int gl = 1; gl + 1 < total_layers; ++gl) {
+          for (int t = 0; t < K::kTiles; ++t) mbar_wait(bar_acc + t, (uint32_t)(gl - 1) & 1u);
+          load_layer(gl + 1);
+        }
+      }
+      if (mw == 0 && elected) {
+        const uint32_t wp_leader = mapa_a(smem_u32(bar_wp), 0u);
+        for (int gl = 0; gl < total_layers; ++gl) {
+          mbar_wait(bar_w + (gl % K::kWStages), (uint32_t)(gl / K::kWStages) & 1u);
+          mbar_arrive_cluster_a(wp_leader + 8u * (uint32_t)(gl % K::kWStages));
+        }
+      }
+      __syncwarp();
+    } else {
     // descriptor templates: only the 14-bit start-address field (units of 16 B) changes per MMA
     const uint64_t a_desc0 = make_desc(act_addr + (uint32_t)kHalo * 16u, K::kChunkBytes, 128u);
-    const uint64_t b_desc0 = make_desc(wgt_addr, 1024u, 128u);
+    const uint64_t b_desc0 = make_desc(wgt_addr, (uint32_t)K::kBRows * 16u, 128u);
     constexpr uint64_t kALo = (uint64_t)(K::kActBytes / 16);   // lo activation image
-    constexpr uint64_t kBLo = (uint64_t)(kLayerBytes / 16);    // lo weight image
+    constexpr uint64_t kBLo = (uint64_t)(K::kLayerB / 16);     // lo weight image
+    // one MMA of this kernel: cta_group::1 (M = 128) or, PAIR, cta_group::2 (M = 256 over both CTAs, half of B from each)
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+      if (PAIR) umma_bf16_pair(d, ad, bd, rt_idesc_pair(64), acc);
+      else umma_bf16(d, ad, bd, kIdesc, acc);
+    };
     const int pitch = gm.pitch;
     for (int gl = 0; gl < total_layers; ++gl) {
       const bool first = (gl % n_layers) == 0;
       const uint64_t b_layer = b_desc0 + (uint64_t)((uint32_t)(gl % K::kWStages) * (K::kWStageBytes / 16));
       mbar_wait(bar_w + (gl % K::kWStages), (uint32_t)(gl / K::kWStages) & 1u);
+      if (PAIR) mbar_wait(bar_wp + (gl % K::kWStages), (uint32_t)(gl / K::kWStages) & 1u);
       if (elected) TC_TRACE(6, gl * 2 + mw);  // weights present
       const uint32_t act_par = (uint32_t)gl & 1u;  // stage gl of bar_act = "input / epilogue of layer gl-1"
 #pragma unroll 1
@@ -275,9 +331,9 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             for (int tap = 0; tap < 9; ++tap) {
               const int sh = (tap / 3 - 1) * pitch + (tap % 3 - 1);
               const uint64_t ad = a_tile + (uint64_t)(int64_t)sh;
-              const uint64_t bd = b_layer + (uint64_t)(tap * (kTapBytesIn / 16));
-              umma_bf16(d_tmem, ad, bd, kIdesc, tap > 0 ? 1u : 0u);
-              if (K::kSplit) umma_bf16(d_tmem, ad, bd + kBLo, kIdesc, 1u);
+              const uint64_t bd = b_layer + (uint64_t)(tap * (K::kTapBIn / 16));
+              mma(d_tmem, ad, bd, tap > 0 ? 1u : 0u);
+              if (K::kSplit) mma(d_tmem, ad, bd + kBLo, 1u);
             }
           } else {
 #pragma unroll
@@ -286,16 +342,17 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 const uint64_t ad = a_tile + (uint64_t)(int64_t)(sh + kk * 2 * K::kActRows);
-                const uint64_t bd = b_layer + (uint64_t)(tap * (kTapBytes / 16) + kk * (2048 / 16));
-                umma_bf16(d_tmem, ad, bd, kIdesc, (tap | kk) ? 1u : 0u);
+                const uint64_t bd = b_layer + (uint64_t)(tap * (K::kTapB / 16) + kk * (2 * K::kBRows));
+                mma(d_tmem, ad, bd, (tap | kk) ? 1u : 0u);
                 if (K::kSplit) {
-                  umma_bf16(d_tmem, ad + kALo, bd, kIdesc, 1u);   // lo(a) * hi(w)
-                  umma_bf16(d_tmem, ad, bd + kBLo, kIdesc, 1u);   // hi(a) * lo(w)
+                  mma(d_tmem, ad + kALo, bd, 1u);   // lo(a) * hi(w)
+                  mma(d_tmem, ad, bd + kBLo, 1u);   // hi(a) * lo(w)
                 }
               }
             }
           }
-          umma_commit(bar_acc + t);
+          if (PAIR) umma_commit_pair_a(smem_u32(bar_acc + t));
+          else umma_commit(bar_acc + t);
           TC_TRACE(1, gl * 4 + t);  // MMA issued + committed
         }
         __syncwarp();
@@ -313,6 +370,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         }
       }
     }
+    }  // leader / single-CTA form
   } else {
     // ========================================= epilogue warps =========================================
     // Code size matters here (the v1 kernel was 127 KB of SASS and lived in instruction-cache misses):
@@ -322,6 +380,16 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int HW = gm.H * gm.W;
     float* featc = headf_s;  // dense head features [board][3][HW], accumulated by the two column halves
+    // "tile t rewritten, accumulator drained".  PAIR: the barrier lives in the leader CTA and counts WARPS of both CTAs
+    const uint32_t act_leader = PAIR ? mapa_a(smem_u32(bar_act), 0u) : 0u;
+    auto act_arrive = [&](int t) {
+      if (PAIR) {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_cluster_a(act_leader + 8u * (uint32_t)t);
+      } else {
+        mbar_arrive(bar_act + t);
+      }
+    };
 
     auto write_inputs = [&](long long leaf0) {
 #pragma unroll 1
@@ -343,14 +411,13 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
         }
         *reinterpret_cast<uint4*>(act + (size_t)(half * K::kActRows + kHalo + p) * 16) = make_uint4(lo, 0u, 0u, 0u);
         fence_async_smem();
-        mbar_arrive(bar_act + t);
+        act_arrive(t);
       }
     };
 
-    write_inputs((long long)blockIdx.x * nb);
+    write_inputs(group_leaf0(0));
     for (int gi = 0; gi < my_groups; ++gi) {
-      const long long grp = blockIdx.x + (long long)gi * gridDim.x;
-      const long long leaf0 = grp * nb;
+      const long long leaf0 = group_leaf0(gi);
 #pragma unroll 1
       for (int layer = 0; layer < n_layers; ++layer) {
         const int gl = gi * n_layers + layer;
@@ -418,7 +485,7 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_act + t);
+            act_arrive(t);
             if (tid == 0) TC_TRACE(3, gl * 4 + t);  // epilogue done (warp 0)
           } else {
             // 1x1 head convolutions: this thread holds 32 of the 64 channels, the partner warp the rest
@@ -446,12 +513,12 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
       tc_fence_before();  // the last layer's accumulators have been read (wait::ld above)
       if (gi + 1 < my_groups) {
         mbar_arrive(bar_feat + 0);  // this thread's head features are in place (release) -> head warps
-        write_inputs((blockIdx.x + (long long)(gi + 1) * gridDim.x) * nb);
+        write_inputs(group_leaf0(gi + 1));
         if (tid == 0) TC_TRACE(4, gi);  // last-layer epilogue + next inputs done
       } else {
         // last group of this CTA: nothing left to overlap with, so all eight epilogue warps do the heads
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int nvalid = (int)min((long long)nb, count - leaf0);
+        const int nvalid = group_valid(leaf0);
         if (headfeat_out != nullptr) export_heads<kEpiThreads, 1>(gm, nvalid, leaf0, tid, headf_s, headw_s, headfeat_out, headfeat_lo_off, headfeat_kc8);
         else run_heads<kEpiThreads, 1>(gm, nb, nvalid, leaf0, tid, headf_s, fc_s, headw_s, blob, L, pol_fc_t, val_fc1_t, probs, values);
         if (tid == 0) TC_TRACE(5, gi);
@@ -462,9 +529,11 @@ net_tc_kernel(R rules, TcGeom gm, const typename R::Board* __restrict__ boards, 
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA of a pair leaves (or frees TMEM) while the other may still be signalled or read
   if (warp == kMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::kTmemCols) : "memory");
   }
 }
 
@@ -531,7 +600,26 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
     const int hrc = caro_net_heads_pack(net, h);
     if (hrc != CARO_OK) return hrc;
   }
-  if (!net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
+  // CTA-pair form: one compact image per cluster rank (hi part only): per tap [8-channel chunk][32 of the 64 out channels][8]
+  const size_t pair_bytes = 9 * (size_t)TcPair::kTapBIn + (size_t)blocks * TcPair::kLayerB;
+  std::vector<uint16_t> pimg(2 * pair_bytes / 2, 0);
+  for (int r = 0; r < 2; ++r) {
+    auto copy_taps = [&](size_t src_base, size_t src_tap_bytes, size_t dst_base, size_t dst_tap_bytes, int chunks) {
+      for (int tap = 0; tap < 9; ++tap)
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int row = 0; row < 32; ++row)
+            for (int e = 0; e < 8; ++e)
+              pimg[((size_t)r * pair_bytes + dst_base + tap * dst_tap_bytes + (size_t)(ch * 32 + row) * 16) / 2 + e] =
+                  img[(src_base + tap * src_tap_bytes + (size_t)(ch * 64 + 32 * r + row) * 16) / 2 + e];
+    };
+    copy_taps(0, kTapBytesIn, 0, TcPair::kTapBIn, 2);
+    for (int l = 0; l < blocks; ++l)
+      copy_taps(2 * (size_t)kLayerBytesIn + (size_t)l * 2 * kLayerBytes, kTapBytes, 9 * (size_t)TcPair::kTapBIn + (size_t)l * TcPair::kLayerB,
+                TcPair::kTapB, 8);
+  }
+  if (!net->d_tc_pair_weights) ce = cudaMalloc(&net->d_tc_pair_weights, 2 * pair_bytes);
+  if (ce == cudaSuccess) ce = cudaMemcpy(net->d_tc_pair_weights, pimg.data(), 2 * pair_bytes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && !net->d_tc_weights) ce = cudaMalloc(&net->d_tc_weights, img_bytes);
   if (ce == cudaSuccess && !net->d_tc_bias) ce = cudaMalloc(&net->d_tc_bias, bias.size() * sizeof(float));
   if (ce == cudaSuccess && !net->d_pol_fc_t) ce = cudaMalloc(&net->d_pol_fc_t, polt.size() * sizeof(float));
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_tc_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
@@ -543,6 +631,8 @@ int caro_net_tc_pack(caro_net* net, const float* h) {
 
 void caro_net_tc_free(caro_net* net) {
   if (net->d_tc_weights) cudaFree(net->d_tc_weights);
+  if (net->d_tc_pair_weights) cudaFree(net->d_tc_pair_weights);
+  net->d_tc_pair_weights = nullptr;
   if (net->d_tc_bias) cudaFree(net->d_tc_bias);
   if (net->d_pol_fc_t) cudaFree(net->d_pol_fc_t);
   if (net->d_headfeat) cudaFree(net->d_headfeat);
@@ -579,10 +669,34 @@ static int launch_tc(const R& rules, caro_net* net, const void* boards, const ui
   const size_t image = (size_t)net->headfeat_leaves * kc64 * 64 * 2;  // bytes of one (hi or lo) image of a slot
   if (net->d_headfeat != nullptr && max_count <= net->headfeat_leaves)
     headfeat = (uint8_t*)net->d_headfeat + (size_t)(net->headfeat_seq++ % kHeadfeatSlots) * 2 * image;
-  kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
-                                          (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
-                                          net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat, image,
-                                          kc64 * 8, (long long*)net->d_trace);
+  if (K::kPair) {  // clusters of two CTAs (one TPC each)
+    const long long max_units = (max_groups + 1) / 2;
+    const long long max_pairs = sm_count / 2 > 0 ? sm_count / 2 : 1;
+    const unsigned pairs = (unsigned)(max_units < max_pairs ? max_units : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = K::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
+                                              (const uint8_t*)net->d_tc_pair_weights, (const float*)net->d_tc_bias, (const float*)net->d_blob,
+                                              net->layout, (const float*)net->d_pol_fc_t,
+                                              (const float*)(net->d_pol_fc_t + (size_t)2 * HW * net->A), probs, values, headfeat, image,
+                                              kc64 * 8, (long long*)net->d_trace);
+    if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
+  } else {
+    kern<<<grid, kThreads, K::kTotal, st>>>(rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count,
+                                            (const uint8_t*)net->d_tc_weights, net->d_tc_bias, net->d_blob, net->layout,
+                                            net->d_pol_fc_t, net->d_pol_fc_t + (size_t)2 * HW * net->A, probs, values, headfeat, image,
+                                            kc64 * 8, (long long*)net->d_trace);
+  }
   int rc = caro_check_launch("net_tc_kernel");
   if (rc == CARO_OK && headfeat != nullptr) rc = caro_net_heads_forward(net, headfeat, image, d_count, max_count, probs, values, st);
   return rc;
@@ -595,16 +709,23 @@ int caro_net_tc_prepare() {
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcFast::kTotal);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcExact::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<C4Rules, TcPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPair::kTotal);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(net_tc_kernel<MnkRules, TcPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPair::kTotal);
   if (ce != cudaSuccess) return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
   return CARO_OK;
 }
 
 int caro_net_tc_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
                         const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int exact, cudaStream_t st) {
+  // exact: 0 = one pass, 1 = split precision, 2 = one pass as CTA pairs (cta_group::2); CARO_TC_PAIR=1 turns 0 into 2
+  static const bool pair_env = getenv("CARO_TC_PAIR") ? atoi(getenv("CARO_TC_PAIR")) != 0 : false;
+  if (exact == 0 && pair_env) exact = 2;
   if (game == CARO_GAME_CONNECT4) {
-    if (exact) return launch_tc<C4Rules, TcExact>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+    if (exact == 1) return launch_tc<C4Rules, TcExact>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+    if (exact == 2) return launch_tc<C4Rules, TcPair>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
     return launch_tc<C4Rules, TcFast>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   }
-  if (exact) return launch_tc<MnkRules, TcExact>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if (exact == 1) return launch_tc<MnkRules, TcExact>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
+  if (exact == 2) return launch_tc<MnkRules, TcPair>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   return launch_tc<MnkRules, TcFast>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
 }

@@ -123,6 +123,9 @@ int caro_net_set_grid_limit(caro_net* net, int ctas);
  *             5 = the row-tiled bf16 tower as CTA pairs (tcgen05 cta_group::2: clusters of two CTAs, each fetching half of
  *                 every B operand; bit-identical to impl 0, boards up to 6 x 7 only; measured slower than impl 0, kept for
  *                 A/B runs -- CARO_RT_PAIR=1 in the environment makes impl 0 use it),
+ *             6 = the tap-per-MMA bf16 tower as CTA pairs (each CTA stores 32 of the 64 output channels of every tap; bit-identical
+ *                 to impl 3; no faster stand-alone -- an M = 128, K = 16 MMA takes 48 cycles whatever N <= 64 is --, +1.5 % inside the
+ *                 Caro self-play step; CARO_TC_PAIR=1 makes impl 0 / 3 use it),
  *             1 = fp32 SIMT tower (numerics reference kernel used by the tests). */
 int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards,
                      const uint8_t* d_who, const int32_t* d_count, int64_t max_count,

@@ -316,6 +316,20 @@ def test_cta_pair_tower_is_bit_identical(torch_cuda):
             torch.cuda.synchronize()
             assert torch.equal(p0, p5) and torch.equal(v0, v5), (game.obs_shape, "limit", limit)
         dn.close()
+    # the tap-per-MMA tower (large boards) has the same switch: impl 6 = impl 3 as CTA pairs, each CTA storing 32 of the 64
+    # output channels of every tap
+    for game, counts in ((TicTacToe(15, 5), (1, 3, 300, 1501)), (TicTacToe(9, 5), (7, 2000)), (ConnectFour(), (17, 1000))):
+        og = oracle_for(game)
+        dn = DeviceNet(_random_net(game), game, precision="bf16")
+        base = [random_position(og, rng, int(rng.integers(0, 14))) for _ in range(100)]
+        for count in counts:
+            pos = [base[i % len(base)] for i in range(count)]
+            states, players = [p[0] for p in pos], [p[1] for p in pos]
+            p3, v3 = dn.forward_states(states, players, impl=3)
+            p6, v6 = dn.forward_states(states, players, impl=6)
+            torch.cuda.synchronize()
+            assert torch.equal(p3, p6) and torch.equal(v3, v6), (game.obs_shape, count)
+        dn.close()
 
 
 def test_caro_heads_on_tensor_cores(torch_cuda):
