@@ -304,6 +304,7 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
         for e in engs:
             e.close()
         dn.close()
+        torch.cuda.empty_cache()  # the arenas of one configuration must not stay cached next to the next one's
 
     if small:  # the contract test: the same code on toy sizes
         run("connect4_4096_games", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)")
@@ -330,6 +331,9 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
     run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 3,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
         "2,048 concurrent games per GPU (2 pipeline parts of 1,024)")
+    run("caro_15x15_1600_sims_20_plies", TicTacToe(15, 5), 2, 256, 200, 8, 36864, 1, 20,
+        "the same over 20 timed plies: a game's tree is kept across its moves (the reference's semantics), 21 x 1,600 descents need "
+        "arenas of 36,864 nodes x 3.6 KB per game, so 512 games per GPU (2 parts of 256, 69 GB of arenas) instead of 2,048")
     run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 2,
         "the same with the 'deep residual net' BASELINE configs[3] names and the reference does not define: here 10 residual blocks "
         "of 64 filters (Net(blocks=10); 166.7 MFLOP per leaf)", blocks=10)

@@ -1,6 +1,6 @@
 """Caro 15,15,5 at search_batch(200,8) -- or, with GAME=c4trained, Connect4 at search_batch(100,8) with the reference's trained
 checkpoint (split-precision tower) --: leaf evaluations/s against the number of pipeline parts and games per part.
-Usage: [GAME=c4trained] [NET_SMS=n] [PLIES=n] python tools/caro_sweep.py PARTSxGAMES[:flag] ...   (e.g. 2x1024 3x1024 2x1536:recycle)"""
+Usage: [GAME=c4trained] [NET_SMS=n] [PLIES=n] [CAP=nodes per game] python tools/caro_sweep.py PARTSxGAMES[:flag] ...   (e.g. 2x1024 3x1024 2x1536:recycle)"""
 import json
 import os
 import sys
@@ -30,7 +30,7 @@ def main():
         parts, games = (int(x) for x in spec.split("x"))
         plies = int(os.environ.get("PLIES", "3"))
         flags = {"recycle_tree": True} if flag == "recycle" else {}
-        engs = [SelfPlayEngine(game, games, max_batch=8, node_capacity=8192, seed=7 * h, **flags) for h in range(parts)]
+        engs = [SelfPlayEngine(game, games, max_batch=8, node_capacity=int(os.environ.get("CAP", "8192")), seed=7 * h, **flags) for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=1, count=count, batch=8, tau_plies=10, auto_restart=True)
         torch.cuda.synchronize()
         c0 = [e.counters() for e in engs]
