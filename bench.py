@@ -314,6 +314,7 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
             run("connect4_trained_checkpoint", ConnectFour(), 2, 64, 8, SIMS_BATCH, 2048, 1, 2, "toy size (--extra-small)",
                 checkpoint=TRAINED_C4)
         run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)")
+        run("caro_15x15_1600_sims_20_plies", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 4, "toy size (--extra-small)", compact_tree=True)
         run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 16, 6, 8, 512, 1, 2, "toy size (--extra-small)", blocks=10)
         return out
     run("connect4_4096_games", ConnectFour(), 2, 2048, SIMS_COUNT, SIMS_BATCH, 12288, 3, 12,
@@ -331,9 +332,12 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
     run("caro_15x15_1600_sims", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 3,
         "BASELINE configs[3] shape per GPU: Caro 15,15,5, search_batch(200,8) = 1,600 descents/move, reference-shape 5x64 net, "
         "2,048 concurrent games per GPU (2 pipeline parts of 1,024)")
-    run("caro_15x15_1600_sims_20_plies", TicTacToe(15, 5), 2, 256, 200, 8, 36864, 1, 20,
-        "the same over 20 timed plies: a game's tree is kept across its moves (the reference's semantics), 21 x 1,600 descents need "
-        "arenas of 36,864 nodes x 3.6 KB per game, so 512 games per GPU (2 parts of 256, 69 GB of arenas) instead of 2,048")
+    run("caro_15x15_1600_sims_20_plies", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 20,
+        "the same 2,048 games over 20 timed plies.  A game's tree is kept across its moves (the reference's semantics): 21 x 1,600 "
+        "descents would need 36,864-node arenas of 3.6 KB records (276 GB for 2,048 games), so this run sets CARO_FLAG_COMPACT_TREE: "
+        "after every move the nodes that can no longer be reached are dropped and the arena packed -- every statistic, policy and "
+        "move stays bit-identical to the keep-everything tree (tests/test_gpu_round2.py), the arenas stay below 1,000 nodes",
+        compact_tree=True)
     run("caro_15x15_1600_sims_deep10", TicTacToe(15, 5), 2, 1024, 200, 8, 8192, 1, 2,
         "the same with the 'deep residual net' BASELINE configs[3] names and the reference does not define: here 10 residual blocks "
         "of 64 filters (Net(blocks=10); 166.7 MFLOP per leaf)", blocks=10)

@@ -20,7 +20,7 @@ class EngineConfig(C.Structure):
                 ("explore", C.c_double), ("seed", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
-FLAG_VIRTUAL_LOSS, FLAG_MASK_PRIORS, FLAG_FRESH_TREE, FLAG_RECYCLE_TREE = 1, 2, 4, 8
+FLAG_VIRTUAL_LOSS, FLAG_MASK_PRIORS, FLAG_FRESH_TREE, FLAG_RECYCLE_TREE, FLAG_COMPACT_TREE = 1, 2, 4, 8, 16
 
 
 _P = C.c_void_p

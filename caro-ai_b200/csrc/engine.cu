@@ -36,6 +36,15 @@ struct Carver {
   }
 };
 
+// compact_kernel's dynamic shared memory: an index map of node_cap words + a staging buffer of `chunk` node records
+static size_t compact_smem_bytes(const Dims& dm, int chunk) { return ((size_t)dm.node_cap + (size_t)chunk * dm.RS) * 4; }
+static int compact_chunk_nodes(const Dims& dm) {
+  const long long budget = 220 * 1024 - (long long)dm.node_cap * 4;
+  long long chunk = budget / ((long long)dm.RS * 4);
+  if (chunk > 256) chunk = 256;
+  return chunk < 1 ? 0 : (int)chunk;
+}
+
 static int round_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -166,7 +175,9 @@ int fill_dims(const caro_engine_config* cfg, Dims* dm, int* max_plies) {
   dm->max_plies = plies;
   dm->replay_cap = cfg->replay_capacity;
   dm->flags = cfg->flags;
-  if (cfg->flags & ~15u) return caro_fail(CARO_E_ARG, "unknown engine flags");
+  if (cfg->flags & ~31u) return caro_fail(CARO_E_ARG, "unknown engine flags");
+  if ((cfg->flags & FLAG_COMPACT_TREE) && compact_chunk_nodes(*dm) < 1)
+    return caro_fail(CARO_E_ARG, "CARO_FLAG_COMPACT_TREE: node_capacity does not fit the shared-memory index map");
   *max_plies = plies;
   return CARO_OK;
 }
@@ -276,6 +287,17 @@ int caro_engine_create(const caro_engine_config* cfg, void* d_workspace, size_t 
     e->board_bytes = sizeof(MnkBoard);
   }
   cudaError_t ce = cudaMemsetAsync(e->ws, 0, need, S(stream));
+  if (ce == cudaSuccess && (dm.flags & FLAG_COMPACT_TREE)) {  // here, not at launch: launches may sit inside a graph capture
+    // the attribute belongs to the kernel, not to the engine: keep it at the largest request of any engine created so far
+    static std::atomic<int> most[2] = {{0}, {0}};
+    const int which = cfg->game == CARO_GAME_CONNECT4 ? 0 : 1;
+    int smem = (int)compact_smem_bytes(dm, compact_chunk_nodes(dm));
+    int seen = most[which].load();
+    while (smem > seen && !most[which].compare_exchange_weak(seen, smem)) {}
+    smem = smem > seen ? smem : seen;
+    if (which == 0) ce = cudaFuncSetAttribute(compact_kernel<C4Rules>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    else ce = cudaFuncSetAttribute(compact_kernel<MnkRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }
   if (ce != cudaSuccess) {
     delete e;
     return caro_fail(CARO_E_CUDA, cudaGetErrorString(ce));
@@ -685,7 +707,16 @@ int caro_engine_advance(caro_engine* e, int tau_plies, const double* d_uniform, 
   else
     advance_kernel<MnkRules><<<grid, 128, 0, S(stream)>>>(e->v_mnk, e->mnk, e->dm, e->sp, tau_plies, d_uniform, auto_restart,
                                                              first_player, d_action_out);
-  return caro_check_launch("advance_kernel");
+  int rc = caro_check_launch("advance_kernel");
+  if (rc == CARO_OK && (e->dm.flags & FLAG_COMPACT_TREE)) {  // drop what the move made unreachable, pack the arenas
+    const int chunk = compact_chunk_nodes(e->dm);
+    const size_t smem = compact_smem_bytes(e->dm, chunk);
+    const unsigned trees = (unsigned)(e->dm.G * e->dm.tpg);
+    if (e->cfg.game == CARO_GAME_CONNECT4) compact_kernel<C4Rules><<<trees, 256, smem, S(stream)>>>(e->v_c4, C4Rules(), e->dm, chunk);
+    else compact_kernel<MnkRules><<<trees, 256, smem, S(stream)>>>(e->v_mnk, e->mnk, e->dm, chunk);
+    rc = caro_check_launch("compact_kernel");
+  }
+  return rc;
 }
 
 int caro_engine_play(caro_engine* e, caro_net* net_p0, caro_net* net_p1, int moves, int count, int batch, int tau_plies,

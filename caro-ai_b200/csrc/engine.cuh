@@ -65,7 +65,7 @@ struct Dims {
   int replay_cap;
   unsigned flags;  // CARO_FLAG_* (include/caro_b200.h): throughput-mode extensions, 0 = the reference's search
 };
-enum : unsigned { FLAG_VIRTUAL_LOSS = 1u, FLAG_MASK_PRIORS = 2u, FLAG_FRESH_TREE = 4u, FLAG_RECYCLE_TREE = 8u };
+enum : unsigned { FLAG_VIRTUAL_LOSS = 1u, FLAG_MASK_PRIORS = 2u, FLAG_FRESH_TREE = 4u, FLAG_RECYCLE_TREE = 8u, FLAG_COMPACT_TREE = 16u };
 
 struct SearchParams {
   double c_puct, alpha, explore;

@@ -992,6 +992,111 @@ __global__ void root_policy_kernel(View<typename R::Board> e, R rules, Dims dm, 
   }
 }
 
+// ----------------------------------------------------------------------------------- tree compaction
+// CARO_FLAG_COMPACT_TREE: after a move, every node whose position can no longer occur (tokens are only added: it does not
+// contain the new root position) is dropped and the survivors are moved to the front of the arena.  The reference never
+// frees anything (its dicts keep every state of the game, lib/mcts.py:29-46), but a dropped state can never be looked up
+// again, so N / W / Q / P of every state that can still be reached -- and with them every later search -- are unchanged:
+// the arena then only has to hold the searches of the last few moves, whatever the length of the game.
+// One block per tree: (1) reachability flags + an exclusive scan -> old -> new index map in shared memory, (2) records,
+// boards, players and key tails moved in index order, a chunk at a time through shared memory (new index <= old index: a
+// chunk's destinations lie in chunks that have been read), child links rewritten through the map, (3) the hash table is
+// dropped (generation bump) and re-inserted from the surviving boards.
+template <class R>
+__global__ void __launch_bounds__(256)
+compact_kernel(View<typename R::Board> e, R rules, Dims dm, int chunk_nodes) {
+  using Board = typename R::Board;
+  extern __shared__ __align__(16) uint32_t cs[];
+  int32_t* map = reinterpret_cast<int32_t*>(cs);            // [node_cap]
+  uint32_t* stage = cs + dm.node_cap;                       // [chunk_nodes][RS]
+  __shared__ int s_scan[256 / 32];
+  __shared__ int s_base;
+  const int tree = blockIdx.x;
+  const int g = tree / dm.tpg;
+  if (e.status[g] != ST_ACTIVE) return;
+  const int count = e.node_count[tree];
+  if (count <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t nb = (size_t)tree * dm.node_cap;
+  const Board root = e.root_board[g];
+  // ---- (1) map ----
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < count; i0 += 256) {
+    const int i = i0 + tid;
+    const int keep = (i < count && R::reachable(root, e.node_board[nb + i])) ? 1 : 0;
+    int x = keep;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_scan[w];
+    if (i < count) map[i] = keep ? before + x - 1 : -1;
+    __syncthreads();
+    if (tid == 255) s_base = before + x;
+    __syncthreads();
+  }
+  const int kept = s_base;
+  if (kept == count) return;  // nothing to drop (uniform for the block)
+  // ---- (2) move ----
+  uint32_t* rec = reinterpret_cast<uint32_t*>(e.N);
+  const int RS = dm.RS, c_row = 3 * dm.Apad;
+  for (int i0 = 0; i0 < count; i0 += chunk_nodes) {
+    const int n_here = min(chunk_nodes, count - i0);
+    for (int k = tid; k < n_here * RS; k += 256) {
+      const int node = i0 + k / RS;
+      if (map[node] >= 0) stage[k] = rec[(nb + (size_t)node) * RS + (k % RS)];
+    }
+    // the small per-node fields travel in registers (one node per thread and pass)
+    for (int n0 = 0; n0 < n_here; n0 += 256) {
+      const int node = i0 + n0 + tid;
+      const bool mine = n0 + tid < n_here && map[node] >= 0;
+      Board b;
+      uint8_t pl = 0;
+      uint64_t kh = 0;
+      if (mine) {
+        b = e.node_board[nb + node];
+        pl = e.node_player[nb + node];
+        if (RulesTraits<R>::kHasKeyHi) kh = e.key_hi[nb + node];
+      }
+      __syncthreads();
+      if (mine) {
+        const int to = map[node];
+        e.node_board[nb + to] = b;
+        e.node_player[nb + to] = pl;
+        if (RulesTraits<R>::kHasKeyHi) e.key_hi[nb + to] = kh;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int k = tid; k < n_here * RS; k += 256) {
+      const int node = i0 + k / RS, w = k % RS;
+      const int to = map[node];
+      if (to < 0) continue;
+      uint32_t v = stage[k];
+      if (w >= c_row) {  // child link: through the map (a surviving node's children survive with it)
+        const int32_t c = (int32_t)v;
+        v = (uint32_t)(c >= 0 ? map[c] : -1);
+      }
+      rec[(nb + (size_t)to) * RS + w] = v;
+    }
+    __syncthreads();
+  }
+  // ---- (3) hash table ----
+  const uint32_t gen = e.tree_gen[tree] + 1u;
+  __syncthreads();
+  if (tid == 0) {
+    e.tree_gen[tree] = gen;
+    e.node_count[tree] = kept;
+  }
+  HashSlot* ht = e.ht + (size_t)tree * dm.hash_cap;
+  for (int i = tid; i < kept; i += 256) ht_insert_cas(ht, dm.hash_cap, gen, rules.key(e.node_board[nb + i]).lo, i);
+}
+
 // ----------------------------------------------------------------------------------- advance
 // One ply of lib/utils.py:76-106 for every active game.  One thread per game.
 template <class R>

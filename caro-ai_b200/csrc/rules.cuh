@@ -54,6 +54,8 @@ struct C4Rules {
   CARO_HD int cols() const { return kCols; }
 
   CARO_HD static Board empty() { return Board{0ULL, 0ULL}; }
+  // can position q still occur in a game that has reached position r?  (tokens are only ever added)
+  CARO_HD static bool reachable(const Board& r, const Board& q) { return (r.mask & ~q.mask) == 0ULL && (q.black & r.mask) == r.black; }
 
   // connect_four.py:157-165 -- a column is playable while its top cell is empty
   CARO_HD bool legal(const Board& s, int col) const { return ((s.mask >> (7 * col + 5)) & 1ULL) == 0ULL; }
@@ -114,6 +116,12 @@ struct MnkRules {
     Board s;
     for (int i = 0; i < 4; ++i) s.w[i] = s.b[i] = 0ULL;
     return s;
+  }
+  // can position q still occur in a game that has reached position r?  (tokens are only ever added)
+  CARO_HD static bool reachable(const Board& r, const Board& q) {
+    bool ok = true;
+    for (int i = 0; i < 4; ++i) ok = ok && (r.w[i] & ~q.w[i]) == 0ULL && (r.b[i] & ~q.b[i]) == 0ULL;
+    return ok;
   }
   CARO_HD static bool test(const uint64_t* v, int idx) { return (v[idx >> 6] >> (idx & 63)) & 1ULL; }
 

@@ -23,10 +23,12 @@ class SelfPlayEngine:
     def __init__(self, game, games: int, trees_per_game: int = 1, max_batch: int = 8, node_capacity: int = 4096,
                  replay_capacity: int = 0, c_puct: float = 1.0, alpha: float = 0.30, explore: float = 0.25,
                  seed: int = 0, device: Optional[str] = None, virtual_loss: bool = False, mask_priors: bool = False,
-                 fresh_tree: bool = False, recycle_tree: bool = False):
+                 fresh_tree: bool = False, recycle_tree: bool = False, compact_tree: bool = False):
         """``virtual_loss`` / ``mask_priors`` / ``fresh_tree`` / ``recycle_tree``: throughput-mode extensions that are NOT in the reference
         (include/caro_b200.h CARO_FLAG_*), all off by default; with any of them on the trees are no longer the
-        reference's bit for bit."""
+        reference's bit for bit.  ``compact_tree`` is different: after every move it drops the nodes that can no longer be
+        reached and packs the arena -- every reachable statistic, policy and move stays bit-identical, only the arena demand
+        changes (long games fit a small ``node_capacity``)."""
         _cabi.require_cuda()
         self.game = game
         self.G = int(games)
@@ -34,7 +36,8 @@ class SelfPlayEngine:
         self.max_batch = int(max_batch)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         flags = ((_cabi.FLAG_VIRTUAL_LOSS if virtual_loss else 0) | (_cabi.FLAG_MASK_PRIORS if mask_priors else 0) |
-                 (_cabi.FLAG_FRESH_TREE if fresh_tree else 0) | (_cabi.FLAG_RECYCLE_TREE if recycle_tree else 0))
+                 (_cabi.FLAG_FRESH_TREE if fresh_tree else 0) | (_cabi.FLAG_RECYCLE_TREE if recycle_tree else 0) |
+                 (_cabi.FLAG_COMPACT_TREE if compact_tree else 0))
         self.cfg = _cabi.EngineConfig(game.game_kind, game.n, game.k, self.G, trees_per_game, max_batch, node_capacity,
                                       replay_capacity, c_puct, alpha, explore, seed, flags, 0)
         lib = _cabi.lib()

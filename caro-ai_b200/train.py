@@ -149,6 +149,8 @@ def parse_args(argv=None):
     p.add_argument("--replay-exchange", default="gather", choices=["gather", "local"],
                    help="several ranks: all-gather BATCH_SIZE/world rows per rank (default) or train on local rows only")
     p.add_argument("--augment", action="store_true", help="extension: random board symmetries on the sampled replay rows")
+    p.add_argument("--compact-tree", action="store_true",
+                   help="drop unreachable tree nodes after every move (bit-identical play, small arenas; for large boards)")
     p.add_argument("--evaluate-every", type=int, default=cfg.EVALUATE_EVERY_STEP, help="arena evaluation period in steps")
     return p.parse_args(argv)
 
@@ -174,7 +176,8 @@ def main(argv=None):
     optimizer = optim.SGD(net.parameters(), lr=cfg.LEARNING_RATE, momentum=0.9)
     bucket = D.FlatGradients(net.parameters())
     worker = SelfPlayWorker(game, args.games, cfg.MCTS_SEARCHES, cfg.MCTS_BATCH_SIZE, cfg.STEPS_BEFORE_TAU_0,
-                            replay_steps=args.replay_steps, min_replay=cfg.REPLAY_BUFFER, seed=1000003 * rank + 17)
+                            replay_steps=args.replay_steps, min_replay=cfg.REPLAY_BUFFER, seed=1000003 * rank + 17,
+                            compact_tree=args.compact_tree)
     step_idx = best_idx = 0
     with TBMeanTracker(writer, batch_size=10) as tb:
         while args.max_steps == 0 or step_idx < args.max_steps:

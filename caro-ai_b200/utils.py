@@ -147,14 +147,20 @@ class SelfPlayWorker:
     single-game steps, so the ring is sized in steps of ``games`` games, not in positions)."""
 
     def __init__(self, game, games: int, mcts_searches: int, mcts_batch_size: int, steps_before_tau_0: int,
-                 replay_steps: int = 4, min_replay: int = 5000, seed: int = 0, node_capacity: Optional[int] = None):
+                 replay_steps: int = 4, min_replay: int = 5000, seed: int = 0, node_capacity: Optional[int] = None,
+                 compact_tree: bool = False):
+        """``compact_tree``: drop unreachable nodes after every move (CARO_FLAG_COMPACT_TREE: bit-identical play, arenas of a
+        few moves' searches instead of a whole game's -- what large boards need)."""
         self.game, self.games = game, int(games)
         self.searches, self.batch, self.tau_plies = mcts_searches, mcts_batch_size, steps_before_tau_0
         max_plies = _max_plies(game)
-        cap = node_capacity or min(1 << 16, mcts_searches * mcts_batch_size * max_plies + 8)
+        per_move = mcts_searches * mcts_batch_size
+        cap = node_capacity or min(1 << 16, (8 * per_move if compact_tree else per_move * max_plies) + 8)
+        if compact_tree:
+            cap = min(cap, 40000)  # the compaction kernel's index map lives in shared memory
         self.replay_capacity = max(int(min_replay), replay_steps * self.games * max_plies)
         self.engine = SelfPlayEngine(game, self.games, trees_per_game=1, max_batch=mcts_batch_size, node_capacity=cap,
-                                     replay_capacity=self.replay_capacity, seed=seed)
+                                     replay_capacity=self.replay_capacity, seed=seed, compact_tree=compact_tree)
         self._last = self.engine.counters()
 
     def play_step(self, net: "model.DeviceNet") -> Dict[str, int]:

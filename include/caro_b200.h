@@ -168,8 +168,16 @@ typedef struct {
  *                  long 15 x 15 games at 1,600 descents per move need.
  *   RECYCLE_TREE   the tree is kept from move to move until it fills more than half of its arena and is cleared then: no
  *                  overflow while one move's searches fit half an arena, and most moves still reuse the previous subtree
- *                  (stands in for re-rooting / compaction, which is not built). */
-enum { CARO_FLAG_VIRTUAL_LOSS = 1, CARO_FLAG_MASK_PRIORS = 2, CARO_FLAG_FRESH_TREE = 4, CARO_FLAG_RECYCLE_TREE = 8 };
+ *                  (a cruder stand-in for COMPACT_TREE).
+ *   COMPACT_TREE   after every move the nodes whose position can no longer occur (it does not contain the new root position:
+ *                  tokens are only ever added) are dropped and the survivors moved to the front of the arena.  NOT a change of
+ *                  the search: a dropped state can never be looked up again, so every N / W / Q / P that can still be reached,
+ *                  and with it every later search, policy and move, is bit-identical to the reference's keep-everything tree
+ *                  (lib/mcts.py:29-46).  The arena then holds the last few moves' searches instead of the whole game's: what
+ *                  whole 15 x 15 games at 1,600 descents per move need.  node_capacity must fit a shared-memory index map
+ *                  (<= ~45,000 nodes). */
+enum { CARO_FLAG_VIRTUAL_LOSS = 1, CARO_FLAG_MASK_PRIORS = 2, CARO_FLAG_FRESH_TREE = 4, CARO_FLAG_RECYCLE_TREE = 8,
+       CARO_FLAG_COMPACT_TREE = 16 };
 
 /* Bytes of device workspace the engine needs; the caller allocates it (e.g. a torch uint8 CUDA
  * tensor) and keeps it alive for the life of the handle. */

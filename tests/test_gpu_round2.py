@@ -867,3 +867,64 @@ def test_masked_priors_and_fresh_tree_flags(torch_cuda):
             assert reused > 32 * 6 and int(eng.region("node_count").max().item()) <= 1024
         eng.close()
     dc.close()
+
+
+def test_tree_compaction_changes_nothing_that_can_be_reached(torch_cuda):
+    """CARO_FLAG_COMPACT_TREE drops, after every move, the nodes whose position can no longer occur and packs the arena.
+    Against a twin engine that keeps everything (the reference's tree), with the same seeds and the real tower: the same
+    moves, policies, roots and counters ply after ply (so every later search saw the same statistics), every surviving
+    node bit-identical to its twin (N / W / Q / P / promotion flags), every twin node that contains the root position still
+    present, far fewer nodes -- for Connect4 (one and two trees per game) and a 9 x 9 five-in-a-row board; and a 15 x 15
+    game of 14 moves at 200 descents per move fits a 2,048-node arena that the keep-everything tree overflows."""
+    torch = torch_cuda
+    from caro_ai_b200.engine import SelfPlayEngine
+    from caro_ai_b200.game import ConnectFour, TicTacToe
+    from caro_ai_b200.model import DeviceNet, Net
+    for game, tpg, G, cap, count, plies in ((ConnectFour(), 1, 256, 4096, 20, 14), (ConnectFour(), 2, 128, 4096, 12, 10),
+                                            (TicTacToe(9, 5), 1, 48, 4096, 20, 10)):
+        og = oracle_for(game)
+        torch.manual_seed(0)
+        dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game, precision="bf16")
+        keep = SelfPlayEngine(game, G, trees_per_game=tpg, max_batch=8, node_capacity=cap, seed=11)
+        comp = SelfPlayEngine(game, G, trees_per_game=tpg, max_batch=8, node_capacity=cap, seed=11, compact_tree=True)
+        for ply in range(plies):
+            acts = []
+            for e in (keep, comp):
+                e.search(dn, count, 8, first_minibatch=ply * count)
+                pi, q, n = e.root_policy(2, 10)
+                acts.append((pi.clone(), q.clone(), n.clone(), e.advance(10, None, auto_restart=True).clone()))
+            for a, b in zip(acts[0], acts[1]):
+                assert torch.equal(a, b), (game.obs_shape, tpg, ply)
+            assert keep.roots() == comp.roots() and keep.counters() == comp.counters()
+        assert comp.counters()["errors"] == 0
+        nk, nc = keep.region("node_count").cpu().numpy(), comp.region("node_count").cpu().numpy()
+        assert (nc <= nk).all() and nc.sum() < 0.7 * nk.sum(), (nk.sum(), nc.sum())
+        roots, _ = comp.roots()
+        for tree in range(0, G * tpg, max(1, G * tpg // 9)):
+            tk, tc = keep.export_tree(tree), comp.export_tree(tree)
+            root = roots[tree // tpg]
+            rb = game.boards_from_states([root]).view(np.uint64)[0]
+            for s, node in tc.items():
+                twin = tk[s]
+                assert node["N"] == twin["N"] and node["f32"] == twin["f32"]
+                for k in ("W", "Q", "P"):
+                    assert np.array_equal(node[k], twin[k]), (tree, s, k)
+            for s in tk:  # everything that still contains the root position survived
+                qb = game.boards_from_states([s]).view(np.uint64)[0]
+                if isinstance(game, ConnectFour):
+                    inside = (rb[0] & ~qb[0]) == 0 and (qb[1] & rb[0]) == rb[1]
+                else:
+                    inside = all((rb[i] & ~qb[i]) == 0 for i in range(8))
+                assert (s in tc) == bool(inside), (tree, s)
+        keep.close()
+        comp.close()
+        dn.close()
+    caro = TicTacToe(15, 5)
+    torch.manual_seed(0)
+    dc = DeviceNet(Net(caro.obs_shape, caro.action_space).eval(), caro, precision="bf16")
+    for compact in (True, False):
+        eng = SelfPlayEngine(caro, 32, max_batch=8, node_capacity=2048, seed=3, compact_tree=compact)
+        eng.play(dc, dc, moves=14, count=25, batch=8, tau_plies=10, auto_restart=True)
+        assert bool(eng.counters()["errors"] & 1) == (not compact), (compact, eng.counters())
+        eng.close()
+    dc.close()

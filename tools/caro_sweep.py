@@ -16,8 +16,9 @@ from caro_ai_b200.model import DeviceNet, Net, load_checkpoint
 
 def main():
     trained = os.environ.get("GAME") == "c4trained"
-    game = ConnectFour() if trained else TicTacToe(15, 5)
-    count = 100 if trained else 200
+    c4 = trained or os.environ.get("GAME") == "c4"
+    game = ConnectFour() if c4 else TicTacToe(15, 5)
+    count = 100 if c4 else 200
     torch.manual_seed(0)
     if trained:
         dn = DeviceNet(load_checkpoint(os.path.join(ROOT, "tests", "golden", "checkpoints", "connect4_best_026_12000.dat"), game).eval(), game)
@@ -29,7 +30,7 @@ def main():
         spec, _, flag = spec.partition(":")
         parts, games = (int(x) for x in spec.split("x"))
         plies = int(os.environ.get("PLIES", "3"))
-        flags = {"recycle_tree": True} if flag == "recycle" else {}
+        flags = {"recycle_tree": True} if flag == "recycle" else {"compact_tree": True} if flag == "compact" else {}
         engs = [SelfPlayEngine(game, games, max_batch=8, node_capacity=int(os.environ.get("CAP", "8192")), seed=7 * h, **flags) for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=1, count=count, batch=8, tau_plies=10, auto_restart=True)
         torch.cuda.synchronize()
@@ -43,7 +44,7 @@ def main():
         sec = t0.elapsed_time(t1) / 1e3
         leaf = sum(b["leaf_evals"] - a["leaf_evals"] for a, b in zip(c0, c1))
         print(json.dumps({"parts": parts, "games_per_part": games, "flag": flag, "plies": plies, "ms_per_ply": 1e3 * sec / plies,
-                          "leaf_evals_per_sec": leaf / sec, "leaves_per_launch": leaf / (plies * count * parts), "precision": dn.precision,
+                          "leaf_evals_per_sec": leaf / sec, "leaves_per_launch": leaf / (plies * count * parts), "precision": dn.precision, "max_nodes": max(int(e.region("node_count").max().item()) for e in engs),
                           "errors": sum(c["errors"] for c in c1)}), flush=True)
         for e in engs:
             e.close()
