@@ -37,9 +37,9 @@ struct Carver {
 };
 
 // compact_kernel's dynamic shared memory: an index map of node_cap words + a staging buffer of `chunk` node records
-static size_t compact_smem_bytes(const Dims& dm, int chunk) { return ((size_t)dm.node_cap + (size_t)chunk * dm.RS) * 4; }
+static size_t compact_smem_bytes(const Dims& dm, int chunk) { return ((size_t)((dm.node_cap + 3) & ~3) + (size_t)chunk * dm.RS) * 4; }
 static int compact_chunk_nodes(const Dims& dm) {
-  const long long budget = 220 * 1024 - (long long)dm.node_cap * 4;
+  const long long budget = 220 * 1024 - (long long)((dm.node_cap + 3) & ~3) * 4;
   long long chunk = budget / ((long long)dm.RS * 4);
   if (chunk > 256) chunk = 256;
   return chunk < 1 ? 0 : (int)chunk;

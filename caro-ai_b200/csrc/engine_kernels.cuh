@@ -1008,7 +1008,7 @@ compact_kernel(View<typename R::Board> e, R rules, Dims dm, int chunk_nodes) {
   using Board = typename R::Board;
   extern __shared__ __align__(16) uint32_t cs[];
   int32_t* map = reinterpret_cast<int32_t*>(cs);            // [node_cap]
-  uint32_t* stage = cs + dm.node_cap;                       // [chunk_nodes][RS]
+  uint32_t* stage = cs + ((dm.node_cap + 3) & ~3);           // [chunk_nodes][RS], 16-byte aligned
   __shared__ int s_scan[256 / 32];
   __shared__ int s_base;
   const int tree = blockIdx.x;
@@ -1043,18 +1043,19 @@ compact_kernel(View<typename R::Board> e, R rules, Dims dm, int chunk_nodes) {
   const int kept = s_base;
   if (kept == count) return;  // nothing to drop (uniform for the block)
   // ---- (2) move ----
-  uint32_t* rec = reinterpret_cast<uint32_t*>(e.N);
-  const int RS = dm.RS, c_row = 3 * dm.Apad;
+  uint4* rec = reinterpret_cast<uint4*>(e.N);  // records are 16 * Apad bytes, Apad a multiple of 8: 16-byte units throughout
+  uint4* stage4 = reinterpret_cast<uint4*>(stage);
+  const int RS = dm.RS / 4, c_row = 3 * dm.Apad / 4;
   for (int i0 = 0; i0 < count; i0 += chunk_nodes) {
     const int n_here = min(chunk_nodes, count - i0);
     for (int k = tid; k < n_here * RS; k += 256) {
       const int node = i0 + k / RS;
-      if (map[node] >= 0) stage[k] = rec[(nb + (size_t)node) * RS + (k % RS)];
+      if (map[node] >= 0 && map[node] != node) stage4[k] = rec[(nb + (size_t)node) * RS + (k % RS)];
     }
     // the small per-node fields travel in registers (one node per thread and pass)
     for (int n0 = 0; n0 < n_here; n0 += 256) {
       const int node = i0 + n0 + tid;
-      const bool mine = n0 + tid < n_here && map[node] >= 0;
+      const bool mine = n0 + tid < n_here && map[node] >= 0 && map[node] != node;
       Board b;
       uint8_t pl = 0;
       uint64_t kh = 0;
@@ -1077,10 +1078,14 @@ compact_kernel(View<typename R::Board> e, R rules, Dims dm, int chunk_nodes) {
       const int node = i0 + k / RS, w = k % RS;
       const int to = map[node];
       if (to < 0) continue;
-      uint32_t v = stage[k];
-      if (w >= c_row) {  // child link: through the map (a surviving node's children survive with it)
-        const int32_t c = (int32_t)v;
-        v = (uint32_t)(c >= 0 ? map[c] : -1);
+      const bool links = w >= c_row;  // child links go through the map (a surviving node's children survive with it)
+      if (to == node && !links) continue;  // in place already
+      uint4 v = to == node ? rec[(nb + (size_t)node) * RS + w] : stage4[k];
+      if (links) {
+        v.x = (uint32_t)((int32_t)v.x >= 0 ? map[(int32_t)v.x] : -1);
+        v.y = (uint32_t)((int32_t)v.y >= 0 ? map[(int32_t)v.y] : -1);
+        v.z = (uint32_t)((int32_t)v.z >= 0 ? map[(int32_t)v.z] : -1);
+        v.w = (uint32_t)((int32_t)v.w >= 0 ? map[(int32_t)v.w] : -1);
       }
       rec[(nb + (size_t)to) * RS + w] = v;
     }
