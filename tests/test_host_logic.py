@@ -24,6 +24,23 @@ def test_library_exports_every_declared_symbol():
     assert lib.caro_abi_version() == 2
 
 
+def test_flag_constants_match_the_header_and_are_validated():
+    """The CARO_FLAG_* values of include/caro_b200.h are the ones the Python mirror passes; unknown bits and a compaction
+    request whose index map cannot fit shared memory are refused by the (CPU-side) configuration check."""
+    from caro_ai_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "caro_b200.h")).read()
+    values = {k: int(v) for k, v in re.findall(r"CARO_FLAG_([A-Z_]+)\s*=\s*(\d+)", header)}
+    assert values == {"VIRTUAL_LOSS": _cabi.FLAG_VIRTUAL_LOSS, "MASK_PRIORS": _cabi.FLAG_MASK_PRIORS, "FRESH_TREE": _cabi.FLAG_FRESH_TREE,
+                      "RECYCLE_TREE": _cabi.FLAG_RECYCLE_TREE, "COMPACT_TREE": _cabi.FLAG_COMPACT_TREE}
+    lib = _cabi.lib()
+    ok = _cabi.EngineConfig(0, 0, 0, 64, 1, 8, 8192, 0, 1.0, 0.3, 0.25, 0, _cabi.FLAG_COMPACT_TREE, 0)
+    assert lib.caro_engine_workspace_bytes(C.byref(ok)) > 0
+    unknown = _cabi.EngineConfig(0, 0, 0, 64, 1, 8, 8192, 0, 1.0, 0.3, 0.25, 0, 32, 0)
+    assert lib.caro_engine_workspace_bytes(C.byref(unknown)) == 0 and b"flags" in lib.caro_last_error()
+    too_big = _cabi.EngineConfig(0, 0, 0, 4, 1, 8, 70000, 0, 1.0, 0.3, 0.25, 0, _cabi.FLAG_COMPACT_TREE, 0)
+    assert lib.caro_engine_workspace_bytes(C.byref(too_big)) == 0 and b"COMPACT_TREE" in lib.caro_last_error()
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_compute_entry_points_fail_loudly_without_a_gpu():
     from caro_ai_b200 import _cabi
