@@ -569,6 +569,32 @@ def test_selfplay_worker_keeps_one_engine_and_a_ring_of_several_steps(torch_cuda
     assert tuple(planes.shape) == (256, 2, 3, 3) and tuple(pi.shape) == (256, 9) and tuple(z.shape) == (256,)
     assert bool(((z == 0) | (z == 1) | (z == -1)).all()) and torch.allclose(pi.sum(dim=1), torch.ones(256, device="cuda"), atol=1e-5)
     w.close()
+    # the same worker with tree compaction (small arenas): the same games, position for position, in the replay ring
+    from caro_ai_b200.game import ConnectFour
+    c4 = ConnectFour()
+    torch.manual_seed(0)
+    d4 = DeviceNet(Net(c4.obs_shape, c4.action_space).eval(), c4)
+    a = SelfPlayWorker(c4, 96, 8, 8, 10, replay_steps=1, min_replay=100, seed=5)
+    b = SelfPlayWorker(c4, 96, 8, 8, 10, replay_steps=1, min_replay=100, seed=5, compact_tree=True)
+    assert b.engine.cfg.node_capacity < a.engine.cfg.node_capacity
+    for step in range(2):
+        sa, sb = a.play_step(d4), b.play_step(d4)
+        assert sa == sb and sa["games"] == 96
+    assert a.replay_len() == b.replay_len()
+
+    def rows(w):  # ring entries as a sorted list (games that finish in the same ply reserve their slots in no fixed order)
+        n = w.replay_len()
+        e = w.engine
+        bd = e.region("replay_board")[:n].cpu().numpy().view(np.uint64).reshape(n, -1)
+        pl = e.region("replay_player")[:n].cpu().numpy()
+        pi = e.region("replay_pi")[:n].cpu().numpy()
+        z = e.region("replay_z")[:n].cpu().numpy()
+        return sorted((tuple(bd[i].tolist()), int(pl[i]), tuple(pi[i].tolist()), float(z[i])) for i in range(n))
+
+    assert rows(a) == rows(b)
+    a.close()
+    b.close()
+    d4.close()
     dn.close()
 
 

@@ -76,7 +76,9 @@ def main():
     torch.manual_seed(0)
     dn = DeviceNet(Net(game.obs_shape, game.action_space).eval(), game)
     for G in sizes:
-        eng = SelfPlayEngine(game, G, max_batch=8, node_capacity=24576 if G <= 8192 else 8192, seed=7)
+        compact = os.environ.get("COMPACT") == "1"  # CARO_FLAG_COMPACT_TREE: packed arenas (the same search, bit for bit)
+        cap = int(os.environ.get("CAP", "0")) or (24576 if G <= 8192 else 8192)
+        eng = SelfPlayEngine(game, G, max_batch=8, node_capacity=cap, seed=7, compact_tree=compact)
         eng.play(dn, dn, moves=6, count=100, batch=8, tau_plies=10, auto_restart=True)  # mid-game trees
         eng.search(dn, 40, 8)                                                             # grow the current roots' trees
         torch.cuda.synchronize()
@@ -96,7 +98,7 @@ def main():
         sel_b = depth_sum * (12 * A + 20)
         bak_b = depth_sum * 20 + leaves * (16 * A + 12)
         plan_b = desc * 17 + leaves * 17
-        out = {"games": G, "descents_per_minibatch": desc / n, "avg_path_len": d, "unique_leaves_per_minibatch": leaves / n}
+        out = {"games": G, "compact_tree": compact, "node_capacity": cap, "descents_per_minibatch": desc / n, "avg_path_len": d, "unique_leaves_per_minibatch": leaves / n}
         noise_b = desc * A * 8  # float64 [descents][A] written by noise_kernel (read again by select: not in select's byte model)
         for name, ms, b in (("noise", p["noise_ms"], noise_b), ("select", p["select_ms"], sel_b), ("plan", p["plan_ms"], plan_b),
                             ("expand+backup", p["expand_backup_ms"], bak_b)):
