@@ -59,7 +59,8 @@
                            // NEXT TO a tower CTA (tools/coresidency_test.py; at 112 they have to wait for it to end)
 #endif
 #ifndef CARO_RT_CP
-#define CARO_RT_CP 2  // channel parts of the epilogue: 2 -> 8 epilogue warps of 32 channels, 4 -> 16 warps of 16
+#define CARO_RT_CP 2  // channel parts of the epilogue: 2 -> 8 epilogue warps of 32 channels, 4 -> 16 warps of 16 (needs
+                      // -DCARO_RT_MAXREG=80; measured 2-4 % slower: the per-warp fixed cost of a tile is paid twice as often)
 #endif
 
 namespace caro {
@@ -85,7 +86,8 @@ struct RtCfg {
   static constexpr int kHeadWarps = 4;
   static constexpr int kHeadThreads = 32 * kHeadWarps;
   static constexpr int kThreads = kEpiThreads + 64 + kHeadThreads;
-  static_assert(CP == 2, "the last layer's even/odd tile split assumes two channel parts");
+  static_assert(CP == 2 || CP == 4, "two or four channel parts");
+  static_assert(CP == 2 || !PAIR_, "the pair form is built for two channel parts");
   static constexpr int kAct = 0;
   static constexpr int kWgt = kAct + kRtActBytes;
   static constexpr int kHeadF = kWgt + kRtRegions * kRegionBytes;  // float [nb][3][HW] head features (PAIR: in global memory)
@@ -475,6 +477,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   } else {
     // ========================================= epilogue warps =========================================
     const int quarter = warp & 3, cp = warp >> 2;
+    constexpr int CH = K::kCH, QN = CH / 4, C8N = CH / 8;   // channels per warp, groups of four, 16-byte chunks
     const int row = quarter * 32 + (tid & 31);              // lane of the tile = TMEM lane
     const int bidx = row >> gm.pshift, col = row & (gm.pitch - 1);
     const bool real = col < gm.W;
@@ -528,19 +531,20 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       const uint32_t a_acc = tmem_base + lane_base + (uint32_t)(y * 64 + c0);
       const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + c0 / 4);
       const float4* bl4 = reinterpret_cast<const float4*>(consts.bias + layer * 64 + c0);
-      uint32_t ra[32], rl[8];
-      uint4 hv[4];
+      uint32_t ra[CH], rl[QN];
+      uint4 hv[C8N];
       TMEM_LD16(a_acc, ra);
-      TMEM_LD16(a_acc + 16u, (ra + 16));
+      if (CH == 32) TMEM_LD16(a_acc + 16u, (ra + CH - 16));
       if (HAS_RES) {
-        TMEM_LD8(a_lo, rl);
+        if (CH == 32) TMEM_LD8(a_lo, rl);
+        else TMEM_LD4(a_lo, rl);
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
+        for (int c8 = 0; c8 < C8N; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const float2 slope = make_float2(kLeaky, kLeaky);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < QN; ++q) {
         const float4 bq = bl4[q];
         const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4]), __uint_as_float(ra[q * 4 + 1])), make_float2(bq.x, bq.y));
         const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(ra[q * 4 + 2]), __uint_as_float(ra[q * 4 + 3])), make_float2(bq.z, bq.w));
@@ -572,13 +576,13 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         act_arrive(y);
         return;
       }
-      uint8_t* arow = act + (size_t)(cp * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
-      float2 v[16];
-      load_values(has_res_c, layer, y, cp * 32, v, arow);
-      if (PAIR) zero_acc(y, cp * 32);
+      uint8_t* arow = act + (size_t)(cp * C8N * kRtActRows + kRtHalo + y * 128 + row) * 16;
+      float2 v[CH / 2];
+      load_values(has_res_c, layer, y, cp * CH, v, arow);
+      if (PAIR) zero_acc(y, cp * CH);
       const float2 minus1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
+      for (int c8 = 0; c8 < C8N; ++c8) {
         uint32_t packed[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -590,11 +594,12 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         }
         *reinterpret_cast<uint4*>(arow + (size_t)c8 * kRtChunkBytes) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
-      uint32_t rl[8];
+      uint32_t rl[QN];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
-      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * 8);
-      TMEM_ST8(a_lo, rl);
+      for (int q = 0; q < QN; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
+      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * QN);
+      if (CH == 32) TMEM_ST8(a_lo, rl);
+      else TMEM_ST4(a_lo, rl);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_async_smem();
       tc_fence_before();
@@ -611,17 +616,17 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       __syncwarp();
       tc_fence_after();
       if (tid == 0) TC_TRACE(2, gl * 8 + y);
-      if (!dbg_skip_epilogue && (y & 1) == cp) {
+      if (!dbg_skip_epilogue && (y % K::kCP) == cp) {
         float av = 0.0f, ap0 = 0.0f, ap1 = 0.0f;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint8_t* arow = act + (size_t)(hh * 4 * kRtActRows + kRtHalo + y * 128 + row) * 16;
-          float2 v[16];
-          load_values(std::true_type{}, gm.layers - 1, y, hh * 32, v, arow);
-          if (PAIR) zero_acc(y, hh * 32);
-          const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * 32);
+        for (int hh = 0; hh < K::kCP; ++hh) {
+          uint8_t* arow = act + (size_t)(hh * C8N * kRtActRows + kRtHalo + y * 128 + row) * 16;
+          float2 v[CH / 2];
+          load_values(std::true_type{}, gm.layers - 1, y, hh * CH, v, arow);
+          if (PAIR) zero_acc(y, hh * CH);
+          const float4* hw4 = reinterpret_cast<const float4*>(consts.headw + hh * CH);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < QN; ++q) {
             const float4 w0 = hw4[q], w1 = hw4[16 + q], w2 = hw4[32 + q];
             const float2 a = v[q * 2], b = v[q * 2 + 1];
             av = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(b.x, w0.z, fmaf(b.y, w0.w, av))));
@@ -638,7 +643,7 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         if (PAIR) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
-      if (more) write_inputs(y, next_leaf0, y & 1);  // by the set that just read this tile's residual
+      if (more) write_inputs(y, next_leaf0, y % K::kCP);  // by the set that just read this tile's residual
       if (tid == 0) TC_TRACE(3, gl * 8 + y);
     };
 
@@ -796,7 +801,7 @@ void caro_net_rt_free(caro_net* net) {
 bool caro_net_rt_supports(const caro_net* net) { return net->H >= 2 && net->H <= kRtMaxH && net->W >= 2 && net->W <= kRtMaxW; }
 
 using RtK = RtCfg<CARO_RT_CP>;
-using RtKPair = RtCfg<CARO_RT_CP, true>;
+using RtKPair = RtCfg<2, true>;  // the pair form keeps two channel parts
 
 // CARO_RT_PAIR=1/0 switches the CTA-pair form of the tower on / off (read once)
 static bool rt_pair_enabled() {
