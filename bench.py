@@ -27,6 +27,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 TRAINED_C4 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "checkpoints", "connect4_best_026_12000.dat")
+# the tower DeviceNet(precision="auto") selects by measuring against the fp32 tower on the device (model.py): the one-pass fp16
+# tower for the benchmark's random-init networks -- tcgen05 kind::f16 like bf16, same tensor rate, 11 instead of 8 mantissa bits
+# on both operands (3.7e-5 / 8.1e-5 off fp32 where bf16 is 1.1e-4 / 5.0e-4); the bf16 number of the same workload is
+# the line's `bf16_same_workload`
+DTYPE_OF = {"fp16": "f16", "bf16": "bf16", "bf16x3": "f16 hi+lo x3", "fp32-simt": "f32"}
+TOWER_OF = {"fp16": "fp16 tcgen05, fp32 accumulate", "bf16": "bf16 tcgen05, fp32 accumulate",
+            "bf16x3": "split-precision fp16 hi + lo tcgen05, fp32 accumulate", "fp32-simt": "fp32 SIMT"}
 FLOP_PER_LEAF_C4 = 15598672  # conv_in 96,768*... + 5 x 3,096,576*... + heads (2 x MAC)
 SIMS_COUNT, SIMS_BATCH, TAU_PLIES = 100, 8, 10
 GAMES_PER_GPU = 16384  # two software-pipelined half-batches of 8192 (north_star: >= 4096 concurrent games per GPU; the line at
@@ -263,7 +270,7 @@ def extra_train(torch, dist, game, ring_engine, world, rank, rounds=20):
     return out
 
 
-def extra_configs(torch, dist, world, rank, seed, small=False):
+def extra_configs(torch, dist, world, rank, seed, small=False, net_sms=0):
     """Short, honestly sized runs of the other BASELINE.json configurations.  EVERY rank runs them on its own GPU (games
     shard by rank, no collective on the data path) and the per-rank rates are summed: at N GPUs the entries are the
     aggregate of N x the stated per-GPU workload (weak scaling).  Every number is measured by CUDA events around the plies
@@ -273,13 +280,15 @@ def extra_configs(torch, dist, world, rank, seed, small=False):
     from caro_ai_b200.model import DeviceNet, Net
     out = {}
 
-    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, blocks=5, checkpoint=None, **flags):
+    def run(tag, game, parts, games_per_part, count, batch, cap, warm, plies, note, blocks=5, checkpoint=None, precision="auto", **flags):
         torch.manual_seed(0)
         if checkpoint is not None:  # a TRAINED network: precision "auto" has to pick the split-precision tower for it
             from caro_ai_b200.model import load_checkpoint
-            dn = DeviceNet(load_checkpoint(checkpoint, game).eval(), game)
+            dn = DeviceNet(load_checkpoint(checkpoint, game).eval(), game, precision=precision)
         else:
-            dn = DeviceNet(Net(game.obs_shape, game.action_space, blocks=blocks).eval(), game)
+            dn = DeviceNet(Net(game.obs_shape, game.action_space, blocks=blocks).eval(), game, precision=precision)
+        if net_sms:
+            dn.set_grid_limit(net_sms)
         engs = [SelfPlayEngine(game, games_per_part, max_batch=batch, node_capacity=cap, seed=seed + 7 * h + 101 * rank, **flags)
                 for h in range(parts)]
         SelfPlayEngine.play_multi(engs, dn, moves=warm, count=count, batch=batch, tau_plies=TAU_PLIES, auto_restart=True)
@@ -363,7 +372,7 @@ def engine_arm(args):
     game = ConnectFour()
     torch.manual_seed(0)
     net = Net(game.obs_shape, game.action_space).eval()
-    dnet = DeviceNet(net, game)
+    dnet = DeviceNet(net, game, precision=args.precision)
     if args.net_sms:
         dnet.set_grid_limit(args.net_sms)
     G = args.games
@@ -464,6 +473,33 @@ def engine_arm(args):
     e2e_ms = ee0.elapsed_time(ee1)
     ce1 = counters()
     workspace_gb = sum(e.workspace_bytes for e in engs) / 1e9
+    # the same engines, mid-game states and plies with the one-pass BF16 tower forced -- the dtype BASELINE.json's north_star
+    # names -- when the device check selected another tower for the headline
+    bf16_same = None
+    if dnet.precision != "bf16" and not args.no_extra:
+        dn_b = DeviceNet(net, game, precision="bf16")
+        if args.net_sms:
+            dn_b.set_grid_limit(args.net_sms)
+        main_net, dnet = dnet, dn_b
+        n_b = max(4, min(16, args.steps // 3))
+        play(2)
+        barrier()
+        cb0 = counters()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        play(n_b)
+        b1.record(stream)
+        barrier()
+        cb1 = counters()
+        t = torch.tensor([float(cb1["leaf_evals"] - cb0["leaf_evals"])], dtype=torch.float64, device="cuda")
+        tm = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        bf16_same = {"precision": "bf16", "plies": n_b, "value": float(t[0]) / (float(tm[0]) / 1e3), "unit": "leaf_evals/s",
+                     "ms_per_step": float(tm[0]) / n_b}
+        dnet = main_net
+        dn_b.close()
     extra = {}
     if not args.no_extra:
         extra["train"] = extra_train(torch, dist, game, engs[0], world, rank)
@@ -513,9 +549,9 @@ def engine_arm(args):
         line = {
             "metric": "connect4_mcts_leaf_evals_per_sec", "value": leaf / sec, "unit": "leaf_evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[dnet.precision], "data": "synthetic",
             "config": {"workload": "connect4 6x7 self-play, search_batch(100,8)=800 descents/move, %d concurrent games per GPU, "
-                                   "random-init 5x64 residual net (bf16 tcgen05, fp32 accumulate), tau=1 for 10 plies" % G,
+                                   "random-init 5x64 residual net (%s), tau=1 for 10 plies" % (G, TOWER_OF[dnet.precision]),
                        "games_per_gpu": G, "sims_per_move": SIMS_COUNT * SIMS_BATCH, "node_capacity": args.node_capacity,
                        "pipeline": ("%d part-batches of %d games, each part's tree kernels on its own side stream under the other parts' network passes" % (halves, G // halves)) if halves >= 2 else "single stream",
                        "cache": "tree arenas %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
@@ -538,6 +574,7 @@ def engine_arm(args):
                                   if args.profile_level >= 2 or k == "net_ms"},
             "clocks": sampler.summary(), "engine_errors": int(errors),
             "net_precision": {"selected": dnet.precision, "calibration": dnet.calibration},
+            "bf16_same_workload": bf16_same,
         }
         if extra:
             line["extra"] = extra
@@ -568,6 +605,8 @@ def main():
     ap.add_argument("--parts", type=int, default=2, help="software-pipelined parts the game batch is split into")
     ap.add_argument("--net-sms", type=int, default=0, help="SMs the network kernel may occupy (0 = all); the rest serve the tree kernels")
     ap.add_argument("--profile-level", type=int, default=1, help="1: CUDA events around the network kernel only, 2: all phases")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp16", "bf16", "bf16x3"],
+                    help="tower of the headline run: auto = the fastest one-pass tower within 1e-3 of fp32 on the device check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-small", action="store_true", help="toy sizes for extra.configs (tests)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.train / extra.configs measurements after the headline")

@@ -191,6 +191,7 @@ int caro_net_create(int rows, int cols, int actions, const float* h_blob, size_t
   net->d_tc_weights = nullptr;
   net->d_rt_weights = nullptr;
   net->d_rt_pair_weights = nullptr;
+  net->d_rt_f16_weights = nullptr;
   net->d_tc_pair_weights = nullptr;
   net->d_rt_scratch = nullptr;
   net->rt_scratch_seq = 0;
@@ -275,8 +276,8 @@ int caro_net_forward(caro_net* net, int game, int n, int k, const void* d_boards
     if (game == CARO_GAME_CONNECT4) return launch_simt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
     return launch_simt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   }
-  if ((impl == 0 || impl == 5) && caro_net_rt_supports(net))
-    return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 5, st);
+  if ((impl == 0 || impl == 5 || impl == 7) && caro_net_rt_supports(net))
+    return caro_net_rt_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, impl == 5 ? 1 : impl == 7 ? 2 : 0, st);
   if (impl == 2 && caro_net_rt_supports(net))
     return caro_net_rx_forward(net, game, n, k, d_boards, d_who, d_count, max_count, d_probs, d_values, st);
   if (impl == 0 || impl == 2 || impl == 3 || impl == 4 || impl == 6)

@@ -59,6 +59,7 @@ struct caro_net {
   void* d_tc_weights;   // bf16 UMMA B-operand images, one per (layer, tap) -- see net_tc.cu
   void* d_rt_weights;   // bf16 UMMA B-operand blocks of the row-tiled tower -- see net_rt.cu
   void* d_tc_pair_weights;  // tap-per-MMA tower as CTA pairs: one compact bf16 image per cluster rank
+  void* d_rt_f16_weights;   // the row-tiled tower's blocks in fp16 (F16 mode)
   void* d_rt_pair_weights;  // the same for the CTA-pair form: one image per cluster rank, 7 KB blocks
   void* d_rt_scratch;       // CTA-pair form: head features + FC scratch of every CTA, kRtScratchSlots launches in flight
   unsigned rt_scratch_seq;  // next slot (round robin per launch)
@@ -94,7 +95,7 @@ int caro_net_rt_prepare();
 void caro_net_rt_free(caro_net* net);
 bool caro_net_rt_supports(const caro_net* net);
 int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int pair, cudaStream_t st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int mode, cudaStream_t st);
 
 // net_rx.cu (split-precision row-tiled tower, fp16 hi + lo, boards up to 6 x 7)
 int caro_net_rx_pack(caro_net* net, const float* h_blob);

@@ -70,9 +70,15 @@ namespace caro {
 // boards (activations, accumulators, epilogue, heads) but stores and fetches only HALF of every B operand, 4 + 3 KB per
 // N = 192 MMA instead of 4 + 6.  The blocks grow from 6 to 7 KB (three windows, rt_common.cuh), which the head features and
 // the FC scratch pay for by moving to global memory.
-template <int CP, bool PAIR_ = false>
+// F16: activations AND weights in fp16 (11 mantissa bits on both MMA operands instead of bf16's 8), fp32 accumulation.  The
+// residual stream is then the fp16 activations themselves -- as precise as the bf16 + e5m2 pair -- so the e5m2 tail in TMEM and
+// 40 % of the epilogue's instructions go away.  What fp16 gives up is range (|x| < 65,504): the precision selection measures
+// the result against the fp32 tower after every weight upload and falls back when that ever bites (model.py).
+template <int CP, bool PAIR_ = false, bool F16_ = false>
 struct RtCfg {
   static constexpr bool kPair = PAIR_;
+  static constexpr bool kF16 = F16_;
+  static_assert(!(PAIR_ && F16_), "the pair form exists for the bf16 mode only");
   static constexpr int kBlockBytes = PAIR_ ? kRtPairBlockBytes : kRtBlockBytes;
   static constexpr int kBlockUnits = kBlockBytes / 16;
   static constexpr int kRegionBytes = kRtRegionBlocks * kBlockBytes;
@@ -117,7 +123,7 @@ __device__ __forceinline__ constexpr int rt_value(int v) { return v; }
 // middle of an N = 192 tile the MMAs already queued hide ~265 cycles of it, next to a commit only ~95 (tools/cta2_probe.cu).
 // PAIR (cta_group::2, issued by the leader CTA for both): every MMA accumulates -- the epilogues leave the accumulators they
 // have read zeroed --, B comes from the window of the tile's position, `fullp` = the barriers the peer's weights are reported on.
-template <int POS, bool FIRST, bool PAIR, class Mid>
+template <int POS, bool FIRST, bool PAIR, bool F16, class Mid>
 __device__ __forceinline__ void rt_issue_tile(bool do_mid, Mid&& mid, uint32_t elected, uint64_t a_tile, uint64_t rb0, uint64_t rb1, uint32_t d_main,
                                               uint32_t d_new, uint32_t full0, uint32_t full1, uint32_t ph0, uint32_t ph1,
                                               uint32_t empty0, uint32_t empty1, uint32_t next_bar, uint32_t next_bar2, uint32_t next_par,
@@ -156,10 +162,10 @@ __device__ __forceinline__ void rt_issue_tile(bool do_mid, Mid&& mid, uint32_t e
       } else {
         const uint64_t bd = (i < 6 ? rb0 + (uint64_t)(i * kUnits) : rb1 + (uint64_t)((i - 6) * kUnits)) + (POS == 0 ? 64ull : 0ull);
         if (POS == 1 && i == 0) {
-          umma_bf16(d_main, ad, bd, rt_idesc(128), 1u);
-          umma_bf16(d_new, ad, bd + 128ull, rt_idesc(64), 0u);
+          umma_bf16(d_main, ad, bd, rt_idesc_fmt<F16>(128), 1u);
+          umma_bf16(d_new, ad, bd + 128ull, rt_idesc_fmt<F16>(64), 0u);
         } else {
-          umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc(192) : rt_idesc(128), (POS == 0 && i == 0) ? 0u : 1u);
+          umma_bf16(d_main, ad, bd, POS == 1 ? rt_idesc_fmt<F16>(192) : rt_idesc_fmt<F16>(128), (POS == 0 && i == 0) ? 0u : 1u);
         }
         if (POS == 2 && (i == 5 || i == NB - 1)) umma_commit_a(i < 6 ? empty0 : empty1);
       }
@@ -444,13 +450,13 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
           npar = par ^ 1u;
         }
         if (first) {
-          if (y == 0) rt_issue_tile<0, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
-          else if (y == H - 1) rt_issue_tile<2, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
-          else rt_issue_tile<1, true, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          if (y == 0) rt_issue_tile<0, true, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else if (y == H - 1) rt_issue_tile<2, true, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else rt_issue_tile<1, true, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
         } else {
-          if (y == 0) rt_issue_tile<0, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1, tr && gl < 100 ? trace + 5000 + gl * 6 : nullptr);
-          else if (y == H - 1) rt_issue_tile<2, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
-          else rt_issue_tile<1, false, PAIR>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          if (y == 0) rt_issue_tile<0, false, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1, tr && gl < 100 ? trace + 5000 + gl * 6 : nullptr);
+          else if (y == H - 1) rt_issue_tile<2, false, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
+          else rt_issue_tile<1, false, PAIR, K::kF16>(y == 1, mid, elected, a_tile, rb0t, rb1t, d_main, d_new, full0, full1, ph0, ph1, empty0, empty1, nb0, nb1, npar, fullp0, fullp1);
         }
         if (elected) {
           if (PAIR) umma_commit_pair_a(acc_a + 8u * (uint32_t)y);
@@ -512,8 +518,9 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         if (real && leaf < count) {
           const typename R::Board s = boards[leaf];
           const int wm = who[leaf];
-          const uint32_t mine = rules.plane_value(s, wm, 0, y, col) ? 0x3F80u : 0u;  // bf16(1.0)
-          const uint32_t other = rules.plane_value(s, wm, 1, y, col) ? 0x3F80u : 0u;
+          constexpr uint32_t kOne = K::kF16 ? 0x3C00u : 0x3F80u;  // 1.0 in fp16 / bf16
+          const uint32_t mine = rules.plane_value(s, wm, 0, y, col) ? kOne : 0u;
+          const uint32_t other = rules.plane_value(s, wm, 1, y, col) ? kOne : 0u;
           lo = mine | (other << 16);
         }
         uint8_t* dst = act + (size_t)(kRtHalo + y * 128 + row) * 16;
@@ -536,8 +543,10 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
       TMEM_LD16(a_acc, ra);
       if (CH == 32) TMEM_LD16(a_acc + 16u, (ra + CH - 16));
       if (HAS_RES) {
-        if (CH == 32) TMEM_LD8(a_lo, rl);
-        else TMEM_LD4(a_lo, rl);
+        if (!K::kF16) {
+          if (CH == 32) TMEM_LD8(a_lo, rl);
+          else TMEM_LD4(a_lo, rl);
+        }
 #pragma unroll
         for (int c8 = 0; c8 < C8N; ++c8) hv[c8] = *reinterpret_cast<const uint4*>(arow + (size_t)c8 * kRtChunkBytes);
       }
@@ -552,12 +561,17 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
         float2 m01 = make_float2(fmaxf(x01.x, t01.x), fmaxf(x01.y, t01.y));
         float2 m23 = make_float2(fmaxf(x23.x, t23.x), fmaxf(x23.y, t23.y));
         if (HAS_RES) {
-          float2 l01, l23;
-          e5m2x4_to_float(rl[q], l01, l23);
           const uint4 h4 = hv[q >> 1];
           const uint32_t w0 = (q & 1) ? h4.z : h4.x, w1 = (q & 1) ? h4.w : h4.y;
-          m01 = __fadd2_rn(m01, __fadd2_rn(bf16x2_to_float2(w0), l01));
-          m23 = __fadd2_rn(m23, __fadd2_rn(bf16x2_to_float2(w1), l23));
+          if (K::kF16) {
+            m01 = __fadd2_rn(m01, __half22float2(*reinterpret_cast<const __half2*>(&w0)));
+            m23 = __fadd2_rn(m23, __half22float2(*reinterpret_cast<const __half2*>(&w1)));
+          } else {
+            float2 l01, l23;
+            e5m2x4_to_float(rl[q], l01, l23);
+            m01 = __fadd2_rn(m01, __fadd2_rn(bf16x2_to_float2(w0), l01));
+            m23 = __fadd2_rn(m23, __fadd2_rn(bf16x2_to_float2(w1), l23));
+          }
         }
         v[q * 2] = m01;
         v[q * 2 + 1] = m23;
@@ -587,20 +601,27 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 vv = v[c8 * 4 + j];
-          const __nv_bfloat162 h = __floats2bfloat162_rn(vv.x, vv.y);
-          const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
-          packed[j] = real ? hw : 0u;
-          v[c8 * 4 + j] = __ffma2_rn(bf16x2_to_float2(hw), minus1, vv);  // lo part
+          if (K::kF16) {
+            const __half2 h = __floats2half2_rn(vv.x, vv.y);
+            packed[j] = real ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+          } else {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(vv.x, vv.y);
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+            packed[j] = real ? hw : 0u;
+            v[c8 * 4 + j] = __ffma2_rn(bf16x2_to_float2(hw), minus1, vv);  // lo part
+          }
         }
         *reinterpret_cast<uint4*>(arow + (size_t)c8 * kRtChunkBytes) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
-      uint32_t rl[QN];
+      if (!K::kF16) {
+        uint32_t rl[QN];
 #pragma unroll
-      for (int q = 0; q < QN; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
-      const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * QN);
-      if (CH == 32) TMEM_ST8(a_lo, rl);
-      else TMEM_ST4(a_lo, rl);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        for (int q = 0; q < QN; ++q) rl[q] = float_to_e5m2x4(v[q * 2], v[q * 2 + 1]);
+        const uint32_t a_lo = tmem_base + lane_base + kRtLoCol + (uint32_t)(y * 16 + cp * QN);
+        if (CH == 32) TMEM_ST8(a_lo, rl);
+        else TMEM_ST4(a_lo, rl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       fence_async_smem();
       tc_fence_before();
       act_arrive(y);
@@ -702,6 +723,24 @@ net_rt_kernel(R rules, RtGeom gm, const typename R::Board* __restrict__ boards, 
   }
 }
 
+// float -> IEEE half, round to nearest even (host side of the fp16 weight image)
+static uint16_t rt_f32_to_f16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t absu = u & 0x7fffffffu;
+  if (absu >= 0x7f800000u) return (uint16_t)(sign | (absu > 0x7f800000u ? 0x7e00u : 0x7c00u));  // NaN / inf
+  if (absu >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                                   // rounds to >= 65,520: inf
+  if (absu < 0x33000001u) return (uint16_t)sign;                                                // below half the smallest subnormal
+  int e = (int)(absu >> 23) - 127;
+  uint32_t m = (absu & 0x7fffffu) | 0x800000u;
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);  // bits of the 24-bit significand that do not fit
+  uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) ++q;
+  const uint32_t out = e >= -14 ? (((uint32_t)(e + 15) << 10) + (q - 0x400u)) : q;  // a carry out of the mantissa bumps the exponent
+  return (uint16_t)(sign | out);
+}
+
 static uint16_t rt_f32_to_bf16(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -722,10 +761,11 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
   const BlobLayout& L = net->layout;
   const int blocks = L.blocks;
   const size_t img_bytes = (size_t)(1 + 2 * blocks) * kRtRegionBlocks * kRtBlockBytes;
-  std::vector<uint16_t> img(img_bytes / 2, 0);
+  std::vector<uint16_t> img(img_bytes / 2, 0), himg(img_bytes / 2, 0);  // bf16 image, fp16 image (F16 mode)
   auto put = [&](int block, int j, int co, int c, float w) {
     const size_t off = (size_t)block * kRtBlockBytes + (size_t)(c / 8) * 3072 + (size_t)(j * 64 + co) * 16 + (size_t)(c % 8) * 2;
     img[off / 2] = rt_f32_to_bf16(w);
+    himg[off / 2] = rt_f32_to_f16(w);
   };
   for (int kx = 0; kx < 3; ++kx)
     for (int j = 0; j < 3; ++j)
@@ -781,6 +821,8 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
   cudaError_t ce = cudaSuccess;
   if (!net->d_rt_weights) ce = cudaMalloc(&net->d_rt_weights, img_bytes);  // the depth of a handle never changes (caro_net_update checks the blob size)
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_weights, img.data(), img_bytes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && !net->d_rt_f16_weights) ce = cudaMalloc(&net->d_rt_f16_weights, img_bytes);
+  if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_f16_weights, himg.data(), img_bytes, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess && !net->d_rt_pair_weights) ce = cudaMalloc(&net->d_rt_pair_weights, 2 * pair_bytes);
   if (ce == cudaSuccess) ce = cudaMemcpy(net->d_rt_pair_weights, pimg.data(), 2 * pair_bytes, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess && !net->d_rt_scratch)
@@ -792,6 +834,8 @@ int caro_net_rt_pack(caro_net* net, const float* h) {
 void caro_net_rt_free(caro_net* net) {
   if (net->d_rt_weights) cudaFree(net->d_rt_weights);
   if (net->d_rt_pair_weights) cudaFree(net->d_rt_pair_weights);
+  if (net->d_rt_f16_weights) cudaFree(net->d_rt_f16_weights);
+  net->d_rt_f16_weights = nullptr;
   if (net->d_rt_scratch) cudaFree(net->d_rt_scratch);
   net->d_rt_weights = nullptr;
   net->d_rt_pair_weights = nullptr;
@@ -802,6 +846,7 @@ bool caro_net_rt_supports(const caro_net* net) { return net->H >= 2 && net->H <=
 
 using RtK = RtCfg<CARO_RT_CP>;
 using RtKPair = RtCfg<2, true>;  // the pair form keeps two channel parts
+using RtKF16 = RtCfg<CARO_RT_CP, false, true>;
 
 // CARO_RT_PAIR=1/0 switches the CTA-pair form of the tower on / off (read once)
 static bool rt_pair_enabled() {
@@ -811,7 +856,8 @@ static bool rt_pair_enabled() {
 
 template <class R>
 static int launch_rt(const R& rules, caro_net* net, const void* boards, const uint8_t* who, const int32_t* d_count,
-                     int64_t max_count, float* probs, float* values, bool pair, cudaStream_t st) {
+                     int64_t max_count, float* probs, float* values, int mode, cudaStream_t st) {
+  const bool pair = mode == 1;  // mode: 0 = bf16, 1 = bf16 as CTA pairs, 2 = fp16
   RtGeom gm;
   gm.H = net->H;
   gm.W = net->W;
@@ -858,6 +904,14 @@ static int launch_rt(const R& rules, caro_net* net, const void* boards, const ui
     return caro_check_launch("net_rt_kernel (pair)");
   }
   const unsigned grid = (unsigned)(max_groups < ctas ? max_groups : ctas);
+  if (mode == 2) {
+    auto fkern = gm.H == 6 && !generic_env ? net_rt_kernel<R, RtKF16, 6> : net_rt_kernel<R, RtKF16, 0>;
+    fkern<<<grid, RtKF16::kThreads, RtKF16::kTotal, st>>>(
+        rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_f16_weights,
+        *reinterpret_cast<const RtConsts*>(net->h_rt_consts), net->d_blob, net->layout, net->d_pol_fc_t,
+        net->d_pol_fc_t + (size_t)2 * net->H * net->W * net->A, probs, values, (long long*)net->d_trace, nullptr);
+    return caro_check_launch("net_rt_kernel (fp16)");
+  }
   auto kern = gm.H == 6 && !generic_env ? net_rt_kernel<R, RtK, 6> : net_rt_kernel<R, RtK, 0>;
   kern<<<grid, RtK::kThreads, RtK::kTotal, st>>>(
       rules, gm, (const typename R::Board*)boards, who, d_count, (long long)max_count, (const uint8_t*)net->d_rt_weights,
@@ -875,6 +929,10 @@ int caro_net_rt_prepare() {
   set(net_rt_kernel<C4Rules, RtK, 6>, RtK::kTotal);
   set(net_rt_kernel<MnkRules, RtK, 0>, RtK::kTotal);
   set(net_rt_kernel<MnkRules, RtK, 6>, RtK::kTotal);
+  set(net_rt_kernel<C4Rules, RtKF16, 0>, RtKF16::kTotal);
+  set(net_rt_kernel<C4Rules, RtKF16, 6>, RtKF16::kTotal);
+  set(net_rt_kernel<MnkRules, RtKF16, 0>, RtKF16::kTotal);
+  set(net_rt_kernel<MnkRules, RtKF16, 6>, RtKF16::kTotal);
   set(net_rt_kernel<C4Rules, RtKPair, 0>, RtKPair::kTotal);
   set(net_rt_kernel<C4Rules, RtKPair, 6>, RtKPair::kTotal);
   set(net_rt_kernel<MnkRules, RtKPair, 0>, RtKPair::kTotal);
@@ -884,7 +942,7 @@ int caro_net_rt_prepare() {
 }
 
 int caro_net_rt_forward(caro_net* net, int game, int n, int k, const void* d_boards, const uint8_t* d_who,
-                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int pair, cudaStream_t st) {
-  if (game == CARO_GAME_CONNECT4) return launch_rt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, pair != 0, st);
-  return launch_rt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, pair != 0, st);
+                        const int32_t* d_count, int64_t max_count, float* d_probs, float* d_values, int mode, cudaStream_t st) {
+  if (game == CARO_GAME_CONNECT4) return launch_rt<C4Rules>(C4Rules(), net, d_boards, d_who, d_count, max_count, d_probs, d_values, mode, st);
+  return launch_rt<MnkRules>(MnkRules{n, k}, net, d_boards, d_who, d_count, max_count, d_probs, d_values, mode, st);
 }

@@ -39,6 +39,11 @@ __host__ __device__ constexpr uint32_t rt_idesc(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// operand format of the one-pass row-tiled tower: bf16 (a / b format fields = 1) or fp16 (fields = 0)
+template <bool F16>
+__host__ __device__ constexpr uint32_t rt_idesc_fmt(uint32_t n) {
+  return F16 ? ((1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24)) : rt_idesc(n);
+}
 // CTA-pair form (cta_group::2, net_rt.cu with PAIR): M = 256 = the 128 lanes of both CTAs, each CTA supplies half of B
 __host__ __device__ constexpr uint32_t rt_idesc_pair(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);

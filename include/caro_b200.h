@@ -123,6 +123,11 @@ int caro_net_set_grid_limit(caro_net* net, int ctas);
  *             5 = the row-tiled bf16 tower as CTA pairs (tcgen05 cta_group::2: clusters of two CTAs, each fetching half of
  *                 every B operand; bit-identical to impl 0, boards up to 6 x 7 only; measured slower than impl 0, kept for
  *                 A/B runs -- CARO_RT_PAIR=1 in the environment makes impl 0 use it),
+ *             7 = one-pass FP16 row-tiled tower (boards up to 6 x 7): activations and weights fp16, fp32 accumulate -- the same
+ *                 tcgen05 kind::f16 rate as bf16 with 11 instead of 8 mantissa bits on both operands, and the fp16 activations ARE
+ *                 the residual stream (no e5m2 tail): 3.7e-5 / 8.1e-5 off fp32 on random-init Connect4 networks (impl 0: 1.1e-4 /
+ *                 5.0e-4) and 8 % faster.  fp16's range is the caller's to check: the host mirror's precision="auto" measures
+ *                 impl 7, then impl 0 against impl 1 on the device after every weight upload and falls back to impl 2,
  *             6 = the tap-per-MMA bf16 tower as CTA pairs (each CTA stores 32 of the 64 output channels of every tap; bit-identical
  *                 to impl 3; no faster stand-alone -- an M = 128, K = 16 MMA takes 48 cycles whatever N <= 64 is --, +1.5 % inside the
  *                 Caro self-play step; CARO_TC_PAIR=1 makes impl 0 / 3 use it),

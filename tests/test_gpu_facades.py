@@ -345,14 +345,15 @@ def test_bench_engine_arm_prints_the_contract_line():
     assert d["metric"] == "connect4_mcts_leaf_evals_per_sec" and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 4
     assert d["engine_errors"] == 0 and d["gpu_launches"] >= 4 * 100 * 2 * 5  # noise, select, plan, tower, expand+backup per minibatch and part
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 512 * 17 <= d["e2e"]["d2h_bytes_per_step"]
-    assert d["net_precision"]["selected"] == "bf16" and d["net_precision"]["calibration"]["max_abs_prior_diff"] < 1e-3
+    assert d["net_precision"]["selected"] == "fp16" and d["net_precision"]["calibration"]["max_abs_prior_diff"] < 1e-3
+    assert d["bf16_same_workload"]["precision"] == "bf16" and d["bf16_same_workload"]["value"] > 0
     tr = d["extra"]["train"]
     assert tr["rounds"] == 20 and tr["sgd_ms_per_round"] > 0 and tr["gradient_bytes"] == 188301 * 4 and tr["allreduce_us"] is None
     for tag in ("connect4_4096_games", "connect4_4096_games_virtual_loss", "caro_15x15_1600_sims", "caro_15x15_1600_sims_deep10"):
         assert d["extra"]["configs"][tag]["leaf_evals_per_sec"] > 0 and d["extra"]["configs"][tag]["errors"] == 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and 0 < r["frac"] < 1.5 and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert "workload" in d["config"] and d["dtype"] == "bf16" and d["scaling"] == "weak"
+    assert "workload" in d["config"] and d["dtype"] == "f16" and d["scaling"] == "weak"
 
 
 def test_connect4_pipeline_matches_single_engine_play():

@@ -249,6 +249,41 @@ def test_net_tcgen05_matches_pytorch(torch_cuda):
         assert dp < 1e-3 and dv < 1e-3 and agree >= 0.99, (tag, dp, dv, agree)
 
 
+def test_net_tcgen05_fp16_one_pass_matches_pytorch(torch_cuda):
+    """One-pass FP16 row-tiled tower (impl 7: activations and weights fp16, fp32 accumulate, no residual tail) vs PyTorch
+    fp32 on every random-init network of the row-tiled towers' boards: 1e-3 on priors and values like the bf16 tower, and in
+    fact closer than it (11 instead of 8 mantissa bits on both operands); ragged counts; bit-identical from run to run."""
+    import torch
+    from caro_ai_b200.model import DeviceNet
+    rng = np.random.default_rng(5)
+    seen = 0
+    for tag, game, net in _net_cases():
+        if tag.endswith("-trained") or game.obs_shape[1] > 6 or game.obs_shape[2] > 7:
+            continue
+        dp7, dv7, agree = _net_errors(game, net, 7, rng)
+        dp0, dv0, _ = _net_errors(game, net, 0, rng)
+        assert dp7 < 1e-3 and dv7 < 1e-3 and agree >= 0.99, (tag, dp7, dv7, agree)
+        assert dv7 < dv0, (tag, dv7, dv0)
+        seen += 1
+    assert seen >= 2
+    from caro_ai_b200.game import ConnectFour
+    from harness import oracle_for, random_position
+    game = ConnectFour()
+    og = oracle_for(game)
+    dn = DeviceNet(_random_net(game), game, precision="fp16")
+    base = [random_position(og, rng, int(rng.integers(0, 30))) for _ in range(64)]
+    for count in (1, 15, 17, 1000, 4737):
+        pos = [base[i % len(base)] for i in range(count)]
+        a = dn.forward_states([p[0] for p in pos], [p[1] for p in pos])
+        b = dn.forward_states([p[0] for p in pos], [p[1] for p in pos])
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and bool(torch.isfinite(a[0]).all())
+        for i in range(0, count, len(base)):  # every copy of a position gets the same numbers, whatever its slot
+            m = min(len(base), count - i)
+            assert torch.equal(a[0][i:i + m], a[0][:m]) and torch.equal(a[1][i:i + m], a[1][:m])
+    dn.close()
+
+
 def test_net_tcgen05_x3_matches_pytorch_on_trained_checkpoints(torch_cuda):
     """"bf16x3" tensor-core tower (hi/lo split, 3 MMAs per product) vs PyTorch fp32: 1e-3 absolute on priors and values
     for EVERY test network including the shipped trained checkpoints (policy logits of +-100)."""

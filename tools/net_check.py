@@ -23,7 +23,7 @@ def main():
         states, players = [p[0] for p in pos], [p[1] for p in pos]
         ref_p, ref_v = T._reference_outputs(game, net, states, players)
         dn = DeviceNet(net, game)
-        for impl in (1, 0, 3, 2):
+        for impl in (1, 0, 7, 3, 2):
             try:
                 p, v = dn.forward_states(states, players, impl=impl)
                 torch.cuda.synchronize()
