@@ -563,7 +563,8 @@ def engine_arm(args):
             "gpu_launches": int(prof["launches"]) + int(graph_launches),
             "roofline": {"kernel": "net_rt_kernel (row-tiled tcgen05 residual tower)", "bound": "tensor", "achieved": achieved_tflops,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops_sustained"],
-                         "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "traffic": traffic, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step; the dense bf16 figure -- fp16 and "
+                                        "bf16 operands run the same tcgen05 kind::f16 instruction at the same rate)",
                          "note": "average CUDA-event time per tower launch over the evented plies of the timed region (the other timed "
                                  "plies replay a CUDA graph, where events cannot be recorded); the parts' towers run on their own streams "
                                  "and overlap tail-to-head, so `achieved` is a lower bound (stand-alone: tools/net_bench.py, DESIGN.md "
