@@ -30,8 +30,11 @@
 //
 // What bounds it (round 2): the EPILOGUE CHAIN -- the same eight warps rewrite the six tiles of a layer
 // back to back, ~1,050 cycles of work (344 SASS instructions per thread) + ~230 cycles of barrier / fence / loop per tile =
-// ~7,660 cycles per layer against a tensor floor of 6,144, with the MMA warp far ahead.  Two template switches:
+// ~7,660 cycles per layer against a tensor floor of 6,144, with the MMA warp far ahead (bf16 form).  Three template switches:
 //   HC    the board height as a compile-time constant (6): the MMA warp's tile loop unrolled, every position test folded;
+//   F16   fp16 instead of bf16 operands (weights packed as fp16 too): the activations carry 11 mantissa bits by themselves and ARE
+//         the residual stream -- no e5m2 tail, 40 % fewer epilogue instructions: +8 %, MMA-bound at 99 % of the sustained cuBLAS
+//         rate, and 3-6x closer to fp32.  impl 7; what precision="auto" picks whenever its device check passes;
 //   PAIR  two CTAs of a cluster run ONE cta_group::2 MMA stream (M = 256, each CTA stores and fetches half of every B
 //         operand: 30 % fewer operand wavefronts, half the bank conflicts, bit-identical results) -- 7 % slower, because the
 //         pair couples two epilogue chains and shared memory was not the limit; kept as impl 5 / CARO_RT_PAIR=1 for A/B runs.
